@@ -1,0 +1,224 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json from the UNMODIFIED reference compiled here
+(oracle/_ref, see oracle/Makefile).  Run in the build container only -- the GPU
+box has no /root/reference; the committed fixtures travel instead.
+
+    python oracle/make_golden.py
+
+Every value below is produced by the reference's own code (ntHashIterator,
+ntRead/ntComp, compEst, and the ntcard_ref CLI); the oracle restatement and the
+CUDA path are both tested against these files.
+"""
+import json
+import os
+import random
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.pyoracle import Oracle, Reference, REF_CLI, build  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def rand_seq(rng, L, alphabet=b"ACGT", junk=0.0, junk_chars=b"NnXRY-.*"):
+    out = bytearray()
+    for _ in range(L):
+        if junk and rng.random() < junk:
+            out.append(rng.choice(junk_chars))
+        else:
+            out.append(rng.choice(alphabet))
+    return bytes(out)
+
+
+def main():
+    build(ref=True)
+    os.makedirs(GOLD, exist_ok=True)
+    ref = Reference()
+    orc = Oracle()  # used ONLY for its read generator (ours, not the reference's)
+
+    # ---- 1. ntHash vectors ---------------------------------------------------
+    rng = random.Random(20261017)
+    seqs = [
+        b"ACGTACACTGGACTGAGTCT",
+        b"AGACTCAGTCCAGTGTACGT",
+        b"GAGTGTCAAACATTCAGACAACAGCAGGGGTGCTCTGGAATCCTATGTGAGGAACAAACATTCAGGCCACAGTAG",
+        b"ACGTNACGTACGTTTGA",
+        b"acgtacactggactgagtct",
+        b"ACGUACACUGGACUGAGUCU",
+        b"NNNNNNNNNN",
+        b"ACGT",
+        b"",
+        b"ACGTACGTACGTNACGTACGTACGTNNACGTACGTACGTACGTACGTACGT",
+    ]
+    for L in (40, 150, 151, 300, 1000):
+        seqs.append(rand_seq(rng, L))
+        seqs.append(rand_seq(rng, L, alphabet=b"ACGTacgtUu", junk=0.03))
+    vec = []
+    for s in seqs:
+        for k in (1, 4, 12, 18, 20, 31, 32, 33, 64, 70, 96, 128):
+            h, p = ref.hash_seq(s, k)
+            x = 0
+            for v in h:
+                x ^= int(v)
+            vec.append({
+                "seq": s.decode("latin1"), "k": k, "n": int(len(h)),
+                "pos_first": int(p[0]) if len(p) else -1, "pos_last": int(p[-1]) if len(p) else -1,
+                "pos_sum": int(np.sum(p.astype(np.uint64))),
+                "first": f"{int(h[0]):#018x}" if len(h) else None,
+                "last": f"{int(h[-1]):#018x}" if len(h) else None,
+                "xor": f"{x:#018x}",
+                "hashes": [f"{int(v):#018x}" for v in h] if len(s) <= 80 else None,
+                "pos": [int(v) for v in p] if len(s) <= 80 else None,
+            })
+    kmer = b"ACGTACACTGGACTGAGTCT"
+    fh, rh = ref.kmer_hashes(kmer)
+    mst = {str(k): {chr(c): f"{ref.mstab(c, k):#018x}" for c in b"ACGT"} for k in
+           (1, 2, 12, 30, 31, 32, 33, 34, 62, 63, 64, 65, 66, 96, 100, 127, 128, 200, 250, 1023, 1024)}
+    with open(os.path.join(GOLD, "nthash_vectors.json"), "w") as f:
+        json.dump({"source": "vendor/ntHash ntHashIterator / NTF64 / NTR64 / msTab via oracle/_ref",
+                   "unit_test_kmer": {"seq": kmer.decode(), "fh": f"{fh:#018x}", "rh": f"{rh:#018x}"},
+                   "srol_k_of_seed": mst, "vectors": vec}, f, indent=0)
+
+    # ---- 2. sketches (ntRead/ntComp) on seeded inputs ------------------------
+    sk_cases = []
+
+    def sketch_case(name, reads, kList, rBits, sBits, keep_full=False):
+        sk, tot = ref.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+        rB = 1 << rBits
+        tabs = []
+        for ki in range(len(kList)):
+            for t in range(2):
+                tab = sk[(ki * 2 + t) * rB:(ki * 2 + t + 1) * rB]
+                d = orc.table_digest(np.ascontiguousarray(tab))
+                d["digest"] = f"{d['digest']:#018x}"
+                if d["nnz"] == 0:
+                    d["first"] = -1
+                if keep_full:
+                    nz = np.nonzero(tab)[0]
+                    d["nonzero"] = [[int(i), int(tab[i])] for i in nz]
+                tabs.append(d)
+        # estimator on the same sketch (full recurrence), rows 1..64 kept
+        est = []
+        for ki in range(len(kList)):
+            F0, fm = ref.compest(np.ascontiguousarray(sk[ki * 2 * rB:(ki + 1) * 2 * rB]), rBits, sBits)
+            est.append({"F0": float(F0), "f": [float(x) for x in fm[1:65]]})
+        return {"name": name, "k": list(kList), "rBits": rBits, "sBits": sBits,
+                "F1": [int(x) for x in tot], "tables": tabs, "est": est}
+
+    def gen(S, n, L, mode=0, U=0):
+        a = orc.gen_reads(S, 0, n, L, mode, U)
+        return [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+
+    # FX1 of SURVEY 8c: seed 1, L 150, n 200000, U 25000 (repeat mode), s=7, r=27
+    fx1 = gen(1, 200000, 150, 1, 25000)
+    c = sketch_case("FX1", fx1, [12, 31, 32, 64], 27, 7)
+    c["gen"] = {"S": 1, "n": 200000, "L": 150, "mode": 1, "U": 25000}
+    sk_cases.append(c)
+    # small table, many collisions; s=3 so that plenty is sampled
+    c = sketch_case("small_r12_s3", gen(7, 2000, 100, 1, 500), [12, 32], 12, 3, keep_full=False)
+    c["gen"] = {"S": 7, "n": 2000, "L": 100, "mode": 1, "U": 500}
+    sk_cases.append(c)
+    # Ns (mode 2), s=11 / s=7
+    for s in (7, 11):
+        c = sketch_case(f"nmode_s{s}", gen(4, 3000, 400, 2, 0), [31, 64], 20, s)
+        c["gen"] = {"S": 4, "n": 3000, "L": 400, "mode": 2, "U": 0}
+        sk_cases.append(c)
+    # counter wrap: one k-mer-rich read repeated 70000 times must wrap mod 65536
+    # (uint16 ++, ntcard.cpp:133,143).  s=1 so everything with top bit 0 is sampled.
+    wrap_read = gen(9, 1, 40, 0, 0)[0]
+    c = sketch_case("wrap_u16", [wrap_read] * 70000, [32], 10, 1, keep_full=True)
+    c["gen"] = {"S": 9, "n": 1, "L": 40, "mode": 0, "U": 0, "repeat": 70000}
+    sk_cases.append(c)
+    # ragged lengths incl. shorter than k and empty
+    rr = random.Random(5)
+    ragged = [rand_seq(rr, rr.choice((0, 1, 5, 11, 12, 13, 31, 32, 33, 63, 64, 65, 100, 150, 250, 1000)),
+                       alphabet=b"ACGT", junk=0.01) for _ in range(1500)]
+    c = sketch_case("ragged_r16_s2", ragged, [12, 32, 64], 16, 2)
+    c["reads"] = [r.decode("latin1") for r in ragged]
+    sk_cases.append(c)
+    with open(os.path.join(GOLD, "sketch_cases.json"), "w") as f:
+        json.dump({"source": "ntRead/ntComp/compEst of ntcard.cpp via oracle/_ref; reads from the SURVEY 8d generator",
+                   "digest": "FNV-1a-64 over (idx,count) of nonzero buckets in index order",
+                   "cases": sk_cases}, f, indent=0)
+
+    # ---- 3. compEst on synthetic counter-value histograms ---------------------
+    est_cases = []
+    rs = np.random.RandomState(3)
+    for rBits, sBits, lam in ((20, 7, 0.02), (16, 3, 0.3), (18, 11, 1.5)):
+        rB = 1 << rBits
+        sk = np.minimum(rs.poisson(lam, size=2 * rB) * rs.randint(1, 9, size=2 * rB), 65535).astype(np.uint16)
+        F0, fm = ref.compest(sk, rBits, sBits)
+        p = np.stack([np.bincount(sk[:rB], minlength=65536), np.bincount(sk[rB:], minlength=65536)]).astype(np.uint32)
+        nzp = [[int(t), int(i), int(p[t, i])] for t in range(2) for i in np.nonzero(p[t])[0]]
+        est_cases.append({"rBits": rBits, "sBits": sBits, "p_hist_nonzero": nzp, "F0": float(F0),
+                          "f": [float(x) for x in fm[1:1001]]})
+    # empty sketch early-out (ntcard.cpp:262-264)
+    sk = np.zeros(2 << 12, dtype=np.uint16)
+    F0, fm = ref.compest(sk, 12, 7)
+    est_cases.append({"rBits": 12, "sBits": 7, "p_hist_nonzero": [[0, 0, 4096], [1, 0, 4096]], "F0": float(F0),
+                      "f": [float(x) for x in fm[1:1001]]})
+    with open(os.path.join(GOLD, "compest_cases.json"), "w") as f:
+        json.dump({"source": "compEst of ntcard.cpp:237-275 via oracle/_ref", "cases": est_cases}, f, indent=0)
+
+    # ---- 4. the unmodified CLI on small files (formats + .hist layout) --------
+    cli = {}
+    with tempfile.TemporaryDirectory() as td:
+        reads = gen(1, 20000, 150, 1, 2500)
+        nreads = gen(4, 2000, 400, 2, 0)
+        fq = os.path.join(td, "a.fq")
+        with open(fq, "w") as f:
+            for i, r in enumerate(reads):
+                f.write(f"@r{i}\n{r.decode()}\n+\n{'I' * len(r)}\n")
+        fa = os.path.join(td, "a.fa")
+        with open(fa, "w") as f:
+            for i, r in enumerate(reads):
+                s = r.decode()
+                f.write(f">r{i}\n" + "\n".join(s[j:j + 60] for j in range(0, len(s), 60)) + "\n")
+        sam = os.path.join(td, "a.sam")
+        with open(sam, "w") as f:
+            f.write("@HD\tVN:1.6\n@SQ\tSN:x\tLN:100\n")
+            for i, r in enumerate(reads):
+                f.write(f"r{i}\t4\t*\t0\t0\t*\t*\t0\t0\t{r.decode()}\t{'I' * len(r)}\n")
+        fqn = os.path.join(td, "n.fq")
+        with open(fqn, "w") as f:
+            for i, r in enumerate(nreads):
+                f.write(f"@r{i}\n{r.decode()}\n+\n{'I' * len(r)}\n")
+
+        def run(args, files):
+            pref = os.path.join(td, "out")
+            p = subprocess.run([REF_CLI] + args + ["-p", pref] + files, capture_output=True, text=True, check=True)
+            outs = {}
+            for fn in sorted(os.listdir(td)):
+                if fn.startswith("out_k") and fn.endswith(".hist"):
+                    with open(os.path.join(td, fn)) as f:
+                        outs[fn[4:]] = f.read()
+                    os.remove(os.path.join(td, fn))
+            return outs
+
+        cli["gen_a"] = {"S": 1, "n": 20000, "L": 150, "mode": 1, "U": 2500}
+        cli["gen_n"] = {"S": 4, "n": 2000, "L": 400, "mode": 2, "U": 0}
+        cli["fq_k12_k32_c50"] = run(["-k12,32", "-c50"], [fq])
+        cli["fa_k12_k32_c50"] = run(["-k12,32", "-c50"], [fa])
+        cli["sam_k12_k32_c50"] = run(["-k12,32", "-c50"], [sam])
+        cli["nfq_k31_c20"] = run(["-k31", "-c20"], [fqn])
+        cli["two_files_t2_k64_c20"] = run(["-k64", "-c20", "-t2"], [fq, fqn])
+        # compact output (-o): file + stderr lines
+        o = os.path.join(td, "compact.tsv")
+        p = subprocess.run([REF_CLI, "-k12,64", "-c8", "-o", o, fq], capture_output=True, text=True, check=True)
+        with open(o) as f:
+            cli["compact_k12_k64_c8"] = {"file": f.read(),
+                                         "stderr": "".join(l + "\n" for l in p.stderr.splitlines() if not l.startswith("Runtime"))}
+    with open(os.path.join(GOLD, "cli_cases.json"), "w") as f:
+        json.dump({"source": "unmodified ntcard CLI (oracle/_ref/ntcard_ref); inputs written by this script from the SURVEY 8d generator",
+                   "cases": cli}, f, indent=0)
+    for fn in sorted(os.listdir(GOLD)):
+        print(fn, os.path.getsize(os.path.join(GOLD, fn)))
+
+
+if __name__ == "__main__":
+    main()
