@@ -1,0 +1,45 @@
+# Builds the product: ntcard_b200/libntcard_b200.so (C-ABI + sm_100a kernels) and bin/ntcard (host CLI).
+# The checkers under oracle/ have their own Makefile.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX = g++
+ARCH = -gencode arch=compute_100a,code=sm_100a
+NVFLAGS = -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v --expt-relaxed-constexpr
+CXXFLAGS = -O3 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off
+SRC = ntcard_b200/csrc
+BUILD = build
+
+CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(wildcard $(SRC)/bitslice_kernel.cu)
+CPP_SRCS = $(SRC)/host_util.cpp
+CU_OBJS = $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS))
+CPP_OBJS = $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS))
+HDRS = $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)
+LIB = ntcard_b200/libntcard_b200.so
+CLI_SRCS = $(wildcard $(SRC)/cli/*.cpp)
+
+all: $(LIB) cli
+
+$(BUILD)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
+	@grep -E "error|warning|spill|registers" $(BUILD)/$*.ptxas.log | grep -v "0 bytes spill" | head -40 || true
+
+$(BUILD)/%.o: $(SRC)/%.cpp $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(CPP_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -Xlinker --exclude-libs,ALL
+
+ifneq ($(CLI_SRCS),)
+cli: bin/ntcard
+bin/ntcard: $(CLI_SRCS) $(LIB) $(HDRS)
+	@mkdir -p bin
+	$(CXX) $(CXXFLAGS) -fopenmp -Iinclude -o $@ $(CLI_SRCS) -Lntcard_b200 -lntcard_b200 -Wl,-rpath,'$$ORIGIN/../ntcard_b200' -lpthread
+else
+cli:
+endif
+
+clean:
+	rm -rf $(BUILD) $(LIB) bin
+
+.PHONY: all cli clean

@@ -1,0 +1,164 @@
+/*
+ * ntcard_b200.h -- C-ABI of the B200-native ntCard sketch path.
+ *
+ * The reference (bcgsc/ntCard v1.2.2) has no plugin / FFI layer; the seam this
+ * library replaces is the FUNCTION boundary between its readers and its sketch:
+ *
+ *   ntRead(const string& seq, const vector<unsigned>& kList,
+ *          uint16_t* t_Counter, size_t totKmer[])          ntcard.cpp:147-158
+ *      called once per sequence by getEfq/getEfa/getEsm    ntcard.cpp:182,203,230
+ *   ntComp(hVal, t_Counter)                                 ntcard.cpp:132-145
+ *   t_Counter = new uint16_t[nK * nSamp * rBuck]()          ntcard.cpp:437-439
+ *   totalKmers[k] += totKmer[k]                             ntcard.cpp:464-466
+ *   compEst(const uint16_t* t_Counter, double& F0Mean,
+ *           double fMean[])                                 ntcard.cpp:237-275
+ *
+ * A device call per read is meaningless, so the boundary is batch oriented:
+ * the host parses reads, splits them at non-ACGTU characters (a window is hashed
+ * iff all k chars are valid: ntHashIterator.hpp:66-67,80-83), 2-bit packs the
+ * segments into a length-prefixed record stream, and submits batches.  The
+ * device rolls canonical ntHash (NTC64, nthash.hpp:242-279) over every k-mer of
+ * every record for every k, samples (ntComp) and increments the sketch.
+ *
+ * All entry points return 0 on success or a negative NTC_E* code;
+ * ntc_last_error() gives the message (thread local).  There is NO CPU fallback:
+ * every compute entry point fails with NTC_ENODEVICE when no CUDA device is
+ * usable.  Plain pointers and sizes only -- no C++ or torch types.
+ */
+#ifndef NTCARD_B200_H
+#define NTCARD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTC_OK 0
+#define NTC_EINVAL (-1)    /* bad argument */
+#define NTC_ENODEVICE (-2) /* no usable CUDA device / driver */
+#define NTC_ECUDA (-3)     /* a CUDA call failed; see ntc_last_error() */
+#define NTC_ENOMEM (-4)
+#define NTC_ESTATE (-5)    /* call not valid in this state */
+
+#define NTC_MAX_K 16       /* distinct k values per context */
+#define NTC_NSAMP 2        /* opt::nSamp, ntcard.cpp:61 */
+
+typedef struct ntc_ctx ntc_ctx;
+
+/* ---- packed record stream -----------------------------------------------------
+ * A batch is an array of 32-bit little-endian words.  Record i occupies words
+ * [off[i], off[i+1]):
+ *     word 0      : len  = number of bases (all valid: A C G T/U, either case)
+ *     words 1..   : ceil(len/16) words, base j in bits [2(j%16), 2(j%16)+1] of
+ *                   word 1 + j/16;  A=0 C=1 G=2 T/U=3 (complement = 3 - code)
+ *     padding     : zero words up to off[i+1] (optional)
+ * off == NULL means every record has the same word count `stride_words`
+ * (off[i] = i * stride_words); stride_words % 4 == 0 enables the TMA path.
+ * Algorithmic bytes per record = 4 + ceil(len/4)   (SURVEY.md 8d).            */
+
+/* kernel selection for ntc_set_kernel(): */
+#define NTC_KERNEL_AUTO 0
+#define NTC_KERNEL_ROLL64 1   /* general: one thread per piece, 64-bit recurrence */
+#define NTC_KERNEL_BITSLICE 2 /* 32 records bit-sliced per lane, upper-ring filter */
+
+/* Create a context on CUDA device `device` for k values kList[0..nK) with a
+ * sketch of NTC_NSAMP x 2^rBits counters per k, sampling on sBits leading bits
+ * (opt::rBits / opt::sBits, ntcard.cpp:57-58; the caller applies the "sBits = 7
+ * below 50 GB" rule of ntcard.cpp:430-431).  Replaces ntcard.cpp:437-439.
+ * d_counters: optional caller-owned DEVICE buffer of nK*2*2^rBits uint32 (zeroed
+ * by this call), e.g. a torch tensor that torch.distributed will all-reduce;
+ * NULL lets the context allocate it.  cuda_stream: optional cudaStream_t on
+ * which all device work is ordered (NULL = the context creates its own). */
+int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits, unsigned sBits, int device,
+    void* d_counters, void* cuda_stream);
+void ntc_destroy(ntc_ctx* ctx);
+
+/* Zero the sketch and the k-mer totals (a fresh `new uint16_t[...]()`). */
+int ntc_reset(ntc_ctx* ctx);
+int ntc_set_kernel(ntc_ctx* ctx, int kernel);
+
+/* Submit one batch held in HOST memory (replaces n_rec calls of ntRead,
+ * ntcard.cpp:182/203/230).  Pageable memory is copied to internal pinned
+ * staging before the call returns.  Memory from ntc_host_alloc() is copied by
+ * DMA directly and must stay untouched until ntc_wait(ticket) / ntc_sync().
+ * Asynchronous; thread-compatible (one submitting thread per context).
+ * *ticket (optional) identifies the batch for ntc_wait(). */
+int ntc_submit(ntc_ctx* ctx, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec,
+    uint32_t stride_words, uint64_t* ticket);
+/* Same, for a batch already resident in DEVICE memory (synthetic generator,
+ * device-side producers).  The buffers must stay valid until ntc_sync(). */
+int ntc_submit_device(ntc_ctx* ctx, const uint32_t* d_words, size_t n_words, const uint32_t* d_off, size_t n_rec,
+    uint32_t stride_words);
+int ntc_wait(ntc_ctx* ctx, uint64_t ticket); /* host buffer of that batch is reusable */
+int ntc_sync(ntc_ctx* ctx);                  /* all submitted work has finished */
+
+/* Multi-GPU plumbing: the device counters (uint32, [nK][2][2^rBits]; summed
+ * across ranks by the caller's collective, then narrowed mod 2^16 by
+ * ntc_finish) and the per-k totals (F1). */
+int ntc_counters_device(ntc_ctx* ctx, void** d_counters, size_t* n_counters);
+int ntc_totals(ntc_ctx* ctx, uint64_t* totKmer /* [nK] */); /* syncs */
+int ntc_set_totals(ntc_ctx* ctx, const uint64_t* totKmer);  /* after an all-reduce of F1 */
+
+/* Finish: wait for the device, narrow counters mod 2^16 (the reference's
+ * uint16_t ++ wraps, ntcard.cpp:133,143) and return
+ *   t_Counter : [nK][2][2^rBits] uint16, host, caller-owned, may be NULL
+ *   totKmer   : [nK] = F1 (ntcard.cpp:155,466)
+ *   p_hist    : [nK][2][65536] uint32 counter-value histogram computed on the
+ *               device (ntcard.cpp:245-247), may be NULL. */
+int ntc_finish(ntc_ctx* ctx, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_hist);
+
+/* Estimator, host side, plain double arithmetic in the reference's order
+ * (compEst, ntcard.cpp:237-275), truncated at covMax (rows 1..covMax are
+ * bit-identical to the untruncated recurrence).  Exactly one of p_hist
+ * ([2][65536]) / t_Counter ([2][2^rBits]) is non-NULL.  f has covMax+1 entries;
+ * f[0] = 0.  No device needed. */
+int ntc_estimate(const uint32_t* p_hist, const uint16_t* t_Counter, unsigned rBits, unsigned sBits, unsigned covMax,
+    double* F0, double* f);
+
+/* ---- host helpers ----------------------------------------------------------- */
+/* Pinned host memory for zero-copy submission. */
+void* ntc_host_alloc(size_t bytes);
+void ntc_host_free(void* p);
+
+/* Upper bound of words produced by ntc_pack_seqs for `n_seq` sequences holding
+ * `total_bases` characters in total. */
+size_t ntc_pack_bound(size_t n_seq, size_t total_bases);
+/* Split each sequence seq[i] = chars[seq_off[i] .. seq_off[i+1]) at characters
+ * outside ACGTUacgtu, drop segments shorter than min_len, 2-bit pack the rest
+ * as records.  Appends to words[*n_words..] / off[*n_rec..] (off gets
+ * *n_rec+1 valid entries; off may be NULL).  Returns 0 or NTC_ENOMEM if
+ * cap_words / cap_rec would be exceeded (nothing of the failing sequence is
+ * kept; *consumed tells how many sequences were packed). */
+int ntc_pack_seqs(const char* chars, const uint64_t* seq_off, size_t n_seq, uint32_t min_len, uint32_t* words,
+    size_t cap_words, size_t* n_words, uint32_t* off, size_t cap_rec, size_t* n_rec, size_t* consumed);
+
+/* Deterministic synthetic reads (mix64 generator).  mode 0:
+ * uniform; mode 1: read i = gen(i mod U), reverse-complemented when (i/U) is
+ * odd; mode 2: uniform with N runs (ASCII output only).
+ * ntc_gen_ascii writes n*L characters; ntc_gen_packed writes n records of
+ * stride_words words each (mode 0/1); ntc_gen_packed_device does the same on
+ * the device, ordered on the context's stream (mode 0/1). */
+int ntc_gen_ascii(uint64_t seed, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U, char* out);
+int ntc_gen_packed(uint64_t seed, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U, uint32_t stride_words,
+    uint32_t* words);
+int ntc_gen_packed_device(ntc_ctx* ctx, uint64_t seed, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U,
+    uint32_t stride_words, uint32_t* d_words);
+uint32_t ntc_stride_words(uint32_t L, int align4); /* 1 + ceil(L/16), rounded up to 4 if align4 */
+
+/* ---- introspection ----------------------------------------------------------- */
+/* Counters for bench.py / tests: kernel launches issued by this context since
+ * creation, and k-mers hashed as counted on the device. */
+int ntc_stats(ntc_ctx* ctx, uint64_t* n_launches, uint64_t* n_batches);
+/* Milliseconds the sketch kernels of the last ntc_sync()-ed batches took on the
+ * device (CUDA events on the context's stream), and how many launches. */
+int ntc_kernel_time(ntc_ctx* ctx, double* ms_total, uint64_t* n_timed);
+int ntc_device_count(void);
+const char* ntc_last_error(void);
+const char* ntc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTCARD_B200_H */

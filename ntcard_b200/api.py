@@ -1,0 +1,287 @@
+"""ctypes binding of libntcard_b200.so (include/ntcard_b200.h) -- the host-side mirror of the
+reference's ntRead / ntComp / compEst boundary (ntcard.cpp:132-158, 237-275).
+
+There is no Python or CPU implementation of the hot path in this package: if the CUDA library is
+missing, importing this module raises; if no B200 is visible, `Sketch(...)` raises NtcError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libntcard_b200.so")
+
+NTC_OK, NTC_EINVAL, NTC_ENODEVICE, NTC_ECUDA, NTC_ENOMEM, NTC_ESTATE = 0, -1, -2, -3, -4, -5
+NTC_MAX_K = 16
+KERNEL_AUTO, KERNEL_ROLL64, KERNEL_BITSLICE = 0, 1, 2
+
+# every symbol include/ntcard_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_submit", "ntc_submit_device", "ntc_wait",
+    "ntc_sync", "ntc_counters_device", "ntc_totals", "ntc_set_totals", "ntc_finish", "ntc_estimate",
+    "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
+    "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_device_count",
+    "ntc_last_error", "ntc_version",
+]
+
+
+class NtcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ntcard_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` or `make` "
+            "at the repository root. ntcard_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32p, u64p, u16p, dblp = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint16), C.POINTER(C.c_double)
+    sig = {
+        "ntc_create": (C.c_int, [C.POINTER(vp), u32p, C.c_uint, C.c_uint, C.c_uint, C.c_int, vp, vp]),
+        "ntc_destroy": (None, [vp]),
+        "ntc_reset": (C.c_int, [vp]),
+        "ntc_set_kernel": (C.c_int, [vp, C.c_int]),
+        "ntc_submit": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, u64p]),
+        "ntc_submit_device": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]),
+        "ntc_wait": (C.c_int, [vp, C.c_uint64]),
+        "ntc_sync": (C.c_int, [vp]),
+        "ntc_counters_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "ntc_totals": (C.c_int, [vp, u64p]),
+        "ntc_set_totals": (C.c_int, [vp, u64p]),
+        "ntc_finish": (C.c_int, [vp, vp, u64p, vp]),
+        "ntc_estimate": (C.c_int, [vp, vp, C.c_uint, C.c_uint, C.c_uint, dblp, dblp]),
+        "ntc_host_alloc": (vp, [C.c_size_t]),
+        "ntc_host_free": (None, [vp]),
+        "ntc_pack_bound": (C.c_size_t, [C.c_size_t, C.c_size_t]),
+        "ntc_pack_seqs": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t), vp,
+                                    C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+        "ntc_gen_ascii": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint64, vp]),
+        "ntc_gen_packed": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint64, C.c_uint32, vp]),
+        "ntc_gen_packed_device": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint64,
+                                            C.c_uint32, vp]),
+        "ntc_stride_words": (C.c_uint32, [C.c_uint32, C.c_int]),
+        "ntc_stats": (C.c_int, [vp, u64p, u64p]),
+        "ntc_kernel_time": (C.c_int, [vp, dblp, u64p]),
+        "ntc_device_count": (C.c_int, []),
+        "ntc_last_error": (C.c_char_p, []),
+        "ntc_version": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc):
+    if rc != NTC_OK:
+        raise NtcError(rc, lib.ntc_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    return lib.ntc_device_count()
+
+
+def stride_words(L, align4=True):
+    return lib.ntc_stride_words(L, 1 if align4 else 0)
+
+
+def apply_sbits_rule(total_input_bytes, sBits=11):
+    """ntcard.cpp:427-431: sBits is forced to 7 when the input files total < 50 GB."""
+    return 7 if total_input_bytes < 50000000000 else sBits
+
+
+# ---- host helpers -------------------------------------------------------------------------------
+def pack_reads(reads, min_len=1):
+    """Split each read (bytes) at characters outside ACGTUacgtu and 2-bit pack the segments.
+    Returns (words uint32[n_words], off uint32[n_rec+1])."""
+    lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
+    soff = np.zeros(len(reads) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=soff[1:])
+    chars = np.frombuffer(b"".join(reads) + b"\0", dtype=np.uint8)
+    return pack_chars(chars, soff, min_len)
+
+
+def pack_chars(chars, seq_off, min_len=1):
+    """chars: uint8 array of concatenated sequences; seq_off: uint64[n+1]."""
+    chars = np.ascontiguousarray(chars, dtype=np.uint8)
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    n = len(seq_off) - 1
+    total = int(seq_off[-1])
+    cap_w = lib.ntc_pack_bound(n, total)
+    cap_r = n + total // 2 + 2
+    words = np.empty(cap_w, dtype=np.uint32)
+    off = np.empty(cap_r + 1, dtype=np.uint32)
+    nw, nr, cons = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    _check(lib.ntc_pack_seqs(chars.ctypes.data, seq_off.ctypes.data_as(C.POINTER(C.c_uint64)), n, min_len,
+                             words.ctypes.data, cap_w, C.byref(nw), off.ctypes.data, cap_r, C.byref(nr), C.byref(cons)))
+    return words[:nw.value].copy(), off[:nr.value + 1].copy()
+
+
+def gen_ascii(seed, first, n, L, mode=0, U=0):
+    out = np.empty(n * L, dtype=np.uint8)
+    _check(lib.ntc_gen_ascii(seed, first, n, L, mode, U, out.ctypes.data))
+    return out
+
+
+def gen_packed(seed, first, n, L, mode=0, U=0, stride=None, out=None):
+    stride = stride or stride_words(L)
+    if out is None:
+        out = np.empty(n * stride, dtype=np.uint32)
+    _check(lib.ntc_gen_packed(seed, first, n, L, mode, U, stride, out.ctypes.data))
+    return out
+
+
+def estimate(p_hist=None, t_counter=None, rBits=27, sBits=7, covMax=1000):
+    """compEst (ntcard.cpp:237-275).  Returns (F0, f[0..covMax]) with f[0] = 0."""
+    F0 = C.c_double()
+    covMax = min(covMax, 65535)
+    f = np.zeros(covMax + 1, dtype=np.float64)
+    p = np.ascontiguousarray(p_hist, dtype=np.uint32).ctypes.data if p_hist is not None else None
+    t = np.ascontiguousarray(t_counter, dtype=np.uint16).ctypes.data if t_counter is not None else None
+    _check(lib.ntc_estimate(p, t, rBits, sBits, covMax, C.byref(F0), f.ctypes.data_as(C.POINTER(C.c_double))))
+    return F0.value, f
+
+
+class PinnedBuffer:
+    """Pinned host memory from ntc_host_alloc, viewed as a numpy uint32 array."""
+
+    def __init__(self, n_words):
+        self.ptr = lib.ntc_host_alloc(n_words * 4)
+        if not self.ptr:
+            raise NtcError(NTC_ENOMEM, lib.ntc_last_error().decode())
+        self.n_words = n_words
+        self.array = np.ctypeslib.as_array((C.c_uint32 * n_words).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib.ntc_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Sketch:
+    """One ntCard sketch on one GPU: the reference's t_Counter + totalKmers for a k list.
+
+    sketch = Sketch([32], rBits=27, sBits=7)       # ntcard.cpp:437-439
+    sketch.submit(words, off)                      # == ntRead over every record (ntcard.cpp:147-158)
+    t, F1, p = sketch.finish(counters=True)        # uint16 sketch, totKmer, counter-value histogram
+    F0, f = estimate(p_hist=p[0], rBits=27, sBits=7, covMax=1000)
+    """
+
+    def __init__(self, kList, rBits=27, sBits=7, device=0, d_counters=None, stream=None):
+        self.kList = [int(k) for k in kList]
+        self.nK, self.rBits, self.sBits, self.device = len(self.kList), rBits, sBits, device
+        kl = (C.c_uint * self.nK)(*self.kList)
+        h = C.c_void_p()
+        _check(lib.ntc_create(C.byref(h), C.cast(kl, C.POINTER(C.c_uint32)), self.nK, rBits, sBits, device,
+                              C.c_void_p(d_counters) if d_counters else None,
+                              C.c_void_p(stream) if stream else None))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.ntc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reset(self):
+        _check(lib.ntc_reset(self.h))
+
+    def set_kernel(self, kernel):
+        _check(lib.ntc_set_kernel(self.h, kernel))
+
+    def submit(self, words, off=None, n_rec=None, stride=0):
+        """Host batch.  words: uint32 array (numpy or PinnedBuffer.array slice); off: uint32[n_rec+1] or
+        None for a uniform batch of n_rec records of `stride` words.  Returns the ticket."""
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        t = C.c_uint64()
+        if off is not None:
+            off = np.ascontiguousarray(off, dtype=np.uint32)
+            n_rec = len(off) - 1
+            _check(lib.ntc_submit(self.h, words.ctypes.data, len(words), off.ctypes.data, n_rec, 0, C.byref(t)))
+        else:
+            _check(lib.ntc_submit(self.h, words.ctypes.data, len(words), None, n_rec, stride, C.byref(t)))
+        return t.value
+
+    def submit_device(self, d_words, n_words, n_rec, stride=0, d_off=None):
+        _check(lib.ntc_submit_device(self.h, d_words, n_words, d_off, n_rec, stride))
+
+    def submit_reads(self, reads):
+        """Convenience: ASCII reads (list of bytes) -> N-split -> pack -> submit."""
+        words, off = pack_reads(reads, min_len=min(self.kList))
+        if len(off) > 1:
+            self.submit(words, off)
+
+    def wait(self, ticket):
+        _check(lib.ntc_wait(self.h, ticket))
+
+    def sync(self):
+        _check(lib.ntc_sync(self.h))
+
+    def counters_device(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib.ntc_counters_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def totals(self):
+        t = np.zeros(self.nK, dtype=np.uint64)
+        _check(lib.ntc_totals(self.h, t.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return t
+
+    def set_totals(self, tot):
+        t = np.ascontiguousarray(tot, dtype=np.uint64)
+        _check(lib.ntc_set_totals(self.h, t.ctypes.data_as(C.POINTER(C.c_uint64))))
+
+    def finish(self, counters=False, hist=True):
+        """Returns (t_Counter uint16 [nK,2,2^r] or None, totKmer uint64 [nK], p_hist uint32 [nK,2,65536] or None)."""
+        t = np.empty((self.nK, 2, 1 << self.rBits), dtype=np.uint16) if counters else None
+        p = np.empty((self.nK, 2, 65536), dtype=np.uint32) if hist else None
+        tot = np.zeros(self.nK, dtype=np.uint64)
+        _check(lib.ntc_finish(self.h, t.ctypes.data if counters else None, tot.ctypes.data_as(C.POINTER(C.c_uint64)),
+                              p.ctypes.data if hist else None))
+        return t, tot, p
+
+    def gen_packed_device(self, seed, first, n, L, mode, U, stride, d_words):
+        _check(lib.ntc_gen_packed_device(self.h, seed, first, n, L, mode, U, stride, d_words))
+
+    def stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(lib.ntc_stats(self.h, C.byref(a), C.byref(b)))
+        return {"launches": a.value, "batches": b.value}
+
+    def kernel_time(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib.ntc_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def write_hist(path, F1, F0, f, covMax):
+    """outDefault's per-k file (ntcard.cpp:291-294): F1, F0, then rows 1..covMax, tab separated."""
+    with open(path, "w") as fp:
+        fp.write(f"F1\t{int(F1)}\nF0\t{int(np.uint64(F0))}\n")
+        for i in range(1, covMax + 1):
+            fp.write(f"{i}\t{int(np.uint64(f[i]))}\n")

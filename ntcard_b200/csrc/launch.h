@@ -1,0 +1,32 @@
+// launch.h -- host-callable launchers of the sm_100a kernels (internal; the public surface is
+// include/ntcard_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ntc {
+
+struct DevParams;
+
+struct BatchView {          // a packed record stream resident in device memory
+	const uint32_t* words;  // record i at words[off[i]] (or i*stride): [len][ceil(len/16) base words]
+	const uint32_t* off;    // n_rec + 1 word offsets, or nullptr for uniform stride
+	uint32_t stride;        // words per record when off == nullptr
+	uint32_t n_rec;
+	uint64_t n_words;
+	uint32_t uniform_len;   // bases per record when the host knows all records are equal, else 0
+};
+
+size_t piece_scan_temp_bytes(uint32_t n_items);
+cudaError_t launch_piece_tables(const BatchView& b, uint32_t kmin, uint32_t* d_piece_first, uint32_t* d_piece_rec, void* d_tmp,
+    size_t tmp_bytes, cudaStream_t st);
+cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
+    const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t* d_counters, unsigned long long* d_f1, int n_sm,
+    cudaStream_t st);
+cudaError_t launch_narrow_hist(const uint32_t* d_counters, uint32_t n_tables, uint64_t n_per_table, uint16_t* d_narrow,
+    uint32_t* d_phist, cudaStream_t st);
+cudaError_t launch_gen_packed(uint64_t S, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U, uint32_t stride,
+    uint32_t* d_words, cudaStream_t st);
+
+} // namespace ntc

@@ -1,0 +1,591 @@
+// ntc_api.cu -- the C-ABI (include/ntcard_b200.h) over the sm_100a kernels: context, pinned
+// double-buffered H2D pipeline, batch submission, finish.  No CPU fallback anywhere: without a
+// usable CUDA device every compute entry point fails with NTC_ENODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ntcard_b200.h"
+#include "internal.h"
+#include "launch.h"
+#include "sketch_common.cuh"
+
+namespace {
+
+using ntc::set_err;
+
+#define CK(call)                                                                                         \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                         \
+		if (e_ != cudaSuccess)                                                                           \
+			return set_err(NTC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+constexpr int NBUF = 3; // device/pinned staging ring depth
+
+struct Stage {
+	uint32_t* d_words = nullptr;
+	size_t cap_words = 0;
+	uint32_t* d_off = nullptr;
+	size_t cap_off = 0;
+	uint32_t* h_words = nullptr; // pinned staging for pageable sources
+	size_t cap_h_words = 0;
+	uint32_t* h_off = nullptr;
+	size_t cap_h_off = 0;
+	cudaEvent_t copied = nullptr;   // H2D of this slot finished (host source reusable)
+	cudaEvent_t consumed = nullptr; // kernels reading this slot finished (slot reusable)
+	uint64_t ticket = 0;
+};
+
+} // namespace
+
+struct ntc_ctx {
+	int device = 0;
+	int n_sm = 148;
+	cudaStream_t stream = nullptr; // compute stream (own or caller's)
+	bool own_stream = false;
+	cudaStream_t copy_stream = nullptr;
+	unsigned nK = 0, rBits = 0, sBits = 0, kmin = 0, kmax = 0;
+	unsigned k[NTC_MAX_K] = {};
+	int kernel = NTC_KERNEL_AUTO;
+	uint32_t* d_counters = nullptr;
+	bool own_counters = false;
+	size_t n_counters = 0;
+	unsigned long long* d_f1 = nullptr;
+	ntc::DevParams* d_params = nullptr;
+	bool totals_overridden = false;
+	uint64_t totals[NTC_MAX_K] = {};
+	Stage stage[NBUF];
+	uint64_t next_ticket = 1;
+	// piece tables (general kernel)
+	uint32_t* d_piece_first = nullptr;
+	size_t cap_piece_first = 0;
+	uint32_t* d_piece_rec = nullptr;
+	size_t cap_piece_rec = 0;
+	void* d_scan_tmp = nullptr;
+	size_t cap_scan_tmp = 0;
+	// finish buffers
+	uint16_t* d_narrow = nullptr;
+	uint32_t* d_phist = nullptr;
+	// stats / timing
+	uint64_t n_launches = 0, n_batches = 0;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing; // per batch, around the sketch kernels
+	std::vector<cudaEvent_t> event_pool;
+	double kernel_ms = 0;
+	uint64_t n_timed = 0;
+};
+
+namespace {
+
+int use_device(ntc_ctx* c)
+{
+	CK(cudaSetDevice(c->device));
+	return NTC_OK;
+}
+
+template <typename T>
+int grow(T** p, size_t* cap, size_t need, bool pinned_host)
+{
+	if (need <= *cap)
+		return NTC_OK;
+	size_t n = std::max(need, *cap + *cap / 2);
+	if (*p) {
+		if (pinned_host)
+			CK(cudaFreeHost(*p));
+		else
+			CK(cudaFree(*p));
+		*p = nullptr;
+		*cap = 0;
+	}
+	if (pinned_host)
+		CK(cudaHostAlloc((void**)p, n * sizeof(T), cudaHostAllocDefault));
+	else
+		CK(cudaMalloc((void**)p, n * sizeof(T)));
+	*cap = n;
+	return NTC_OK;
+}
+
+int get_event(ntc_ctx* c, cudaEvent_t* ev)
+{
+	if (!c->event_pool.empty()) {
+		*ev = c->event_pool.back();
+		c->event_pool.pop_back();
+		return NTC_OK;
+	}
+	CK(cudaEventCreate(ev));
+	return NTC_OK;
+}
+
+void build_params(const ntc_ctx* c, ntc::DevParams* P)
+{
+	memset(P, 0, sizeof *P);
+	P->nK = c->nK;
+	P->rBits = c->rBits;
+	P->sBits = c->sBits;
+	P->kmin = c->kmin;
+	for (unsigned ki = 0; ki < c->nK; ki++) {
+		const unsigned k = c->k[ki];
+		P->k[ki] = k;
+		for (unsigned in = 0; in < 4; in++)
+			for (unsigned out = 0; out < 4; out++) {
+				// NTF64 / NTR64 sliding forms, nthash.hpp:242-257
+				P->tab[ki].xf[in | out << 2] = ntc::seed_of(in) ^ ntc::srol_n(ntc::seed_of(out), k);
+				P->tab[ki].xr[in | out << 2] = ntc::srol_n(ntc::seed_of(3 - in), k) ^ ntc::seed_of(3 - out);
+			}
+	}
+}
+
+// Run the sketch kernels over one device-resident batch on the compute stream.
+int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
+{
+	if (b.n_rec == 0)
+		return NTC_OK;
+	cudaEvent_t e0, e1;
+	int rc;
+	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
+		return rc;
+	CK(cudaEventRecord(e0, c->stream));
+	uint64_t bound = 0;
+	if (!record_is_piece) {
+		bound = (uint64_t)b.n_rec + (16 * b.n_words) / ntc::PIECE_STARTS + 1;
+		if (bound > 0xFFFFFFFFull)
+			return set_err(NTC_EINVAL, "batch too large: %llu pieces", (unsigned long long)bound);
+		if ((rc = grow(&c->d_piece_first, &c->cap_piece_first, (size_t)b.n_rec + 1, false)) ||
+		    (rc = grow(&c->d_piece_rec, &c->cap_piece_rec, (size_t)bound, false)))
+			return rc;
+		size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
+		char* t = (char*)c->d_scan_tmp;
+		if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
+			return rc;
+		c->d_scan_tmp = t;
+		CK(ntc::launch_piece_tables(b, c->kmin, c->d_piece_first, c->d_piece_rec, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
+		c->n_launches += 3;
+	}
+	CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters, c->d_f1,
+	    c->n_sm, c->stream));
+	c->n_launches += 1;
+	CK(cudaEventRecord(e1, c->stream));
+	c->timing.emplace_back(e0, e1);
+	c->n_batches++;
+	return NTC_OK;
+}
+
+int drain_timing(ntc_ctx* c)
+{
+	for (auto& pr : c->timing) {
+		float ms = 0;
+		CK(cudaEventSynchronize(pr.second));
+		CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+		c->kernel_ms += ms;
+		c->n_timed++;
+		c->event_pool.push_back(pr.first);
+		c->event_pool.push_back(pr.second);
+	}
+	c->timing.clear();
+	return NTC_OK;
+}
+
+bool single_piece_records(const ntc_ctx* c, uint32_t max_rec_words)
+{
+	if (max_rec_words < 1)
+		return true;
+	uint64_t max_len = (uint64_t)(max_rec_words - 1) * 16;
+	return max_len < c->kmin || max_len - c->kmin + 1 <= ntc::PIECE_STARTS;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* ntc_last_error(void) { return ntc::last_err(); }
+const char* ntc_version(void) { return "ntcard-b200 0.1 (sm_100a)"; }
+
+int ntc_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits, unsigned sBits, int device, void* d_counters,
+    void* cuda_stream)
+{
+	if (!out || !kList || nK == 0 || nK > NTC_MAX_K)
+		return set_err(NTC_EINVAL, "ntc_create: need 1..%d k values", NTC_MAX_K);
+	if (rBits < 1 || rBits > 30 || sBits < 1 || sBits + rBits > 62)
+		return set_err(NTC_EINVAL, "ntc_create: rBits=%u sBits=%u out of range", rBits, sBits);
+	for (unsigned i = 0; i < nK; i++)
+		if (kList[i] == 0)
+			return set_err(NTC_EINVAL, "ntc_create: k must be >= 1");
+	int ndev = ntc_device_count();
+	if (ndev <= 0)
+		return set_err(NTC_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
+	if (device < 0 || device >= ndev)
+		return set_err(NTC_EINVAL, "ntc_create: device %d of %d", device, ndev);
+	ntc_ctx* c = new ntc_ctx();
+	c->device = device;
+	c->nK = nK;
+	c->rBits = rBits;
+	c->sBits = sBits;
+	c->kmin = c->kmax = kList[0];
+	for (unsigned i = 0; i < nK; i++) {
+		c->k[i] = kList[i];
+		c->kmin = std::min(c->kmin, kList[i]);
+		c->kmax = std::max(c->kmax, kList[i]);
+	}
+	c->n_counters = (size_t)nK * NTC_NSAMP << rBits;
+	int rc = NTC_OK;
+	auto fail = [&](int code) {
+		ntc_destroy(c);
+		return code;
+	};
+	if ((rc = use_device(c)))
+		return fail(rc);
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+		return fail(set_err(NTC_ECUDA, "cudaGetDeviceProperties failed"));
+	if (prop.major < 10)
+		return fail(set_err(NTC_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor));
+	c->n_sm = prop.multiProcessorCount;
+#define CKF(call)                                                                                      \
+	do {                                                                                               \
+		cudaError_t e_ = (call);                                                                       \
+		if (e_ != cudaSuccess)                                                                         \
+			return fail(set_err(NTC_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)));           \
+	} while (0)
+	if (cuda_stream) {
+		c->stream = (cudaStream_t)cuda_stream;
+	} else {
+		CKF(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		c->own_stream = true;
+	}
+	CKF(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	if (d_counters) {
+		c->d_counters = (uint32_t*)d_counters;
+	} else {
+		CKF(cudaMalloc((void**)&c->d_counters, c->n_counters * sizeof(uint32_t)));
+		c->own_counters = true;
+	}
+	CKF(cudaMalloc((void**)&c->d_f1, NTC_MAX_K * sizeof(unsigned long long)));
+	CKF(cudaMalloc((void**)&c->d_params, sizeof(ntc::DevParams)));
+	ntc::DevParams hp;
+	build_params(c, &hp);
+	CKF(cudaMemcpy(c->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
+	for (int i = 0; i < NBUF; i++) {
+		CKF(cudaEventCreateWithFlags(&c->stage[i].copied, cudaEventDisableTiming));
+		CKF(cudaEventCreateWithFlags(&c->stage[i].consumed, cudaEventDisableTiming));
+	}
+#undef CKF
+	if ((rc = ntc_reset(c)))
+		return fail(rc);
+	*out = c;
+	return NTC_OK;
+}
+
+void ntc_destroy(ntc_ctx* c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	if (c->stream)
+		cudaStreamSynchronize(c->stream);
+	if (c->copy_stream)
+		cudaStreamSynchronize(c->copy_stream);
+	for (auto& pr : c->timing) {
+		cudaEventDestroy(pr.first);
+		cudaEventDestroy(pr.second);
+	}
+	for (auto e : c->event_pool)
+		cudaEventDestroy(e);
+	for (int i = 0; i < NBUF; i++) {
+		Stage& s = c->stage[i];
+		if (s.d_words) cudaFree(s.d_words);
+		if (s.d_off) cudaFree(s.d_off);
+		if (s.h_words) cudaFreeHost(s.h_words);
+		if (s.h_off) cudaFreeHost(s.h_off);
+		if (s.copied) cudaEventDestroy(s.copied);
+		if (s.consumed) cudaEventDestroy(s.consumed);
+	}
+	if (c->d_piece_first) cudaFree(c->d_piece_first);
+	if (c->d_piece_rec) cudaFree(c->d_piece_rec);
+	if (c->d_scan_tmp) cudaFree(c->d_scan_tmp);
+	if (c->d_narrow) cudaFree(c->d_narrow);
+	if (c->d_phist) cudaFree(c->d_phist);
+	if (c->d_f1) cudaFree(c->d_f1);
+	if (c->d_params) cudaFree(c->d_params);
+	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int ntc_reset(ntc_ctx* c)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(uint32_t), c->stream));
+	CK(cudaMemsetAsync(c->d_f1, 0, NTC_MAX_K * sizeof(unsigned long long), c->stream));
+	c->totals_overridden = false;
+	return NTC_OK;
+}
+
+int ntc_set_kernel(ntc_ctx* c, int kernel)
+{
+	if (!c || kernel < NTC_KERNEL_AUTO || kernel > NTC_KERNEL_BITSLICE)
+		return set_err(NTC_EINVAL, "ntc_set_kernel: bad argument");
+	c->kernel = kernel;
+	return NTC_OK;
+}
+
+int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec, uint32_t stride_words,
+    uint64_t* ticket)
+{
+	if (!c || (!words && n_words) || n_rec > 0xFFFFFFF0ull || n_words > 0xFFFFFFF0ull)
+		return set_err(NTC_EINVAL, "ntc_submit: bad argument");
+	if (!off && n_rec && (stride_words == 0 || (uint64_t)stride_words * n_rec > n_words))
+		return set_err(NTC_EINVAL, "ntc_submit: uniform batch needs stride_words*n_rec <= n_words");
+	if (ticket)
+		*ticket = 0;
+	if (n_rec == 0)
+		return NTC_OK;
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	uint32_t max_rec_words = stride_words;
+	if (off) {
+		max_rec_words = 0;
+		if (off[n_rec] > n_words)
+			return set_err(NTC_EINVAL, "ntc_submit: off[n_rec] exceeds n_words");
+		for (size_t i = 0; i < n_rec; i++) {
+			if (off[i + 1] < off[i] + 1)
+				return set_err(NTC_EINVAL, "ntc_submit: record %zu has no length word", i);
+			max_rec_words = std::max(max_rec_words, off[i + 1] - off[i]);
+		}
+	}
+	Stage& s = c->stage[c->next_ticket % NBUF];
+	// the slot's previous batch must have been consumed by its kernels before we overwrite it
+	CK(cudaEventSynchronize(s.consumed));
+	if ((rc = grow(&s.d_words, &s.cap_words, n_words, false)))
+		return rc;
+	if (off && (rc = grow(&s.d_off, &s.cap_off, n_rec + 1, false)))
+		return rc;
+	cudaPointerAttributes attr;
+	bool pinned = cudaPointerGetAttributes(&attr, words) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+	cudaGetLastError();
+	const uint32_t* src_words = words;
+	const uint32_t* src_off = off;
+	if (!pinned) {
+		CK(cudaEventSynchronize(s.copied)); // staging of this slot is free again
+		if ((rc = grow(&s.h_words, &s.cap_h_words, n_words, true)))
+			return rc;
+		memcpy(s.h_words, words, n_words * sizeof(uint32_t));
+		src_words = s.h_words;
+	}
+	if (off) {
+		cudaPointerAttributes a2;
+		bool pinned_off = cudaPointerGetAttributes(&a2, off) == cudaSuccess && a2.type == cudaMemoryTypeHost;
+		cudaGetLastError();
+		if (!pinned_off) {
+			if (pinned)
+				CK(cudaEventSynchronize(s.copied));
+			if ((rc = grow(&s.h_off, &s.cap_h_off, n_rec + 1, true)))
+				return rc;
+			memcpy(s.h_off, off, (n_rec + 1) * sizeof(uint32_t));
+			src_off = s.h_off;
+		}
+	}
+	CK(cudaMemcpyAsync(s.d_words, src_words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+	if (off)
+		CK(cudaMemcpyAsync(s.d_off, src_off, (n_rec + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+	CK(cudaEventRecord(s.copied, c->copy_stream));
+	CK(cudaStreamWaitEvent(c->stream, s.copied, 0));
+	ntc::BatchView b{ s.d_words, off ? s.d_off : nullptr, stride_words, (uint32_t)n_rec, n_words, 0 };
+	if ((rc = run_batch(c, b, single_piece_records(c, max_rec_words))))
+		return rc;
+	CK(cudaEventRecord(s.consumed, c->stream));
+	s.ticket = c->next_ticket++;
+	if (ticket)
+		*ticket = s.ticket;
+	return NTC_OK;
+}
+
+int ntc_submit_device(ntc_ctx* c, const uint32_t* d_words, size_t n_words, const uint32_t* d_off, size_t n_rec,
+    uint32_t stride_words)
+{
+	if (!c || (!d_words && n_words) || n_rec > 0xFFFFFFF0ull || n_words > 0xFFFFFFF0ull)
+		return set_err(NTC_EINVAL, "ntc_submit_device: bad argument");
+	if (!d_off && n_rec && (stride_words == 0 || (uint64_t)stride_words * n_rec > n_words))
+		return set_err(NTC_EINVAL, "ntc_submit_device: uniform batch needs stride_words*n_rec <= n_words");
+	if (n_rec == 0)
+		return NTC_OK;
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	ntc::BatchView b{ d_words, d_off, stride_words, (uint32_t)n_rec, n_words, 0 };
+	return run_batch(c, b, d_off ? false : single_piece_records(c, stride_words));
+}
+
+int ntc_wait(ntc_ctx* c, uint64_t ticket)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	if (ticket == 0)
+		return NTC_OK;
+	for (int i = 0; i < NBUF; i++)
+		if (c->stage[i].ticket == ticket) {
+			CK(cudaEventSynchronize(c->stage[i].copied));
+			return NTC_OK;
+		}
+	return NTC_OK; // older than the ring: long finished
+}
+
+int ntc_sync(ntc_ctx* c)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	CK(cudaStreamSynchronize(c->copy_stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return drain_timing(c);
+}
+
+int ntc_counters_device(ntc_ctx* c, void** d_counters, size_t* n_counters)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	if (d_counters) *d_counters = c->d_counters;
+	if (n_counters) *n_counters = c->n_counters;
+	return NTC_OK;
+}
+
+int ntc_totals(ntc_ctx* c, uint64_t* totKmer)
+{
+	if (!c || !totKmer)
+		return set_err(NTC_EINVAL, "ntc_totals: bad argument");
+	if (c->totals_overridden) {
+		memcpy(totKmer, c->totals, c->nK * sizeof(uint64_t));
+		return NTC_OK;
+	}
+	int rc;
+	if ((rc = ntc_sync(c)))
+		return rc;
+	unsigned long long h[NTC_MAX_K];
+	CK(cudaMemcpy(h, c->d_f1, sizeof h, cudaMemcpyDeviceToHost));
+	for (unsigned i = 0; i < c->nK; i++)
+		totKmer[i] = h[i];
+	return NTC_OK;
+}
+
+int ntc_set_totals(ntc_ctx* c, const uint64_t* totKmer)
+{
+	if (!c || !totKmer)
+		return set_err(NTC_EINVAL, "ntc_set_totals: bad argument");
+	memcpy(c->totals, totKmer, c->nK * sizeof(uint64_t));
+	c->totals_overridden = true;
+	return NTC_OK;
+}
+
+int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_hist)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	if (totKmer && (rc = ntc_totals(c, totKmer)))
+		return rc;
+	const uint32_t n_tables = c->nK * NTC_NSAMP;
+	const uint64_t n_per_table = (uint64_t)1 << c->rBits;
+	if (t_Counter && !c->d_narrow)
+		CK(cudaMalloc((void**)&c->d_narrow, c->n_counters * sizeof(uint16_t)));
+	if (p_hist) {
+		if (!c->d_phist)
+			CK(cudaMalloc((void**)&c->d_phist, (size_t)n_tables * 65536 * sizeof(uint32_t)));
+		CK(cudaMemsetAsync(c->d_phist, 0, (size_t)n_tables * 65536 * sizeof(uint32_t), c->stream));
+	}
+	if (t_Counter || p_hist) {
+		CK(ntc::launch_narrow_hist(c->d_counters, n_tables, n_per_table, t_Counter ? c->d_narrow : nullptr,
+		    p_hist ? c->d_phist : nullptr, c->stream));
+		c->n_launches++;
+	}
+	if (t_Counter)
+		CK(cudaMemcpyAsync(t_Counter, c->d_narrow, c->n_counters * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+	if (p_hist)
+		CK(cudaMemcpyAsync(p_hist, c->d_phist, (size_t)n_tables * 65536 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	if ((rc = ntc_sync(c)))
+		return rc;
+	if (p_hist) {
+		// the kernel counts values >= 1 only; p[0] is what is left of the 2^rBits buckets
+		for (uint32_t t = 0; t < n_tables; t++) {
+			uint64_t nz = 0;
+			uint32_t* p = p_hist + (size_t)t * 65536;
+			for (uint32_t v = 1; v < 65536; v++)
+				nz += p[v];
+			p[0] = (uint32_t)(n_per_table - nz);
+		}
+	}
+	return NTC_OK;
+}
+
+void* ntc_host_alloc(size_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+		set_err(NTC_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return p;
+}
+
+void ntc_host_free(void* p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+int ntc_gen_packed_device(ntc_ctx* c, uint64_t seed, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U,
+    uint32_t stride_words, uint32_t* d_words)
+{
+	if (!c || !d_words || stride_words < 1 + (L + 15) / 16 || mode < 0 || mode > 1)
+		return set_err(NTC_EINVAL, "ntc_gen_packed_device: bad argument");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	CK(ntc::launch_gen_packed(seed, first, n, L, mode, U, stride_words, d_words, c->stream));
+	c->n_launches++;
+	return NTC_OK;
+}
+
+int ntc_stats(ntc_ctx* c, uint64_t* n_launches, uint64_t* n_batches)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	if (n_launches) *n_launches = c->n_launches;
+	if (n_batches) *n_batches = c->n_batches;
+	return NTC_OK;
+}
+
+int ntc_kernel_time(ntc_ctx* c, double* ms_total, uint64_t* n_timed)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	if (ms_total) *ms_total = c->kernel_ms;
+	if (n_timed) *n_timed = c->n_timed;
+	c->kernel_ms = 0;
+	c->n_timed = 0;
+	return NTC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,301 @@
+// sketch_kernels.cu -- general sm_100a kernels of the ntCard sketch path:
+//   * piece bookkeeping for ragged / long records,
+//   * roll64: one thread per piece, 64-bit NTF64/NTR64 recurrence in registers (any k, any s),
+//   * finish: narrow uint32 counters mod 2^16 + counter-value histogram,
+//   * the deterministic synthetic read generator (bench / tests).
+// The bit-sliced fast kernel lives in bitslice_kernel.cu.
+#include <cub/device/device_scan.cuh>
+
+#include "launch.h"
+#include "sketch_common.cuh"
+
+namespace ntc {
+
+// ------------------------------------------------------------------------------------------------
+// piece bookkeeping
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t rec_offset(const uint32_t* __restrict__ off, uint32_t stride, uint32_t rec)
+{
+	return off ? (uint64_t)__ldg(off + rec) : (uint64_t)rec * stride;
+}
+
+__global__ void piece_count_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ off, uint32_t stride,
+    uint32_t n_rec, uint32_t kmin, uint32_t* __restrict__ n_pieces /* [n_rec + 1] */)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n_rec)
+		return;
+	uint32_t np = 0;
+	if (i < n_rec) {
+		uint32_t len = __ldg(words + rec_offset(off, stride, i));
+		if (len >= kmin)
+			np = (len - kmin + 1 + PIECE_STARTS - 1) / PIECE_STARTS;
+	}
+	n_pieces[i] = np; // entry n_rec = 0 so the exclusive scan leaves the total there
+}
+
+__global__ void piece_fill_kernel(const uint32_t* __restrict__ piece_first, uint32_t n_rec, uint32_t* __restrict__ piece_rec)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_rec)
+		return;
+	uint32_t a = piece_first[i], b = piece_first[i + 1];
+	for (uint32_t p = a; p < b; p++)
+		piece_rec[p] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// roll64: the straightforward kernel.  ntRead's loops (ntcard.cpp:147-158) with the iterator's
+// rolling update (ntHashIterator.hpp:85 -> NTC64, nthash.hpp:275-279); records hold valid bases
+// only, so the N-restart branch (ntHashIterator.hpp:80-83) never fires on the device.
+// ------------------------------------------------------------------------------------------------
+struct BaseStream { // sequential 2-bit reader with lazy word refill (never reads past the last needed word)
+	const uint32_t* __restrict__ p;
+	uint32_t w;
+	uint32_t left;
+	__device__ __forceinline__ void open(const uint32_t* __restrict__ b, uint32_t idx)
+	{
+		p = b + (idx >> 4);
+		w = __ldg(p) >> ((idx & 15u) * 2u);
+		left = 16u - (idx & 15u);
+	}
+	__device__ __forceinline__ uint32_t next()
+	{
+		if (left == 0) {
+			w = __ldg(++p);
+			left = 16;
+		}
+		uint32_t c = w & 3u;
+		w >>= 2;
+		--left;
+		return c;
+	}
+};
+
+__device__ __forceinline__ uint32_t process_piece_k(const uint32_t* __restrict__ b, uint32_t len, uint32_t a, uint32_t k,
+    const KTab& T, uint32_t* __restrict__ ctr_k, uint32_t rBits, uint32_t sBits)
+{
+	if (len < k)
+		return 0;
+	const uint32_t ns = len - k + 1;
+	if (a >= ns)
+		return 0;
+	const uint32_t e = min(a + PIECE_STARTS, ns);
+	// from-scratch hashes of the first window: NTF64/NTR64 base forms, nthash.hpp:220-239
+	uint64_t fh = 0, rh = 0;
+	{
+		BaseStream s;
+		s.open(b, a);
+		for (uint32_t i = 0; i < k; i++)
+			fh = srol(fh) ^ seed_of(s.next());
+		for (uint32_t i = k; i-- > 0;)
+			rh = srol(rh) ^ seed_of(3u - base_at(b, a + i));
+	}
+	sample_and_count(rh < fh ? rh : fh, ctr_k, rBits, sBits);
+	BaseStream so, si;
+	so.open(b, a);
+	if (a + 1 < e)
+		si.open(b, a + k);
+	for (uint32_t j = a + 1; j < e; j++) {
+		const uint32_t idx = si.next() | (so.next() << 2);
+		fh = srol(fh) ^ T.xf[idx];
+		rh = sror(rh ^ T.xr[idx]);
+		sample_and_count(rh < fh ? rh : fh, ctr_k, rBits, sBits);
+	}
+	return e - a;
+}
+
+template <bool kRecordIsPiece>
+__global__ void __launch_bounds__(256) roll64_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ off,
+    uint32_t stride, uint32_t n_rec, const uint32_t* __restrict__ piece_first, const uint32_t* __restrict__ piece_rec,
+    const DevParams* __restrict__ P, uint32_t* __restrict__ counters, unsigned long long* __restrict__ f1)
+{
+	__shared__ DevParams sp;
+	__shared__ unsigned long long s_f1[NTC_MAX_K];
+	{
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(P);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(&sp);
+		for (uint32_t i = threadIdx.x; i < sizeof(DevParams) / 4; i += blockDim.x)
+			dst[i] = src[i];
+		if (threadIdx.x < NTC_MAX_K)
+			s_f1[threadIdx.x] = 0;
+	}
+	__syncthreads();
+	const uint32_t n_pieces = kRecordIsPiece ? n_rec : piece_first[n_rec];
+	const uint64_t tab_stride = (uint64_t)2 << sp.rBits;
+	for (uint32_t piece = blockIdx.x * blockDim.x + threadIdx.x; piece < n_pieces; piece += gridDim.x * blockDim.x) {
+		uint32_t rec, a;
+		if (kRecordIsPiece) {
+			rec = piece;
+			a = 0;
+		} else {
+			rec = piece_rec[piece];
+			a = (piece - piece_first[rec]) * PIECE_STARTS;
+		}
+		const uint32_t* r = words + rec_offset(off, stride, rec);
+		const uint32_t len = __ldg(r);
+		for (uint32_t ki = 0; ki < sp.nK; ki++) {
+			uint32_t n = process_piece_k(r + 1, len, a, sp.k[ki], sp.tab[ki], counters + ki * tab_stride, sp.rBits, sp.sBits);
+			if (n)
+				atomicAdd(&s_f1[ki], (unsigned long long)n);
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x < sp.nK && s_f1[threadIdx.x])
+		atomicAdd(f1 + threadIdx.x, s_f1[threadIdx.x]); // totKmer, ntcard.cpp:155,466
+}
+
+// ------------------------------------------------------------------------------------------------
+// finish: narrow + counter-value histogram (compEst's first loop, ntcard.cpp:245-247)
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t HIST_SMEM_BINS = 2048;
+
+// One CTA handles `chunk` consecutive counters of one table.  p_hist[table][v] for v >= 1 only; the
+// host derives p[0] = 2^rBits - sum(v >= 1).
+__global__ void __launch_bounds__(256) narrow_hist_kernel(const uint32_t* __restrict__ counters, uint64_t n_per_table,
+    uint32_t chunk, uint16_t* __restrict__ narrow /* may be null */, uint32_t* __restrict__ p_hist /* may be null */)
+{
+	__shared__ uint32_t sh[HIST_SMEM_BINS];
+	for (uint32_t i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+		sh[i] = 0;
+	__syncthreads();
+	const uint64_t chunks_per_table = (n_per_table + chunk - 1) / chunk;
+	const uint64_t table = blockIdx.x / chunks_per_table;
+	const uint64_t c0 = (blockIdx.x % chunks_per_table) * chunk;
+	const uint64_t c1 = min(c0 + chunk, n_per_table);
+	const uint32_t* src = counters + table * n_per_table;
+	uint32_t* ph = p_hist ? p_hist + table * 65536 : nullptr;
+	for (uint64_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+		const uint32_t v = src[i] & 0xFFFFu; // uint16_t wrap of ntcard.cpp:143
+		if (narrow)
+			narrow[table * n_per_table + i] = (uint16_t)v;
+		if (ph && v) {
+			if (v < HIST_SMEM_BINS)
+				atomicAdd(&sh[v], 1u);
+			else
+				atomicAdd(&ph[v], 1u);
+		}
+	}
+	__syncthreads();
+	if (ph)
+		for (uint32_t i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+			if (sh[i])
+				atomicAdd(&ph[i], sh[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic reads: word w (32 bases) of read i under seed S is mix64((S<<48)^(i<<12)^w),
+// base j of the word = (v >> 2j) & 3 -- which already IS the 2-bit packing.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+	x += 0x9E3779B97F4A7C15ULL;
+	uint64_t z = x;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+	return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ uint32_t gen_base(uint64_t S, uint64_t src, uint32_t j)
+{
+	return (uint32_t)(mix64((S << 48) ^ (src << 12) ^ (uint64_t)(j >> 5)) >> (2 * (j & 31))) & 3u;
+}
+
+__global__ void gen_packed_kernel(uint64_t S, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U, uint32_t stride,
+    uint32_t* __restrict__ words)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t rec = t / stride;
+	const uint32_t w = (uint32_t)(t % stride);
+	if (rec >= n)
+		return;
+	uint32_t out = 0;
+	if (w == 0) {
+		out = L;
+	} else {
+		const uint32_t j0 = (w - 1) * 16;
+		if (j0 < L) {
+			const uint64_t i = first + rec;
+			const bool rep = (mode == 1 && U != 0);
+			const uint64_t src = rep ? i % U : i;
+			const bool rc = rep && ((i / U) & 1);
+			const uint32_t nb = min(16u, L - j0);
+			if (!rc) {
+				uint64_t v = mix64((S << 48) ^ (src << 12) ^ (uint64_t)(j0 >> 5));
+				out = (uint32_t)(v >> (2 * (j0 & 31)));
+				if (nb < 16)
+					out &= (1u << (2 * nb)) - 1;
+			} else {
+				for (uint32_t j = 0; j < nb; j++)
+					out |= (3u - gen_base(S, src, L - 1 - (j0 + j))) << (2 * j);
+			}
+		}
+	}
+	words[rec * stride + w] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+static inline unsigned grid_for(uint64_t n, unsigned block, unsigned cap)
+{
+	uint64_t g = (n + block - 1) / block;
+	if (g < 1) g = 1;
+	if (g > cap) g = cap;
+	return (unsigned)g;
+}
+
+size_t piece_scan_temp_bytes(uint32_t n_items)
+{
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n_items);
+	return bytes;
+}
+
+cudaError_t launch_piece_tables(const BatchView& b, uint32_t kmin, uint32_t* d_piece_first, uint32_t* d_piece_rec, void* d_tmp,
+    size_t tmp_bytes, cudaStream_t st)
+{
+	const uint32_t n = b.n_rec + 1;
+	piece_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.words, b.off, b.stride, b.n_rec, kmin, d_piece_first);
+	cudaError_t e = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_piece_first, d_piece_first, (int)n, st);
+	if (e != cudaSuccess)
+		return e;
+	piece_fill_kernel<<<(b.n_rec + 255) / 256, 256, 0, st>>>(d_piece_first, b.n_rec, d_piece_rec);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
+    const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t* d_counters, unsigned long long* d_f1, int n_sm,
+    cudaStream_t st)
+{
+	// enough CTAs for every SM to hold its resident set, a multiple of the SM count
+	const unsigned cap = (unsigned)n_sm * 8u * 16u;
+	unsigned grid = grid_for(record_is_piece ? b.n_rec : n_pieces_bound, 256, cap);
+	if (record_is_piece)
+		roll64_kernel<true><<<grid, 256, 0, st>>>(b.words, b.off, b.stride, b.n_rec, nullptr, nullptr, d_params, d_counters, d_f1);
+	else
+		roll64_kernel<false><<<grid, 256, 0, st>>>(b.words, b.off, b.stride, b.n_rec, d_piece_first, d_piece_rec, d_params,
+		    d_counters, d_f1);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_narrow_hist(const uint32_t* d_counters, uint32_t n_tables, uint64_t n_per_table, uint16_t* d_narrow,
+    uint32_t* d_phist, cudaStream_t st)
+{
+	const uint32_t chunk = (uint32_t)(n_per_table < 65536 ? n_per_table : 65536);
+	const uint64_t chunks_per_table = (n_per_table + chunk - 1) / chunk;
+	narrow_hist_kernel<<<(unsigned)(n_tables * chunks_per_table), 256, 0, st>>>(d_counters, n_per_table, chunk, d_narrow, d_phist);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_gen_packed(uint64_t S, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U, uint32_t stride,
+    uint32_t* d_words, cudaStream_t st)
+{
+	const uint64_t total = n * stride;
+	if (total == 0)
+		return cudaSuccess;
+	gen_packed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, first, n, L, mode, U, stride, d_words);
+	return cudaGetLastError();
+}
+
+} // namespace ntc

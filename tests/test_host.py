@@ -1,0 +1,121 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, refuses to compute without a device (no CPU fallback), and its host helpers
+(packer, generator, estimator) agree with the oracle / golden vectors."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ntcard_b200 as nt
+from conftest import ROOT, load_golden
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "ntcard_b200.h")).read()
+    declared = set(re.findall(r"\b(ntc_[a-z0-9_]+)\s*\(", hdr)) - {"ntc_ctx"}
+    assert declared == set(nt.SYMBOLS), declared ^ set(nt.SYMBOLS)
+    raw = ctypes.CDLL(nt.LIB_PATH)
+    for s in declared:
+        assert hasattr(raw, s), s
+
+
+def test_no_cpu_fallback():
+    if nt.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(nt.NtcError) as e:
+        nt.Sketch([32])
+    assert e.value.code == nt.api.NTC_ENODEVICE
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ntcard_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in src.replace("test oracle", ""), f"{fn} mentions the oracle"
+
+
+def test_create_argument_errors():
+    h = ctypes.c_void_p()
+    kl = (ctypes.c_uint * 1)(32)
+    p = ctypes.cast(kl, ctypes.POINTER(ctypes.c_uint32))
+    assert nt.lib.ntc_create(ctypes.byref(h), p, 0, 27, 7, 0, None, None) == nt.api.NTC_EINVAL
+    assert nt.lib.ntc_create(ctypes.byref(h), p, 1, 0, 7, 0, None, None) == nt.api.NTC_EINVAL
+    assert nt.lib.ntc_create(ctypes.byref(h), p, 1, 27, 0, 0, None, None) == nt.api.NTC_EINVAL
+    assert b"rBits" in nt.lib.ntc_last_error()
+
+
+def unpack(words, off):
+    out = []
+    for i in range(len(off) - 1):
+        L = int(words[off[i]])
+        w = words[off[i] + 1: off[i] + 1 + (L + 15) // 16]
+        s = bytearray()
+        for j in range(L):
+            s.append(b"ACGT"[(int(w[j >> 4]) >> (2 * (j & 15))) & 3])
+        out.append(bytes(s))
+    return out
+
+
+def test_pack_splits_at_invalid(oracle):
+    reads = [b"ACGTNACGTACGTTTGA", b"", b"NNN", b"acguACGU" * 5, b"A", b"NACGTN", b"ACGT-ACGT.ACGTXACGT\r"]
+    words, off = nt.pack_reads(reads, min_len=1)
+    segs = unpack(words, off)
+    assert segs == [b"ACGT", b"ACGTACGTTTGA", b"ACGTACGT" * 5, b"A", b"ACGT", b"ACGT", b"ACGT", b"ACGT", b"ACGT"]
+    words, off = nt.pack_reads(reads, min_len=5)
+    assert unpack(words, off) == [b"ACGTACGTTTGA", b"ACGTACGT" * 5]
+    # same hashes from segments as from the raw reads (oracle), per k
+    for k in (1, 4, 12):
+        a = np.concatenate([oracle.hash_seq(r, k)[0] for r in reads])
+        b = np.concatenate([oracle.hash_seq(s, k)[0] for s in segs] + [np.zeros(0, dtype=np.uint64)])
+        assert np.array_equal(np.sort(a), np.sort(b))
+
+
+def test_pack_overflow_reports():
+    chars = np.frombuffer(b"ACGTACGTACGTACGTACGT" * 3 + b"\0", dtype=np.uint8)
+    soff = np.array([0, 20, 40, 60], dtype=np.uint64)
+    words = np.empty(4, dtype=np.uint32)  # room for one 20-base record (1+2 words) only
+    off = np.empty(8, dtype=np.uint32)
+    nw, nr, cons = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+    rc = nt.lib.ntc_pack_seqs(chars.ctypes.data, soff.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), 3, 1,
+                              words.ctypes.data, 4, ctypes.byref(nw), off.ctypes.data, 7, ctypes.byref(nr), ctypes.byref(cons))
+    assert rc == nt.api.NTC_ENOMEM and cons.value == 1 and nr.value == 1 and nw.value == 3
+
+
+def test_generator_matches_oracle(oracle):
+    for mode, U in ((0, 0), (1, 7), (2, 0)):
+        for L in (1, 31, 32, 33, 150, 400):
+            a = nt.gen_ascii(3, 5, 40, L, mode, U)
+            b = oracle.gen_reads(3, 5, 40, L, mode, U)
+            assert np.array_equal(a, b), (mode, L)
+            if mode < 2:
+                stride = nt.stride_words(L)
+                p = nt.gen_packed(3, 5, 40, L, mode, U, stride)
+                off = np.arange(41, dtype=np.uint32) * stride
+                assert unpack(p, off) == [bytes(a[i * L:(i + 1) * L]) for i in range(40)]
+
+
+def test_estimate_matches_golden():
+    for c in load_golden("compest_cases.json")["cases"]:
+        p = np.zeros((2, 65536), dtype=np.uint32)
+        for t, i, v in c["p_hist_nonzero"]:
+            p[t, i] = v
+        F0, f = nt.estimate(p_hist=p, rBits=c["rBits"], sBits=c["sBits"], covMax=1000)
+        assert F0 == c["F0"] and [float(x) for x in f[1:]] == c["f"]
+        assert f[0] == 0
+
+
+def test_estimate_from_counters_matches_oracle(oracle):
+    rs = np.random.RandomState(5)
+    sk = (rs.poisson(0.1, size=2 << 13) * rs.randint(1, 4, size=2 << 13)).astype(np.uint16)
+    F0, f = nt.estimate(t_counter=sk, rBits=13, sBits=7, covMax=200)
+    oF0, of = oracle.compest(sk, None, 13, 7, 200)
+    assert F0 == oF0 and np.array_equal(f[1:], of[1:201])
+
+
+def test_sbits_rule():
+    # ntcard.cpp:427-431
+    assert nt.apply_sbits_rule(49_999_999_999) == 7 and nt.apply_sbits_rule(50_000_000_000) == 11
+    assert nt.apply_sbits_rule(60_000_000_000, sBits=9) == 9

@@ -1,0 +1,196 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle and the golden
+fixtures on the same inputs.  Integer results (sketch counters, F1) must be bit-exact; F0 / f_i are
+computed by the product's own estimator and compared for equality with the oracle's compEst on the
+same sketch (tolerance 0 -- tighter than the 1e-6 relative the north star allows)."""
+import random
+
+import numpy as np
+import pytest
+
+import ntcard_b200 as nt
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [nt.KERNEL_ROLL64, nt.KERNEL_AUTO]
+
+
+def H(x):
+    return int(x, 16)
+
+
+def reads_of(case, oracle):
+    if "reads" in case:
+        return [r.encode("latin1") for r in case["reads"]]
+    g = case["gen"]
+    a = oracle.gen_reads(g["S"], 0, g["n"], g["L"], g["mode"], g["U"])
+    reads = [bytes(a[i * g["L"]:(i + 1) * g["L"]]) for i in range(g["n"])]
+    return reads * g.get("repeat", 1)
+
+
+def run_gpu(reads, kList, rBits, sBits, kernel, batches=1):
+    with nt.Sketch(kList, rBits=rBits, sBits=sBits) as sk:
+        sk.set_kernel(kernel)
+        step = (len(reads) + batches - 1) // batches
+        for b in range(0, len(reads), max(step, 1)):
+            sk.submit_reads(reads[b:b + step])
+        t, f1, p = sk.finish(counters=True, hist=True)
+    return t, f1, p
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", ["FX1", "small_r12_s3", "nmode_s7", "nmode_s11", "wrap_u16", "ragged_r16_s2"])
+def test_golden_sketch_cases(oracle, name, kernel):
+    case = next(c for c in load_golden("sketch_cases.json")["cases"] if c["name"] == name)
+    reads = reads_of(case, oracle)
+    rB = 1 << case["rBits"]
+    t, f1, p = run_gpu(reads, case["k"], case["rBits"], case["sBits"], kernel, batches=3)
+    assert [int(x) for x in f1] == case["F1"]
+    flat = t.reshape(-1, rB)
+    for i, gt in enumerate(case["tables"]):
+        tab = np.ascontiguousarray(flat[i])
+        d = oracle.table_digest(tab)
+        assert (d["nnz"], d["sum"], d["max"]) == (gt["nnz"], gt["sum"], gt["max"])
+        assert d["digest"] == H(gt["digest"])
+        assert np.array_equal(p.reshape(-1, 65536)[i], np.bincount(tab, minlength=65536))
+    for ki, ge in enumerate(case["est"]):
+        F0, f = nt.estimate(p_hist=p[ki], rBits=case["rBits"], sBits=case["sBits"], covMax=64)
+        assert F0 == ge["F0"] and [float(x) for x in f[1:]] == ge["f"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_random_ragged_vs_oracle(oracle, kernel):
+    rng = random.Random(77)
+    reads = []
+    for _ in range(4000):
+        L = rng.choice((0, 1, 11, 12, 31, 32, 33, 64, 65, 100, 150, 151, 300, 700, 2500))
+        reads.append(bytes(rng.choice(b"ACGTNacgtuX") if rng.random() < 0.02 else rng.choice(b"ACGT") for _ in range(L)))
+    for kList, rBits, sBits in (([12, 32, 33, 64, 128], 16, 3), ([31], 14, 1), ([20, 96], 18, 7)):
+        want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+        t, f1, _ = run_gpu(reads, kList, rBits, sBits, kernel, batches=2)
+        assert np.array_equal(f1, wf1)
+        assert np.array_equal(t.reshape(-1), want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_long_reads_with_n_vs_oracle(oracle, kernel):
+    # config 5 in miniature: 10 kbp reads with N runs, k=31, s=11 -> pieces with k-1 overlap
+    a = oracle.gen_reads(4, 0, 300, 10000, 2, 0)
+    reads = [bytes(a[i * 10000:(i + 1) * 10000]) for i in range(300)]
+    for sBits in (11, 4):
+        want, wf1 = oracle.sketch_reads(reads, [31, 250], 20, sBits, nthreads=4)
+        t, f1, _ = run_gpu(reads, [31, 250], 20, sBits, kernel)
+        assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_uniform_stride_batches(oracle, kernel):
+    # the packed uniform layout used by the bench (stride multiple of 4 words and not)
+    for L, mode, U in ((150, 0, 0), (150, 1, 500), (100, 1, 100), (64, 0, 0), (33, 0, 0)):
+        n = 6000
+        a = oracle.gen_reads(9, 0, n, L, mode, U)
+        reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+        kList = [k for k in (12, 32, 64) if k <= L] or [12]
+        want, wf1 = oracle.sketch_reads(reads, kList, 18, 5, nthreads=4)
+        for align4 in (True, False):
+            stride = nt.stride_words(L, align4)
+            words = nt.gen_packed(9, 0, n, L, mode, U, stride)
+            with nt.Sketch(kList, rBits=18, sBits=5) as sk:
+                sk.set_kernel(kernel)
+                sk.submit(words[: (n // 2) * stride], None, n // 2, stride)
+                sk.submit(words[(n // 2) * stride:], None, n - n // 2, stride)
+                t, f1, _ = sk.finish(counters=True, hist=False)
+            assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want), (L, mode, align4)
+
+
+def test_device_generator_and_device_submit(oracle):
+    import torch
+    L, n, U = 150, 50000, 5000
+    stride = nt.stride_words(L)
+    a = oracle.gen_reads(12, 100, n, L, 1, U)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, [32], 20, 7, nthreads=4)
+    d = torch.empty(n * stride, dtype=torch.int32, device="cuda")
+    with nt.Sketch([32], rBits=20, sBits=7) as sk:
+        sk.gen_packed_device(12, 100, n, L, 1, U, stride, d.data_ptr())
+        sk.submit_device(d.data_ptr(), n * stride, n, stride)
+        t, f1, _ = sk.finish(counters=True, hist=False)
+        host = nt.gen_packed(12, 100, n, L, 1, U, stride)
+        assert np.array_equal(d.cpu().numpy().view(np.uint32), host)
+    assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+
+
+def test_pinned_submit_external_counters_and_stream(oracle):
+    import torch
+    L, n = 150, 20000
+    stride = nt.stride_words(L)
+    a = oracle.gen_reads(2, 0, n, L, 0, 0)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, [32, 64], 20, 7, nthreads=4)
+    buf = nt.PinnedBuffer(n * stride)
+    nt.gen_packed(2, 0, n, L, 0, 0, stride, out=buf.array)
+    ctr = torch.full((2 * 2 << 20,), 7, dtype=torch.int32, device="cuda")   # garbage: ntc_create must zero it
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        with nt.Sketch([32, 64], rBits=20, sBits=7, d_counters=ctr.data_ptr(), stream=st.cuda_stream) as sk:
+            tk = sk.submit(buf.array, None, n, stride)
+            sk.wait(tk)
+            sk.sync()
+            p, cnt = sk.counters_device()
+            assert p == ctr.data_ptr() and cnt == ctr.numel()
+            st.synchronize()
+            dev = ctr.cpu().numpy().view(np.uint32)
+            assert np.array_equal((dev & 0xFFFF).astype(np.uint16), want)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+    buf.free()
+
+
+def test_empty_and_short_inputs():
+    with nt.Sketch([32], rBits=12, sBits=7) as sk:
+        sk.submit_reads([])
+        sk.submit_reads([b"", b"ACGT", b"N" * 100, b"ACGTACGTAC" * 3 + b"A"])   # all shorter than k after the split
+        t, f1, p = sk.finish(counters=True, hist=True)
+        assert int(f1[0]) == 0 and not t.any() and p[0, 0, 0] == 4096 and p[0, 1, 0] == 4096
+        F0, f = nt.estimate(p_hist=p[0], rBits=12, sBits=7, covMax=10)
+        assert F0 == 0 and not f.any()      # compEst early-out, ntcard.cpp:262-264
+
+
+def test_reset_and_reuse(oracle):
+    a = oracle.gen_reads(3, 0, 3000, 100, 0, 0)
+    reads = [bytes(a[i * 100:(i + 1) * 100]) for i in range(3000)]
+    want, wf1 = oracle.sketch_reads(reads, [20], 14, 2)
+    with nt.Sketch([20], rBits=14, sBits=2) as sk:
+        for _ in range(3):
+            sk.reset()
+            sk.submit_reads(reads)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+            assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_full_size_properties_config2(kernel):
+    """BASELINE config 2 at full size (10 M x 150 bp, k=32, s=7, r=27), device-resident input.
+    Size-independent properties: F1 is analytic; the sketch is additive over batches; the canonical
+    hash makes a read and its reverse complement indistinguishable, so a repeat-mode input whose
+    second half is the reverse complement of the first gives exactly twice the half sketch."""
+    import torch
+    L, n, k, stride = 150, 10_000_000, 32, nt.stride_words(150)
+    d = torch.empty(n * stride, dtype=torch.int32, device="cuda")
+    with nt.Sketch([k], rBits=27, sBits=7) as sk:
+        sk.set_kernel(kernel)
+        sk.gen_packed_device(1, 0, n, L, 1, n // 2, stride, d.data_ptr())     # read i+n/2 = revcomp(read i)
+        sk.submit_device(d.data_ptr(), n * stride, n, stride)
+        f1 = sk.totals()
+        assert int(f1[0]) == n * (L - k + 1)
+        t_full, _, p_full = sk.finish(counters=True, hist=True)
+        sk.reset()
+        half = n // 2
+        sk.submit_device(d.data_ptr(), half * stride, half, stride)
+        t_half, f1h, _ = sk.finish(counters=True, hist=False)
+        assert int(f1h[0]) == half * (L - k + 1)
+        assert np.array_equal(t_full, (t_half.astype(np.uint32) * 2).astype(np.uint16))
+        # estimator sanity on the full sketch: every distinct k-mer occurs exactly twice
+        F0, f = nt.estimate(p_hist=p_full[0], rBits=27, sBits=7, covMax=4)
+        distinct = half * (L - k + 1)
+        assert abs(F0 - distinct) / distinct < 0.02 and f[2] > 0.97 * distinct and f[1] < 0.01 * distinct
