@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers hashed/sec of the ntCard sketch path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU, NCCL
+
+Workload (config.workload): BASELINE config 2 -- 10 M synthetic 150 bp reads PER GPU, k=32, s=7
+(ntcard.cpp:430-431 forces s=7 below 50 GB), r=27; weak scaling, reads sharded over ranks, one
+all-reduce of the sketch at the end.  A step = one whole pass of the hot path over the shard:
+zero the sketch, hash+sample+increment every k-mer, (N>1) all-reduce counters and F1.
+  value : k-mers/s, packed reads already resident in HBM.
+  e2e   : the same through the C-ABI with HOST (pinned) buffers: H2D copies of the packed reads,
+          kernels, all-reduce, finish (narrow + counter-value histogram on device, D2H of the
+          histogram, host estimator) all inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (reads per GPU, L, kList, sBits, description)
+    "config2": (10_000_000, 150, [32], 7, "config 2: 10M synthetic 150 bp reads per GPU, k=32, s=7, r=27"),
+    "config3": (100_000_000, 150, [32, 64, 96, 128], 7, "config 3: 100M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27"),
+    "config4": (125_000_000, 150, [64], 11, "config 4: 125M synthetic 150 bp reads per GPU, k=64, s=11, r=27"),
+    "small": (1_000_000, 150, [32], 7, "dev: 1M synthetic 150 bp reads, k=32, s=7, r=27"),
+}
+RBITS = 27
+METRIC = "k-mers hashed/sec at k=32 on 150bp reads"
+UNIT = "k-mers/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], None, set(), []
+        for ts, line in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1]); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def cpu_arm(args, n_reads_full, L, kList, sBits, bounded_seconds=15.0):
+    """The reference's CPU hot loop (ntRead over reads held in RAM, OpenMP over reads on the shared
+    sketch: ntcard.cpp:147-158, 445-467) on this box's host cores.  Uses oracle/_ref (the unmodified
+    reference) when it was built, else the C restatement.  Returns a function step() -> (kmers, seconds)."""
+    import numpy as np
+    from oracle.pyoracle import Oracle, Reference
+    orc = Oracle()
+    threads = os.cpu_count() or 1
+    kind = "reference" if Reference.available() else "port"
+    ref = Reference() if kind == "reference" else None
+    # calibrate on 100k reads, then size the sample for ~bounded_seconds of CPU work (max: the full workload)
+    def run(n):
+        reads = orc.gen_reads(1, 0, n, L, 0, 0)
+        off = np.arange(n + 1, dtype=np.uint64) * L
+        sk = np.zeros(len(kList) * 2 << RBITS, dtype=np.uint16)
+        tot = np.zeros(len(kList), dtype=np.uint64)
+        t0 = time.perf_counter()
+        if ref is not None:
+            ref.set_opts(RBITS, sBits, len(kList))
+            ref.ntread_batch(reads, off, kList, sk, tot, threads)
+        else:
+            orc.ntread_batch(reads, off, kList, RBITS, sBits, sk, tot, threads)
+        return int(tot.sum()), time.perf_counter() - t0
+    km, dt = run(100_000)
+    rate = km / dt
+    per_read = sum(max(0, L - k + 1) for k in kList)
+    n = int(min(n_reads_full, max(100_000, rate * bounded_seconds / per_read)))
+    sample = f"{n} of the workload's {n_reads_full} reads per step ({per_read} k-mers/read), reads in RAM, sketch shared, OpenMP over reads"
+    return (lambda: run(n)), {"kind": kind, "cores": threads, "sample": sample}
+
+
+def reference_main(args, rank, world):
+    n_reads, L, kList, sBits, desc = WORKLOADS[args.workload]
+    if rank != 0:
+        return
+    step, info = cpu_arm(args, n_reads, L, kList, sBits, bounded_seconds=args.cpu_seconds)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    tot_k, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        km, dt = step()
+        tot_k += km
+        tot_t += dt
+    v = tot_k / tot_t
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": desc, "k": kList, "sBits": sBits, "rBits": RBITS, "read_len": L,
+                      "note": "CPU arm: rank 0 only, bounded sample per step"},
+           "cpu_baseline": dict(info, value=v, unit=UNIT),
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "roll64", "bitslice"])
+    ap.add_argument("--batches", type=int, default=1, help="launches per step on the device-resident leg")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="host batches per step on the e2e leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_main(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ntcard_b200 as nt
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    n_reads, L, kList, sBits, desc = WORKLOADS[args.workload]
+    nK = len(kList)
+    stride = nt.stride_words(L)
+    kmers_per_read = sum(max(0, L - k + 1) for k in kList)
+    kmers_rank = n_reads * kmers_per_read
+    alg_bytes_rank = n_reads * (4 + (L + 3) // 4)  # 4 + ceil(len/4) per record, read once for all k
+    kern = {"auto": nt.KERNEL_AUTO, "roll64": nt.KERNEL_ROLL64, "bitslice": nt.KERNEL_BITSLICE}[args.kernel]
+
+    st = torch.cuda.Stream(device=dev)
+    counters = torch.zeros(nK * 2 << RBITS, dtype=torch.int32, device=dev)
+    f1_dev = torch.zeros(nK, dtype=torch.int64, device=dev)
+    n_words = n_reads * stride
+    d_words = torch.empty(n_words, dtype=torch.int32, device=dev)
+    with torch.cuda.stream(st):
+        sk = nt.Sketch(kList, rBits=RBITS, sBits=sBits, device=local_rank, d_counters=counters.data_ptr(), stream=st.cuda_stream)
+        sk.set_kernel(kern)
+        first = rank * n_reads  # read i lives on GPU i // n_reads (SURVEY 8d config 4 sharding rule)
+        sk.gen_packed_device(1, first, n_reads, L, 0, 0, stride, d_words.data_ptr())
+        sk.sync()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        def reduce_sketch():
+            if world > 1:
+                dist.all_reduce(counters)  # uint32 sums mod 2^32; narrowed mod 2^16 at finish (exact)
+                tot = sk.totals()
+                f1_dev.copy_(torch.from_numpy(tot.astype(np.int64)), non_blocking=False)
+                dist.all_reduce(f1_dev)
+                sk.set_totals(f1_dev.cpu().numpy().astype(np.uint64))
+
+        nb = max(1, args.batches)
+        per = (n_reads + nb - 1) // nb
+
+        def step_resident():
+            sk.reset()
+            for b in range(nb):
+                r0 = b * per
+                r1 = min(n_reads, r0 + per)
+                sk.submit_device(d_words.data_ptr() + r0 * stride * 4, (r1 - r0) * stride, r1 - r0, stride)
+            reduce_sketch()
+
+        def timed(fn, steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            e0.record(st)
+            for _ in range(steps):
+                fn()
+            e1.record(st)
+            e1.synchronize()
+            barrier()
+            t1 = time.time()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item()), t0, t1
+
+        # ---- device-resident leg -------------------------------------------------------------------
+        for _ in range(args.warmup):
+            step_resident()
+        sk.sync()
+        sk.kernel_time()  # clear
+        l0 = sk.stats()["launches"]
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+            time.sleep(0.3)
+        ms_total, t0, t1 = timed(step_resident, args.steps)
+        sk.sync()
+        kms, n_timed = sk.kernel_time()
+        launches = sk.stats()["launches"] - l0
+        clk = clocks.stop(t0, t1) if rank == 0 else None
+        ms_per_step = ms_total / args.steps
+        value = world * kmers_rank / (ms_per_step * 1e-3)
+        tot = sk.totals()
+        assert int(tot.sum()) == kmers_rank * (world if world > 1 else 1), (tot, kmers_rank)
+
+        # ---- e2e leg: host buffers through the C-ABI ------------------------------------------------
+        e2e = None
+        if not args.no_e2e:
+            pinned = nt.PinnedBuffer(n_words)
+            torch.cuda.synchronize(dev)
+            host_view = torch.from_numpy(pinned.array.view(np.int32))
+            host_view.copy_(d_words)  # same bits as the device-resident leg, now in pinned HOST memory
+            nchunk = max(1, args.e2e_chunks)
+            cper = (n_reads + nchunk - 1) // nchunk
+            result = {}
+
+            def step_e2e():
+                sk.reset()
+                for c in range(nchunk):
+                    r0 = c * cper
+                    r1 = min(n_reads, r0 + cper)
+                    sk.submit(pinned.array[r0 * stride:r1 * stride], None, r1 - r0, stride)
+                reduce_sketch()
+                if rank == 0:
+                    _, f1, p = sk.finish(counters=False, hist=True)
+                    result["F1"] = f1
+                    result["est"] = [nt.estimate(p_hist=p[ki], rBits=RBITS, sBits=sBits, covMax=1000) for ki in range(nK)]
+                else:
+                    sk.sync()
+
+            for _ in range(2):
+                step_e2e()
+            esteps = max(3, min(args.steps, 10))
+            ems, _, _ = timed(step_e2e, esteps)
+            e2e = {"value": world * kmers_rank / (ems / esteps * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": int(n_words * 4), "d2h_bytes_per_step": int(nK * 2 * 65536 * 4 + 8 * nK),
+                   "ms_per_step": ems / esteps, "chunks": nchunk}
+            if rank == 0:
+                F0, f = result["est"][0]
+                distinct = world * n_reads * (L - kList[0] + 1)
+                e2e["F1"] = [int(x) for x in result["F1"]]
+                e2e["F0"] = F0
+                e2e["F0_rel_err_vs_distinct"] = abs(F0 - distinct) / distinct
+            pinned.free()
+        sk.close()
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        kernel_ms = kms / max(n_timed, 1)
+        per_launch_bytes = alg_bytes_rank / nb
+        achieved = per_launch_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            with open(prof) as f:
+                traffic = json.load(f).get(args.workload)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": desc, "reads_per_gpu": n_reads, "read_len": L, "k": kList, "sBits": sBits, "rBits": RBITS,
+                       "kernel": args.kernel, "launches_per_step": nb, "sharding": f"reads split over {world} GPU(s), one sketch all-reduce",
+                       "l2": "no flush needed: per-step inputs (480 MB packed reads + 1 GiB sketch per k) exceed the 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": per_launch_bytes,
+                         "kernel_kmers_per_s": kmers_rank / nb / (kernel_ms * 1e-3),
+                         "note": "algorithmic bytes = sum(4 + ceil(len/4)) per record; kernel_ms = CUDA events around the sketch kernel(s) of each launch"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                step, info = cpu_arm(args, n_reads, L, kList, sBits, bounded_seconds=args.cpu_seconds)
+                km, dt = step()
+                out["cpu_baseline"] = dict(info, value=km / dt, unit=UNIT)
+            except Exception as e:  # the baseline is reporting, never the product path
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
