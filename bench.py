@@ -174,6 +174,7 @@ def main():
     import torch.distributed as dist
 
     import ntcard_b200 as nt
+    from ntcard_b200.dist import all_reduce_sketch
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
@@ -193,7 +194,6 @@ def main():
 
     st = torch.cuda.Stream(device=dev)
     counters = torch.zeros(nK * 2 << RBITS, dtype=torch.int32, device=dev)
-    f1_dev = torch.zeros(nK, dtype=torch.int64, device=dev)
     n_words = n_reads * stride
     d_words = torch.empty(n_words, dtype=torch.int32, device=dev)
     with torch.cuda.stream(st):
@@ -210,11 +210,8 @@ def main():
 
         def reduce_sketch():
             if world > 1:
-                dist.all_reduce(counters)  # uint32 sums mod 2^32; narrowed mod 2^16 at finish (exact)
-                tot = sk.totals()
-                f1_dev.copy_(torch.from_numpy(tot.astype(np.int64)), non_blocking=False)
-                dist.all_reduce(f1_dev)
-                sk.set_totals(f1_dev.cpu().numpy().astype(np.uint64))
+                # uint32 sums mod 2^32, narrowed mod 2^16 at finish (exact); F1 summed alongside
+                sk.set_totals(all_reduce_sketch(counters, sk.totals()))
 
         nb = max(1, args.batches)
         per = (n_reads + nb - 1) // nb

@@ -1,0 +1,352 @@
+// reader.cpp -- see reader.h.
+#include "reader.h"
+
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+namespace ntcb {
+
+static bool ends_with(const std::string& s, const char* suf)
+{
+	size_t n = strlen(suf);
+	return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+static std::string shell_quote(const std::string& s)
+{
+	std::string q = "'";
+	for (char c : s) {
+		if (c == '\'')
+			q += "'\\''";
+		else
+			q += c;
+	}
+	return q + "'";
+}
+
+LineReader::LineReader(const std::string& path)
+{
+	const char* tool = nullptr;
+	if (ends_with(path, ".gz") || ends_with(path, ".Z"))
+		tool = "gunzip -c ";
+	else if (ends_with(path, ".bz2"))
+		tool = "bunzip2 -c ";
+	else if (ends_with(path, ".xz"))
+		tool = "xz -dc ";
+	if (tool) {
+		FILE* probe = fopen(path.c_str(), "rb");
+		if (!probe)
+			return;
+		fclose(probe);
+		fp_ = popen((std::string(tool) + shell_quote(path)).c_str(), "r");
+		pipe_ = true;
+	} else {
+		fp_ = fopen(path.c_str(), "rb");
+	}
+	cap_ = (size_t)4 << 20;
+	buf_ = (char*)malloc(cap_);
+}
+
+LineReader::~LineReader()
+{
+	if (fp_) {
+		if (pipe_)
+			pclose(fp_);
+		else
+			fclose(fp_);
+	}
+	free(buf_);
+}
+
+bool LineReader::fill()
+{
+	if (eof_)
+		return false;
+	if (beg_ > 0) {
+		memmove(buf_, buf_ + beg_, end_ - beg_);
+		end_ -= beg_;
+		beg_ = 0;
+	}
+	if (end_ == cap_) { // a line longer than the buffer (FASTA chromosomes on one line)
+		cap_ *= 2;
+		buf_ = (char*)realloc(buf_, cap_);
+	}
+	size_t n = fread(buf_ + end_, 1, cap_ - end_, fp_);
+	if (n == 0) {
+		eof_ = true;
+		return false;
+	}
+	end_ += n;
+	return true;
+}
+
+bool LineReader::next(const char** line, size_t* len)
+{
+	if (!fp_)
+		return false;
+	size_t scanned = 0;
+	for (;;) {
+		char* nl = (char*)memchr(buf_ + beg_ + scanned, '\n', end_ - beg_ - scanned);
+		if (nl) {
+			*line = buf_ + beg_;
+			*len = (size_t)(nl - (buf_ + beg_));
+			beg_ = (size_t)(nl - buf_) + 1;
+			return true;
+		}
+		scanned = end_ - beg_;
+		if (!fill()) {
+			if (end_ > beg_) { // last line without a trailing newline
+				*line = buf_ + beg_;
+				*len = end_ - beg_;
+				beg_ = end_;
+				return true;
+			}
+			return false;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+BatchSubmitter::BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer)
+    : ctx_(ctx), min_len_(min_len), mu_(submit_mu)
+{
+	for (auto& b : buf_)
+		alloc(b, words_per_buffer, words_per_buffer / 4);
+}
+
+BatchSubmitter::~BatchSubmitter()
+{
+	for (auto& b : buf_)
+		release(b);
+}
+
+void BatchSubmitter::alloc(Buf& b, size_t words, size_t recs)
+{
+	b.words = (uint32_t*)ntc_host_alloc(words * sizeof(uint32_t));
+	b.off = (uint32_t*)ntc_host_alloc((recs + 1) * sizeof(uint32_t));
+	if (!b.words || !b.off) {
+		std::cerr << "ntCard: cannot allocate pinned host memory: " << ntc_last_error() << "\n";
+		exit(EXIT_FAILURE);
+	}
+	b.cap_words = words;
+	b.cap_rec = recs;
+	b.n_words = b.n_rec = 0;
+	b.ticket = 0;
+}
+
+void BatchSubmitter::release(Buf& b)
+{
+	ntc_host_free(b.words);
+	ntc_host_free(b.off);
+	b.words = b.off = nullptr;
+}
+
+void BatchSubmitter::add(const char* seq, size_t len)
+{
+	if (len < min_len_)
+		return; // no window fits (ntHashIterator.hpp:61-64)
+	for (int attempt = 0; attempt < 3; attempt++) {
+		Buf& b = buf_[cur_];
+		const uint64_t so[2] = { 0, (uint64_t)len };
+		size_t consumed = 0;
+		int rc = ntc_pack_seqs(seq, so, 1, min_len_, b.words, b.cap_words, &b.n_words, b.off, b.cap_rec, &b.n_rec, &consumed);
+		if (rc == NTC_OK)
+			return;
+		if (rc != NTC_ENOMEM) {
+			std::cerr << "ntCard: " << ntc_last_error() << "\n";
+			exit(EXIT_FAILURE);
+		}
+		if (b.n_rec > 0) {
+			flush(); // full: submit and continue in the other buffer
+			continue;
+		}
+		// a single sequence larger than an empty buffer (e.g. a chromosome): grow this buffer
+		size_t need_w = ntc_pack_bound(1, len), need_r = len / (min_len_ ? min_len_ : 1) + 2;
+		if (b.ticket && ntc_wait(ctx_, b.ticket)) {
+			std::cerr << "ntCard: " << ntc_last_error() << "\n";
+			exit(EXIT_FAILURE);
+		}
+		release(b);
+		alloc(b, need_w > b.cap_words ? need_w : b.cap_words, need_r > b.cap_rec ? need_r : b.cap_rec);
+	}
+	std::cerr << "ntCard: internal error: sequence does not fit the batch buffer\n";
+	exit(EXIT_FAILURE);
+}
+
+void BatchSubmitter::flush()
+{
+	Buf& b = buf_[cur_];
+	if (b.n_rec > 0) {
+		std::lock_guard<std::mutex> lk(*mu_);
+		if (ntc_submit(ctx_, b.words, b.n_words, b.off, b.n_rec, 0, &b.ticket)) {
+			std::cerr << "ntCard: submit failed: " << ntc_last_error() << "\n";
+			exit(EXIT_FAILURE);
+		}
+	}
+	cur_ ^= 1;
+	Buf& n = buf_[cur_];
+	if (n.ticket) { // the DMA engine may still be reading the buffer we are about to refill
+		std::lock_guard<std::mutex> lk(*mu_);
+		if (ntc_wait(ctx_, n.ticket)) {
+			std::cerr << "ntCard: " << ntc_last_error() << "\n";
+			exit(EXIT_FAILURE);
+		}
+		n.ticket = 0;
+	}
+	n.n_words = n.n_rec = 0;
+}
+
+void BatchSubmitter::finish()
+{
+	std::lock_guard<std::mutex> lk(*mu_);
+	for (auto& b : buf_)
+		if (b.ticket) {
+			ntc_wait(ctx_, b.ticket);
+			b.ticket = 0;
+		}
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool all_digits(const std::string& s) // isNumber, ntcard.cpp:96-103
+{
+	if (s.empty())
+		return false;
+	for (unsigned char c : s)
+		if (!isdigit(c))
+			return false;
+	return true;
+}
+
+// whitespace-separated token `idx` (0-based) of a line; false if the line has fewer tokens
+static bool token_at(const char* line, size_t len, unsigned idx, const char** tok, size_t* tlen)
+{
+	size_t i = 0;
+	for (unsigned t = 0;; t++) {
+		while (i < len && isspace((unsigned char)line[i]))
+			i++;
+		if (i >= len)
+			return false;
+		size_t j = i;
+		while (j < len && !isspace((unsigned char)line[j]))
+			j++;
+		if (t == idx) {
+			*tok = line + i;
+			*tlen = j - i;
+			return true;
+		}
+		i = j;
+	}
+}
+
+// FASTQ body after the first header was consumed by the sniffer (getEfq, ntcard.cpp:173-189): a
+// record is hashed only when its quality line could be read.
+static void read_fastq(LineReader& in, BatchSubmitter& sub)
+{
+	std::string seq;
+	const char* l;
+	size_t n;
+	for (;;) {
+		if (!in.next(&l, &n))
+			return;
+		seq.assign(l, n);
+		if (!in.next(&l, &n)) // '+'
+			return;
+		if (!in.next(&l, &n)) // quality
+			return;
+		sub.add(seq.data(), seq.size());
+		if (!in.next(&l, &n)) // next header
+			return;
+	}
+}
+
+// FASTA (getEfa, ntcard.cpp:191-208): lines up to the next '>' are concatenated into one sequence.
+static void read_fasta(LineReader& in, BatchSubmitter& sub)
+{
+	std::string seq;
+	const char* l;
+	size_t n;
+	bool good = true;
+	while (good) {
+		seq.clear();
+		good = in.next(&l, &n);
+		while (good && !(n > 0 && l[0] == '>')) {
+			seq.append(l, n);
+			good = in.next(&l, &n);
+		}
+		sub.add(seq.data(), seq.size());
+	}
+}
+
+// SAM (getEsm, ntcard.cpp:210-235): column 10 of every alignment line.  `seq` persists across
+// lines: a line with fewer than 10 fields leaves it unchanged and the previous sequence is hashed
+// again, exactly as the reference's `iss >> ... >> seq` does.
+static void read_sam(LineReader& in, BatchSubmitter& sub, bool has_header, const std::string& first_line)
+{
+	std::string line, seq;
+	const char* l;
+	size_t n;
+	if (has_header) {
+		bool got = false;
+		while (in.next(&l, &n)) {
+			if (!(n > 0 && l[0] == '@')) {
+				line.assign(l, n);
+				got = true;
+				break;
+			}
+		}
+		if (!got)
+			return;
+	} else {
+		line = first_line;
+	}
+	for (;;) {
+		const char* tok;
+		size_t tlen;
+		if (token_at(line.data(), line.size(), 9, &tok, &tlen))
+			seq.assign(tok, tlen);
+		sub.add(seq.data(), seq.size());
+		if (!in.next(&l, &n))
+			return;
+		line.assign(l, n);
+	}
+}
+
+bool read_file(const std::string& path, BatchSubmitter& sub)
+{
+	LineReader in(path);
+	if (!in.ok())
+		return false;
+	const char* l;
+	size_t n;
+	std::string h;
+	if (in.next(&l, &n))
+		h.assign(l, n);
+	// getftype, ntcard.cpp:105-130
+	if (!h.empty() && h[0] == '>') {
+		read_fasta(in, sub);
+		return true;
+	}
+	if (!h.empty() && h[0] == '@') {
+		const char a = h.size() > 1 ? h[1] : 0, b = h.size() > 2 ? h[2] : 0;
+		if ((a == 'H' && b == 'D') || (a == 'S' && b == 'Q') || (a == 'R' && b == 'G') || (a == 'P' && b == 'G') ||
+		    (a == 'C' && b == 'O')) {
+			read_sam(in, sub, true, h);
+		} else {
+			read_fastq(in, sub);
+		}
+		return true;
+	}
+	const char *t2, *t5;
+	size_t n2, n5;
+	if (token_at(h.data(), h.size(), 1, &t2, &n2) && token_at(h.data(), h.size(), 4, &t5, &n5) &&
+	    all_digits(std::string(t2, n2)) && all_digits(std::string(t5, n5))) {
+		read_sam(in, sub, false, h);
+		return true;
+	}
+	return false;
+}
+
+} // namespace ntcb

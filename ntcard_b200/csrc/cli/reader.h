@@ -1,0 +1,64 @@
+// reader.h -- host ingest of the ntcard CLI: FASTQ / FASTA / SAM parsing with the reference's
+// record rules (ntcard.cpp:105-130 getftype, 173-189 getEfq, 191-208 getEfa, 210-235 getEsm), then
+// N-split + 2-bit packing into pinned double buffers and batch submission through the C-ABI.
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "ntcard_b200.h"
+
+namespace ntcb {
+
+// Buffered line reader over a file or a decompressor pipe (gz/bz2/xz by extension, like the
+// reference's fopen hook, Common/Uncompress.cpp:46-67).  next() has std::getline semantics: returns
+// false only at EOF with nothing read; the line excludes the '\n' (a '\r' is kept).
+class LineReader {
+public:
+	explicit LineReader(const std::string& path);
+	~LineReader();
+	bool ok() const { return fp_ != nullptr; }
+	bool next(const char** line, size_t* len);
+
+private:
+	bool fill();
+	FILE* fp_ = nullptr;
+	bool pipe_ = false;
+	char* buf_ = nullptr;
+	size_t cap_ = 0, beg_ = 0, end_ = 0;
+	bool eof_ = false;
+};
+
+// Packs sequences into two pinned buffers alternately and submits full ones (asynchronously).
+class BatchSubmitter {
+public:
+	BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer = (size_t)8 << 20);
+	~BatchSubmitter();
+	void add(const char* seq, size_t len); // == one ntRead(seq, ...) call of the reference
+	void flush();                           // submit what is buffered
+	void finish();                          // wait until the device no longer needs our buffers
+
+private:
+	struct Buf {
+		uint32_t* words = nullptr;
+		uint32_t* off = nullptr;
+		size_t cap_words = 0, cap_rec = 0;
+		size_t n_words = 0, n_rec = 0;
+		uint64_t ticket = 0;
+	};
+	void alloc(Buf& b, size_t words, size_t recs);
+	void release(Buf& b);
+	ntc_ctx* ctx_;
+	unsigned min_len_;
+	std::mutex* mu_;
+	Buf buf_[2];
+	int cur_ = 0;
+};
+
+// Sniff the format on the first line and feed every sequence of the file to `sub`.
+// Returns false when the format is not recognised / the file cannot be read (ntcard.cpp:459-462).
+bool read_file(const std::string& path, BatchSubmitter& sub);
+
+} // namespace ntcb

@@ -1,0 +1,142 @@
+"""The `ntcard` command line (bin/ntcard): option handling on CPU, and -- on the GPU -- byte-identical
+.hist / compact output against what the unmodified reference CLI printed for the same files
+(tests/golden/cli_cases.json, written by oracle/make_golden.py)."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+import ntcard_b200 as nt
+from conftest import ROOT, load_golden
+
+CLI = os.path.join(ROOT, "bin", "ntcard")
+
+
+def run(args, cwd=None):
+    return subprocess.run([CLI] + args, capture_output=True, text=True, cwd=cwd)
+
+
+def test_cli_built():
+    assert os.path.exists(CLI), "bin/ntcard missing: run __graft_entry__.build()"
+
+
+def test_cli_usage_errors(tmp_path):
+    # messages and exit codes of ntcard.cpp:372-405
+    r = run(["-k32", "x.fq"])
+    assert r.returncode == 1 and "missing argument -p/-o" in r.stderr and "Try `ntCard --help'" in r.stderr
+    r = run(["-p", "o", "x.fq"])
+    assert r.returncode == 1 and "missing argument -k" in r.stderr
+    r = run(["-k32", "-p", "o"])
+    assert r.returncode == 1 and "missing arguments" in r.stderr
+    r = run(["-k32", "-p", "o", "-t", "abc", "x.fq"])
+    assert r.returncode == 1 and "invalid option: `-tabc'" in r.stderr
+    r = run(["--help"])
+    assert r.returncode == 0 and "Usage: ntCard [OPTION]... FILE(S)..." in r.stderr
+    r = run(["--version"])
+    assert r.returncode == 0 and "ntCard 1.2.2" in r.stderr
+    r = run(["-k12", "-g", "2", "-p", "o", "x.fq"])
+    assert r.returncode == 1 and "gap" in r.stderr
+
+
+def write_inputs(td, cases):
+    L = cases["gen_a"]["L"]
+    a = nt.gen_ascii(cases["gen_a"]["S"], 0, cases["gen_a"]["n"], L, cases["gen_a"]["mode"], cases["gen_a"]["U"])
+    reads = [bytes(a[i * L:(i + 1) * L]).decode() for i in range(cases["gen_a"]["n"])]
+    Ln = cases["gen_n"]["L"]
+    b = nt.gen_ascii(cases["gen_n"]["S"], 0, cases["gen_n"]["n"], Ln, cases["gen_n"]["mode"], cases["gen_n"]["U"])
+    nreads = [bytes(b[i * Ln:(i + 1) * Ln]).decode() for i in range(cases["gen_n"]["n"])]
+    p = {k: os.path.join(td, k) for k in ("a.fq", "a.fa", "a.sam", "n.fq", "a.fq.gz", "a_lower_rna.fa", "list.txt", "a_crlf.fq")}
+    with open(p["a.fq"], "w") as f:
+        for i, r in enumerate(reads):
+            f.write(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n")
+    with gzip.open(p["a.fq.gz"], "wt") as f:
+        for i, r in enumerate(reads):
+            f.write(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n")
+    with open(p["a_crlf.fq"], "w", newline="") as f:
+        for i, r in enumerate(reads):
+            f.write(f"@r{i}\r\n{r}\r\n+\r\n{'I' * len(r)}\r\n")
+    with open(p["a.fa"], "w") as f:
+        for i, r in enumerate(reads):
+            f.write(f">r{i}\n" + "\n".join(r[j:j + 60] for j in range(0, len(r), 60)) + "\n")
+    with open(p["a_lower_rna.fa"], "w") as f:
+        for i, r in enumerate(reads):
+            f.write(f">r{i}\n{r.lower().replace('t', 'u')}\n")
+    with open(p["a.sam"], "w") as f:
+        f.write("@HD\tVN:1.6\n@SQ\tSN:x\tLN:100\n")
+        for i, r in enumerate(reads):
+            f.write(f"r{i}\t4\t*\t0\t0\t*\t*\t0\t0\t{r}\t{'I' * len(r)}\n")
+    with open(p["n.fq"], "w") as f:
+        for i, r in enumerate(nreads):
+            f.write(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n")
+    with open(p["list.txt"], "w") as f:
+        f.write(p["a.fq"] + "\n" + p["n.fq"] + "\n")
+    return p
+
+
+def hists(td, prefix="out"):
+    out = {}
+    for fn in sorted(os.listdir(td)):
+        if fn.startswith(prefix + "_k") and fn.endswith(".hist"):
+            with open(os.path.join(td, fn)) as f:
+                out[fn[len(prefix) + 1:]] = f.read()
+            os.remove(os.path.join(td, fn))
+    return out
+
+
+@pytest.mark.gpu
+def test_cli_matches_reference_cli(tmp_path):
+    cases = load_golden("cli_cases.json")["cases"]
+    td = str(tmp_path)
+    p = write_inputs(td, cases)
+    pref = os.path.join(td, "out")
+    for inp in ("a.fq", "a.fa", "a.sam", "a.fq.gz", "a_lower_rna.fa", "a_crlf.fq"):
+        r = run(["-k12,32", "-c50", "-p", pref, p[inp]])
+        assert r.returncode == 0, r.stderr
+        assert "Runtime(sec): " in r.stderr
+        assert hists(td) == cases["fq_k12_k32_c50"], inp
+    r = run(["-k31", "-c20", "-p", pref, p["n.fq"]])
+    assert r.returncode == 0 and hists(td) == cases["nfq_k31_c20"]
+    for args in (["-t2", p["a.fq"], p["n.fq"]], ["-t", "4", "@" + p["list.txt"]], [p["n.fq"], p["a.fq"]]):
+        r = run(["-k64", "-c20", "-p", pref] + args)
+        assert r.returncode == 0 and hists(td) == cases["two_files_t2_k64_c20"]
+    o = os.path.join(td, "compact.tsv")
+    r = run(["-k12,64", "-c8", "-o", o, p["a.fq"]])
+    assert r.returncode == 0
+    assert open(o).read() == cases["compact_k12_k64_c8"]["file"]
+    err = "".join(l + "\n" for l in r.stderr.splitlines() if not l.startswith("Runtime"))
+    assert err == cases["compact_k12_k64_c8"]["stderr"]
+    # both kernels give the same files
+    for kern in ("1", "2"):
+        r = run(["-k12,32", "-c50", "--kernel", kern, "-p", pref, p["a.fq"]])
+        assert r.returncode == 0 and hists(td) == cases["fq_k12_k32_c50"]
+
+
+@pytest.mark.gpu
+def test_cli_unreadable_file(tmp_path):
+    bad = os.path.join(str(tmp_path), "bad.txt")
+    with open(bad, "w") as f:
+        f.write("this is not a sequence file\n")
+    r = run(["-k12", "-p", os.path.join(str(tmp_path), "o"), bad])
+    assert r.returncode == 1 and "Error in reading file: " + bad in r.stderr     # ntcard.cpp:459-462
+
+
+@pytest.mark.gpu
+def test_golden_hist_layout(tmp_path):
+    """BASELINE config 1 substitute: the bundled data/test_k12.hist.good cannot
+    be reproduced (its input is a network download), so check our k=12 output has its exact layout:
+    1002 lines, 'F1', 'F0', rows 1..1000, tab separated non-negative integers."""
+    td = str(tmp_path)
+    a = nt.gen_ascii(1, 0, 5000, 100, 1, 1000)
+    fq = os.path.join(td, "t.fq")
+    with open(fq, "w") as f:
+        for i in range(5000):
+            f.write(f"@r{i}\n{bytes(a[i * 100:(i + 1) * 100]).decode()}\n+\n{'I' * 100}\n")
+    r = run(["-k12", "-p", os.path.join(td, "test"), fq])
+    assert r.returncode == 0
+    lines = open(os.path.join(td, "test_k12.hist")).read().split("\n")
+    assert len(lines) == 1003 and lines[-1] == ""
+    assert lines[0] == f"F1\t{5000 * 89}" and lines[1].startswith("F0\t")
+    for i in range(1, 1001):
+        a_, b_ = lines[i + 1].split("\t")
+        assert int(a_) == i and int(b_) >= 0
