@@ -8,7 +8,11 @@ CXXFLAGS = -O3 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off
 SRC = ntcard_b200/csrc
 BUILD = build
 
-CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(wildcard $(SRC)/bitslice_kernel.cu)
+# k mod 31 variants of the bit-sliced kernel to compile (each is one translation unit)
+BS_KMS ?= 0 1 2 3 4 12
+BS_KM_LIST = $(foreach n,$(BS_KMS),X($(n)))
+CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(SRC)/bitslice_dispatch.cu
+BS_OBJS = $(foreach n,$(BS_KMS),$(BUILD)/bitslice_km$(n).o)
 CPP_SRCS = $(SRC)/host_util.cpp
 CU_OBJS = $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS))
 CPP_OBJS = $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS))
@@ -17,6 +21,15 @@ LIB = ntcard_b200/libntcard_b200.so
 CLI_SRCS = $(wildcard $(SRC)/cli/*.cpp)
 
 all: $(LIB) cli
+
+$(BUILD)/bitslice_km%.o: $(SRC)/bitslice_inst.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -DBS_KM=$* -c $< -o $@ 2> $(BUILD)/bitslice_km$*.ptxas.log || (cat $(BUILD)/bitslice_km$*.ptxas.log; exit 1)
+	@grep -E "error|warning|spill|registers" $(BUILD)/bitslice_km$*.ptxas.log | grep -v "0 bytes spill" | head -8 || true
+
+$(BUILD)/bitslice_dispatch.o: $(SRC)/bitslice_dispatch.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) '-DBS_KM_LIST=$(BS_KM_LIST)' -c $< -o $@
 
 $(BUILD)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(BUILD)
@@ -27,7 +40,7 @@ $(BUILD)/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(CU_OBJS) $(CPP_OBJS)
+$(LIB): $(CU_OBJS) $(BS_OBJS) $(CPP_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -Xlinker --exclude-libs,ALL
 
 ifneq ($(CLI_SRCS),)

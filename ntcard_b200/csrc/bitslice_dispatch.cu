@@ -1,0 +1,58 @@
+// bitslice_dispatch.cu -- picks the compiled (k mod 31) variant; builds the hit-path byte tables.
+// BS_KM_LIST is the list of compiled variants, e.g. -DBS_KM_LIST="X(0) X(1) X(2)".
+#include "bitslice_launch.h"
+#include "nthash_device.cuh"
+
+#ifndef BS_KM_LIST
+#define BS_KM_LIST
+#endif
+
+namespace ntc {
+namespace bs {
+
+#define X(n) cudaError_t launch_km_##n(unsigned sBits, const BsArgs& a);
+BS_KM_LIST
+#undef X
+
+bool have_kernel(unsigned k, unsigned sBits)
+{
+	if (sBits != 7 && sBits != 11)
+		return false;
+	switch (k % 31) {
+#define X(n) case n: return true;
+		BS_KM_LIST
+#undef X
+	default: return false;
+	}
+}
+
+cudaError_t launch(unsigned k, unsigned sBits, const BsArgs& a)
+{
+	switch (k % 31) {
+#define X(n) case n: return launch_km_##n(sBits, a);
+		BS_KM_LIST
+#undef X
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+void build_tables(uint32_t* tab)
+{
+	for (unsigned j = 0; j < 8; j++)
+		for (unsigned b = 0; b < 256; b++) {
+			uint64_t fb = 0, rb = 0;
+			for (unsigned u = 0; u < 4; u++) {
+				const unsigned code = (b >> (2 * u)) & 3, i = 4 * j + u;
+				fb ^= srol_n(seed_of(code), 31 - i);
+				rb ^= srol_n(seed_of(3 - code), i);
+			}
+			uint32_t* e = tab + (j * 256 + b) * 4;
+			e[0] = (uint32_t)fb;
+			e[1] = (uint32_t)(fb >> 32);
+			e[2] = (uint32_t)rb;
+			e[3] = (uint32_t)(rb >> 32);
+		}
+}
+
+} // namespace bs
+} // namespace ntc

@@ -1,0 +1,26 @@
+// bitslice_inst.cu -- one translation unit per k mod 31 (compiled with -DBS_KM=<0..30>), so the 31
+// unrolled variants build in parallel.  Each instantiates the kernel for sBits = 7 and 11, the two
+// values the reference can reach without its hidden -s flag (ntcard.cpp:58, 430-431).
+#include "bitslice_kernel.cuh"
+
+#ifndef BS_KM
+#error "compile with -DBS_KM=<k mod 31>"
+#endif
+
+#define BS_CAT2(a, b) a##b
+#define BS_CAT(a, b) BS_CAT2(a, b)
+
+namespace ntc {
+namespace bs {
+
+cudaError_t BS_CAT(launch_km_, BS_KM)(unsigned sBits, const BsArgs& a)
+{
+	if (sBits == 7)
+		return launch_one<BS_KM, 7>(a);
+	if (sBits == 11)
+		return launch_one<BS_KM, 11>(a);
+	return cudaErrorInvalidValue;
+}
+
+} // namespace bs
+} // namespace ntc

@@ -1,0 +1,40 @@
+// bitslice_launch.h -- host-side launch interface of the bit-sliced kernel (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ntc {
+struct DevParams;
+namespace bs {
+
+struct BsLaunch {          // per-k launch constants, passed by value
+	uint32_t k, ki, rBits, pos_cap; // pos_cap: positions the shared-memory planes of one warp can hold
+	uint32_t F0[31], R0[31];        // initial bit-sliced state (bitslice_core.cuh init_state)
+};
+
+struct BsArgs {
+	const uint32_t* words;
+	uint32_t stride, n_rec;
+	BsLaunch L;
+	const uint4* d_tab;             // [8][256] byte tables of the hit path
+	const DevParams* d_params;
+	uint32_t* ctr_k;                // counters of this k: [2][2^rBits]
+	unsigned long long* f1_k;
+	unsigned grid, warps;
+	size_t smem_bytes;
+	cudaStream_t stream;
+};
+
+constexpr size_t kTabBytes = 8 * 256 * 16;
+constexpr size_t kPerWarpFixed = 31 * 128 + 1024 * 4; // mask buffer + hit queue
+constexpr size_t kSmemMax = 232448;                   // 227 KB opt-in limit per CTA on sm_100
+
+// True when a kernel for (k mod 31, sBits) was compiled in.
+bool have_kernel(unsigned k, unsigned sBits);
+// Launch for one k.  Returns cudaErrorInvalidValue when no instantiation exists.
+cudaError_t launch(unsigned k, unsigned sBits, const BsArgs& a);
+// Fill the hit-path byte tables (host): tab[j*256+b] = {FB lo, FB hi, RB lo, RB hi}.
+void build_tables(uint32_t* tab /* 8*256*4 words */);
+
+} // namespace bs
+} // namespace ntc

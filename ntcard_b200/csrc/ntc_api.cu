@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "../../include/ntcard_b200.h"
+#include "bitslice_core.cuh"
+#include "bitslice_launch.h"
 #include "internal.h"
 #include "launch.h"
 #include "sketch_common.cuh"
@@ -57,6 +59,8 @@ struct ntc_ctx {
 	size_t n_counters = 0;
 	unsigned long long* d_f1 = nullptr;
 	ntc::DevParams* d_params = nullptr;
+	uint4* d_bs_tab = nullptr;            // hit-path byte tables of the bit-sliced kernel
+	ntc::bs::BsLaunch bs_launch[NTC_MAX_K]; // per-k constants of the bit-sliced kernel
 	bool totals_overridden = false;
 	uint64_t totals[NTC_MAX_K] = {};
 	Stage stage[NBUF];
@@ -139,6 +143,41 @@ void build_params(const ntc_ctx* c, ntc::DevParams* P)
 	}
 }
 
+// Which k indices the bit-sliced kernel can take for this batch; plane capacity / warps per CTA in *cfg.
+struct BsConfig {
+	uint32_t kmask = 0, warps = 0, pos_cap = 0;
+	size_t smem = 0;
+};
+
+BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
+{
+	BsConfig cfg;
+	if (c->kernel == NTC_KERNEL_ROLL64 || b.off || !record_is_piece || b.stride < 4 || (b.stride & 3u) ||
+	    b.n_rec < 1024 || (reinterpret_cast<uintptr_t>(b.words) & 15u))
+		return cfg;
+	for (unsigned ki = 0; ki < c->nK; ki++)
+		if (ntc::bs::have_kernel(c->k[ki], c->sBits))
+			cfg.kmask |= 1u << ki;
+	if (!cfg.kmask)
+		return cfg;
+	// planes of one warp hold pos_cap positions; 4 warps per CTA when records are short-read sized
+	const uint32_t need = 16u * (b.stride - 1);
+	for (uint32_t warps = 4; warps >= 1; warps--) {
+		const size_t per_warp = (ntc::bs::kSmemMax - ntc::bs::kTabBytes) / warps;
+		const uint32_t cap = (uint32_t)((per_warp - ntc::bs::kPerWarpFixed) / 256) - 1;
+		// stride 12 (<= 176 bases) is the 150/151 bp short-read layout: keep 4 warps, longer records of such a
+		// batch take the in-kernel general path
+		if (cap >= need || (warps == 4 && need <= 176)) {
+			cfg.warps = warps;
+			cfg.pos_cap = cap < need ? cap : need;
+			cfg.smem = ntc::bs::kTabBytes + warps * ((size_t)(1 + cfg.pos_cap) * 256 + ntc::bs::kPerWarpFixed);
+			return cfg;
+		}
+	}
+	cfg.kmask = 0; // records too long for the shared-memory planes
+	return cfg;
+}
+
 // Run the sketch kernels over one device-resident batch on the compute stream.
 int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 {
@@ -149,25 +188,53 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
 		return rc;
 	CK(cudaEventRecord(e0, c->stream));
-	uint64_t bound = 0;
-	if (!record_is_piece) {
-		bound = (uint64_t)b.n_rec + (16 * b.n_words) / ntc::PIECE_STARTS + 1;
-		if (bound > 0xFFFFFFFFull)
-			return set_err(NTC_EINVAL, "batch too large: %llu pieces", (unsigned long long)bound);
-		if ((rc = grow(&c->d_piece_first, &c->cap_piece_first, (size_t)b.n_rec + 1, false)) ||
-		    (rc = grow(&c->d_piece_rec, &c->cap_piece_rec, (size_t)bound, false)))
-			return rc;
-		size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
-		char* t = (char*)c->d_scan_tmp;
-		if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
-			return rc;
-		c->d_scan_tmp = t;
-		CK(ntc::launch_piece_tables(b, c->kmin, c->d_piece_first, c->d_piece_rec, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
-		c->n_launches += 3;
+	const BsConfig bs = bitslice_config(c, b, record_is_piece);
+	const uint32_t all = c->nK >= 32 ? 0xFFFFFFFFu : ((1u << c->nK) - 1);
+	const uint32_t roll_mask = all & ~bs.kmask;
+	if (c->kernel == NTC_KERNEL_BITSLICE && roll_mask)
+		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", bs.kmask);
+	for (unsigned ki = 0; ki < c->nK; ki++) {
+		if (!((bs.kmask >> ki) & 1u))
+			continue;
+		ntc::bs::BsArgs a;
+		a.words = b.words;
+		a.stride = b.stride;
+		a.n_rec = b.n_rec;
+		a.L = c->bs_launch[ki];
+		a.L.pos_cap = bs.pos_cap;
+		a.d_tab = c->d_bs_tab;
+		a.d_params = c->d_params;
+		a.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
+		a.f1_k = c->d_f1 + ki;
+		a.warps = bs.warps;
+		const unsigned n_tiles = (b.n_rec + 1023) / 1024;
+		a.grid = std::min<unsigned>((unsigned)c->n_sm, (n_tiles + bs.warps - 1) / bs.warps);
+		a.smem_bytes = bs.smem;
+		a.stream = c->stream;
+		CK(ntc::bs::launch(c->k[ki], c->sBits, a));
+		c->n_launches += 1;
 	}
-	CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters, c->d_f1,
-	    c->n_sm, c->stream));
-	c->n_launches += 1;
+	if (roll_mask) {
+		uint64_t bound = 0;
+		if (!record_is_piece) {
+			bound = (uint64_t)b.n_rec + (16 * b.n_words) / ntc::PIECE_STARTS + 1;
+			if (bound > 0xFFFFFFFFull)
+				return set_err(NTC_EINVAL, "batch too large: %llu pieces", (unsigned long long)bound);
+			if ((rc = grow(&c->d_piece_first, &c->cap_piece_first, (size_t)b.n_rec + 1, false)) ||
+			    (rc = grow(&c->d_piece_rec, &c->cap_piece_rec, (size_t)bound, false)))
+				return rc;
+			size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
+			char* t = (char*)c->d_scan_tmp;
+			if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
+				return rc;
+			c->d_scan_tmp = t;
+			CK(ntc::launch_piece_tables(b, c->kmin, c->d_piece_first, c->d_piece_rec, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
+			c->n_launches += 3;
+		}
+		CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters, c->d_f1,
+		    roll_mask, c->n_sm, c->stream));
+		c->n_launches += 1;
+	}
 	CK(cudaEventRecord(e1, c->stream));
 	c->timing.emplace_back(e0, e1);
 	c->n_batches++;
@@ -278,6 +345,20 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 	ntc::DevParams hp;
 	build_params(c, &hp);
 	CKF(cudaMemcpy(c->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
+	{
+		std::vector<uint32_t> tab(8 * 256 * 4);
+		ntc::bs::build_tables(tab.data());
+		CKF(cudaMalloc((void**)&c->d_bs_tab, tab.size() * sizeof(uint32_t)));
+		CKF(cudaMemcpy(c->d_bs_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		for (unsigned ki = 0; ki < nK; ki++) {
+			ntc::bs::BsLaunch& L = c->bs_launch[ki];
+			L.k = c->k[ki];
+			L.ki = ki;
+			L.rBits = rBits;
+			L.pos_cap = 0;
+			ntc::bs::init_state(c->k[ki], L.F0, L.R0);
+		}
+	}
 	for (int i = 0; i < NBUF; i++) {
 		CKF(cudaEventCreateWithFlags(&c->stage[i].copied, cudaEventDisableTiming));
 		CKF(cudaEventCreateWithFlags(&c->stage[i].consumed, cudaEventDisableTiming));
@@ -320,6 +401,7 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->d_phist) cudaFree(c->d_phist);
 	if (c->d_f1) cudaFree(c->d_f1);
 	if (c->d_params) cudaFree(c->d_params);
+	if (c->d_bs_tab) cudaFree(c->d_bs_tab);
 	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

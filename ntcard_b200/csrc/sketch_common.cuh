@@ -43,4 +43,64 @@ __device__ __forceinline__ void sample_and_count(uint64_t h, uint32_t* __restric
 	}
 }
 
+#if defined(__CUDACC__)
+// ---- the general per-piece path (used by roll64_kernel and as the in-kernel fallback of the bit-sliced kernel) ----
+struct BaseStream { // sequential 2-bit reader with lazy word refill (never reads past the last needed word)
+	const uint32_t* __restrict__ p;
+	uint32_t w;
+	uint32_t left;
+	__device__ __forceinline__ void open(const uint32_t* __restrict__ b, uint32_t idx)
+	{
+		p = b + (idx >> 4);
+		w = __ldg(p) >> ((idx & 15u) * 2u);
+		left = 16u - (idx & 15u);
+	}
+	__device__ __forceinline__ uint32_t next()
+	{
+		if (left == 0) {
+			w = __ldg(++p);
+			left = 16;
+		}
+		uint32_t c = w & 3u;
+		w >>= 2;
+		--left;
+		return c;
+	}
+};
+
+__device__ __forceinline__ uint32_t process_piece_k(const uint32_t* __restrict__ b, uint32_t len, uint32_t a, uint32_t k,
+    const KTab& T, uint32_t* __restrict__ ctr_k, uint32_t rBits, uint32_t sBits)
+{
+	if (len < k)
+		return 0;
+	const uint32_t ns = len - k + 1;
+	if (a >= ns)
+		return 0;
+	const uint32_t e = min(a + PIECE_STARTS, ns);
+	// from-scratch hashes of the first window: NTF64/NTR64 base forms, nthash.hpp:220-239
+	uint64_t fh = 0, rh = 0;
+	{
+		BaseStream s;
+		s.open(b, a);
+		for (uint32_t i = 0; i < k; i++)
+			fh = srol(fh) ^ seed_of(s.next());
+		for (uint32_t i = k; i-- > 0;)
+			rh = srol(rh) ^ seed_of(3u - base_at(b, a + i));
+	}
+	sample_and_count(rh < fh ? rh : fh, ctr_k, rBits, sBits);
+	BaseStream so, si;
+	so.open(b, a);
+	if (a + 1 < e)
+		si.open(b, a + k);
+	for (uint32_t j = a + 1; j < e; j++) {
+		const uint32_t idx = si.next() | (so.next() << 2);
+		fh = srol(fh) ^ T.xf[idx];
+		rh = sror(rh ^ T.xr[idx]);
+		sample_and_count(rh < fh ? rh : fh, ctr_k, rBits, sBits);
+	}
+	return e - a;
+}
+
+#endif
+
 } // namespace ntc

@@ -49,66 +49,10 @@ __global__ void piece_fill_kernel(const uint32_t* __restrict__ piece_first, uint
 // rolling update (ntHashIterator.hpp:85 -> NTC64, nthash.hpp:275-279); records hold valid bases
 // only, so the N-restart branch (ntHashIterator.hpp:80-83) never fires on the device.
 // ------------------------------------------------------------------------------------------------
-struct BaseStream { // sequential 2-bit reader with lazy word refill (never reads past the last needed word)
-	const uint32_t* __restrict__ p;
-	uint32_t w;
-	uint32_t left;
-	__device__ __forceinline__ void open(const uint32_t* __restrict__ b, uint32_t idx)
-	{
-		p = b + (idx >> 4);
-		w = __ldg(p) >> ((idx & 15u) * 2u);
-		left = 16u - (idx & 15u);
-	}
-	__device__ __forceinline__ uint32_t next()
-	{
-		if (left == 0) {
-			w = __ldg(++p);
-			left = 16;
-		}
-		uint32_t c = w & 3u;
-		w >>= 2;
-		--left;
-		return c;
-	}
-};
-
-__device__ __forceinline__ uint32_t process_piece_k(const uint32_t* __restrict__ b, uint32_t len, uint32_t a, uint32_t k,
-    const KTab& T, uint32_t* __restrict__ ctr_k, uint32_t rBits, uint32_t sBits)
-{
-	if (len < k)
-		return 0;
-	const uint32_t ns = len - k + 1;
-	if (a >= ns)
-		return 0;
-	const uint32_t e = min(a + PIECE_STARTS, ns);
-	// from-scratch hashes of the first window: NTF64/NTR64 base forms, nthash.hpp:220-239
-	uint64_t fh = 0, rh = 0;
-	{
-		BaseStream s;
-		s.open(b, a);
-		for (uint32_t i = 0; i < k; i++)
-			fh = srol(fh) ^ seed_of(s.next());
-		for (uint32_t i = k; i-- > 0;)
-			rh = srol(rh) ^ seed_of(3u - base_at(b, a + i));
-	}
-	sample_and_count(rh < fh ? rh : fh, ctr_k, rBits, sBits);
-	BaseStream so, si;
-	so.open(b, a);
-	if (a + 1 < e)
-		si.open(b, a + k);
-	for (uint32_t j = a + 1; j < e; j++) {
-		const uint32_t idx = si.next() | (so.next() << 2);
-		fh = srol(fh) ^ T.xf[idx];
-		rh = sror(rh ^ T.xr[idx]);
-		sample_and_count(rh < fh ? rh : fh, ctr_k, rBits, sBits);
-	}
-	return e - a;
-}
-
 template <bool kRecordIsPiece>
 __global__ void __launch_bounds__(256) roll64_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ off,
     uint32_t stride, uint32_t n_rec, const uint32_t* __restrict__ piece_first, const uint32_t* __restrict__ piece_rec,
-    const DevParams* __restrict__ P, uint32_t* __restrict__ counters, unsigned long long* __restrict__ f1)
+    const DevParams* __restrict__ P, uint32_t* __restrict__ counters, unsigned long long* __restrict__ f1, uint32_t kmask)
 {
 	__shared__ DevParams sp;
 	__shared__ unsigned long long s_f1[NTC_MAX_K];
@@ -135,6 +79,8 @@ __global__ void __launch_bounds__(256) roll64_kernel(const uint32_t* __restrict_
 		const uint32_t* r = words + rec_offset(off, stride, rec);
 		const uint32_t len = __ldg(r);
 		for (uint32_t ki = 0; ki < sp.nK; ki++) {
+			if (!((kmask >> ki) & 1u))
+				continue;
 			uint32_t n = process_piece_k(r + 1, len, a, sp.k[ki], sp.tab[ki], counters + ki * tab_stride, sp.rBits, sp.sBits);
 			if (n)
 				atomicAdd(&s_f1[ki], (unsigned long long)n);
@@ -265,17 +211,17 @@ cudaError_t launch_piece_tables(const BatchView& b, uint32_t kmin, uint32_t* d_p
 }
 
 cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
-    const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t* d_counters, unsigned long long* d_f1, int n_sm,
-    cudaStream_t st)
+    const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t* d_counters, unsigned long long* d_f1, uint32_t kmask,
+    int n_sm, cudaStream_t st)
 {
 	// enough CTAs for every SM to hold its resident set, a multiple of the SM count
 	const unsigned cap = (unsigned)n_sm * 8u * 16u;
 	unsigned grid = grid_for(record_is_piece ? b.n_rec : n_pieces_bound, 256, cap);
 	if (record_is_piece)
-		roll64_kernel<true><<<grid, 256, 0, st>>>(b.words, b.off, b.stride, b.n_rec, nullptr, nullptr, d_params, d_counters, d_f1);
+		roll64_kernel<true><<<grid, 256, 0, st>>>(b.words, b.off, b.stride, b.n_rec, nullptr, nullptr, d_params, d_counters, d_f1, kmask);
 	else
 		roll64_kernel<false><<<grid, 256, 0, st>>>(b.words, b.off, b.stride, b.n_rec, d_piece_first, d_piece_rec, d_params,
-		    d_counters, d_f1);
+		    d_counters, d_f1, kmask);
 	return cudaGetLastError();
 }
 

@@ -194,3 +194,73 @@ def test_full_size_properties_config2(kernel):
         F0, f = nt.estimate(p_hist=p_full[0], rBits=27, sBits=7, covMax=4)
         distinct = half * (L - k + 1)
         assert abs(F0 - distinct) / distinct < 0.02 and f[2] > 0.97 * distinct and f[1] < 0.01 * distinct
+
+
+# ---- the bit-sliced kernel (NTC_KERNEL_BITSLICE), forced --------------------------------------
+@pytest.mark.parametrize("sBits", [7, 11])
+@pytest.mark.parametrize("L,kList", [(150, [32]), (150, [12, 31, 64, 96, 128]), (100, [32, 64]), (151, [31, 32]),
+                                     (64, [32, 64]), (40, [12, 32]), (170, [32])])
+def test_bitslice_uniform_reads(oracle, L, kList, sBits):
+    n = 5000 if sBits == 7 else 40000      # partial last tile (n % 1024 != 0) takes the in-kernel general path
+    a = oracle.gen_reads(31, 0, n, L, 1, n // 4)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, kList, 20, sBits, nthreads=4)
+    stride = nt.stride_words(L)
+    words = nt.gen_packed(31, 0, n, L, 1, n // 4, stride)
+    with nt.Sketch(kList, rBits=20, sBits=sBits) as sk:
+        sk.set_kernel(nt.KERNEL_BITSLICE)
+        sk.submit(words, None, n, stride)
+        t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1)
+    assert np.array_equal(t.reshape(-1), want)
+
+
+def test_bitslice_mixed_lengths_in_uniform_stride(oracle):
+    """Records of different lengths inside a uniform-stride batch: tiles that are not uniform fall back
+    to the 64-bit path inside the kernel; results stay exact."""
+    rng = random.Random(5)
+    n, stride = 6000, 12
+    reads = []
+    for i in range(n):
+        L = 150 if (i // 1024) % 2 == 0 else rng.choice((20, 31, 32, 100, 150, 176))
+        reads.append(bytes(rng.choice(b"ACGT") for _ in range(L)))
+    words = np.zeros(n * stride, dtype=np.uint32)
+    for i, r in enumerate(reads):
+        w, _ = nt.pack_reads([r])
+        words[i * stride:i * stride + len(w)] = w
+        if len(r) == 0:
+            words[i * stride] = 0
+    for kList in ([32], [31, 64]):
+        want, wf1 = oracle.sketch_reads(reads, kList, 18, 7, nthreads=4)
+        with nt.Sketch(kList, rBits=18, sBits=7) as sk:
+            sk.set_kernel(nt.KERNEL_BITSLICE)
+            sk.submit(words, None, n, stride)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+        assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+
+
+def test_bitslice_low_complexity_queue_overflow(oracle):
+    """Poly-A / dinucleotide reads: every k-mer of a read has the same hash, so either none or ALL of
+    them are sampled -- the per-body hit queue overflows and the slow exact path must take over."""
+    n, L, stride = 4096, 150, 12
+    pats = [b"A", b"C", b"AC", b"AG", b"ACG", b"AAT", b"ACGT", b"T"]
+    reads = [(pats[i % len(pats)] * 200)[:L] for i in range(n)]
+    words = np.zeros(n * stride, dtype=np.uint32)
+    for i, r in enumerate(reads):
+        w, _ = nt.pack_reads([r])
+        words[i * stride:i * stride + len(w)] = w
+    for sBits in (7, 11):
+        want, wf1 = oracle.sketch_reads(reads, [12, 32], 16, sBits, nthreads=4)
+        with nt.Sketch([12, 32], rBits=16, sBits=sBits) as sk:
+            sk.set_kernel(nt.KERNEL_BITSLICE)
+            sk.submit(words, None, n, stride)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+        assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+
+
+def test_bitslice_refuses_unsupported():
+    with nt.Sketch([32], rBits=12, sBits=5) as sk:      # sBits 5 has no bit-sliced variant
+        sk.set_kernel(nt.KERNEL_BITSLICE)
+        words = nt.gen_packed(1, 0, 2048, 150, 0, 0, 12)
+        with pytest.raises(nt.NtcError):
+            sk.submit(words, None, 2048, 12)
