@@ -95,11 +95,31 @@ BS_HD Words make_words(uint32_t lo, uint32_t hi)
 	return W;
 }
 
-template <int C> BS_HD uint32_t xor3c(uint32_t s, uint32_t a, uint32_t b)
+// state ^ a ^ b (^ 1 if C) as ONE logic op.  On the device this is an explicit lop3 so that the compiler
+// cannot re-associate the XORs back into per-base expressions (it did: 2 LOP3 + stray NOTs per ring bit).
+template <int C, int A, int B> BS_HD uint32_t xor3c(uint32_t s, const Words& in, const Words& out)
 {
-	if (C)
-		return ~(s ^ a ^ b);
-	return s ^ a ^ b;
+#if defined(__CUDA_ARCH__)
+	uint32_t d;
+	if (A != 0 && B != 0) {
+		if (C)
+			asm("lop3.b32 %0, %1, %2, %3, 0x69;" : "=r"(d) : "r"(s), "r"(in.w[A]), "r"(out.w[B]));
+		else
+			asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(s), "r"(in.w[A]), "r"(out.w[B]));
+	} else if (A != 0 || B != 0) {
+		const uint32_t w = A != 0 ? in.w[A] : out.w[B];
+		if (C)
+			asm("lop3.b32 %0, %1, %2, %2, 0xc3;" : "=r"(d) : "r"(s), "r"(w)); // ~(s ^ w)
+		else
+			asm("lop3.b32 %0, %1, %2, %2, 0x3c;" : "=r"(d) : "r"(s), "r"(w)); // s ^ w
+	} else {
+		d = C ? ~s : s;
+	}
+	return d;
+#else
+	const uint32_t v = s ^ in.w[A] ^ out.w[B];
+	return C ? ~v : v;
+#endif
 }
 
 struct State {
@@ -112,8 +132,8 @@ template <int KM, int TQ, int J> struct UpdateAll {
 	{
 		using f = Fwd<KM, TQ, J>;
 		using r = Rev<KM, TQ, J>;
-		st.F[J] = xor3c<f::c>(st.F[J], in.w[f::a], out.w[f::b]);
-		st.R[J] = xor3c<r::c>(st.R[J], in.w[r::a], out.w[r::b]);
+		st.F[J] = xor3c<f::c, f::a, f::b>(st.F[J], in, out);
+		st.R[J] = xor3c<r::c, r::a, r::b>(st.R[J], in, out);
 		UpdateAll<KM, TQ, J + 1>::run(st, in, out);
 	}
 };

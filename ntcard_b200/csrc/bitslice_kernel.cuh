@@ -26,68 +26,150 @@
 namespace ntc {
 namespace bs {
 
-constexpr int kWarpsMax = 4;
+constexpr int kPairsMax = 4;       // scan warps per CTA; each has one partner "hit" warp on the same SM sub-partition
 constexpr uint32_t kTileRecs = 1024;
-constexpr uint32_t kQueue = 1024; // flat hit queue entries per warp per body (expected 31*1024/64 = 496 at s=7)
 
 struct WarpCtx {
 	const uint32_t* __restrict__ words;
 	uint32_t stride;
 	uint32_t rb;        // first record of the tile
-	uint32_t k, rBits, sBits;
+	uint32_t k, rBits;
 	uint32_t nwords;    // base words per record actually holding bases
 	const uint4* tab;   // shared: [8][256] {FB.lo, FB.hi, RB.lo, RB.hi}
+	uint64_t rot_a, rot_b; // byte m: (t + 32m) % 31 and % 33 (rotation of RB_m)
 	uint32_t* __restrict__ ctr_k;
 };
 
-// Full canonical hash of the k-mer starting at base p of a record (b = its base words).
-// k = t + 32*M: the t head bases one at a time (NTF64/NTR64 base forms, nthash.hpp:220-239), then M
-// blocks of 32 bases through the byte tables:
-//   fh = srol^32(fh) ^ FB_m,  FB = XOR_i srol^(31-i) seed[c_i]     rh ^= srol^(t+32m) RB_m,  RB = XOR_i srol^i seed[3-c_i]
-__device__ __forceinline__ void hash_kmer(const WarpCtx& c, const uint32_t* __restrict__ b, uint32_t p, uint64_t& fh, uint64_t& rh)
+// ---- mbarrier helpers (shared::cta) -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-	const uint32_t t = c.k & 31u, M = c.k >> 5;
-	fh = 0;
-	rh = 0;
-	for (uint32_t i = 0; i < t; i++) {
-		const uint32_t code = base_at(b, p + i);
-		fh = srol(fh) ^ seed_of(code);
-		rh ^= srol_n(seed_of(3u - code), i);
-	}
-	for (uint32_t m = 0; m < M; m++) {
-		const uint32_t o = p + t + 32u * m, wi = o >> 4, sh = (o & 15u) * 2u;
-		const uint32_t x0 = __ldg(b + wi), x1 = __ldg(b + wi + 1), x2 = __ldg(b + min(wi + 2, c.nwords - 1));
-		const uint32_t w0 = __funnelshift_r(x0, x1, sh), w1 = __funnelshift_r(x1, x2, sh);
-		uint32_t f0 = 0, f1 = 0, r0 = 0, r1 = 0;
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			const uint32_t byte = ((j < 4 ? w0 : w1) >> (8 * (j & 3))) & 0xFFu;
-			const uint4 e = c.tab[j * 256 + byte];
-			f0 ^= e.x;
-			f1 ^= e.y;
-			r0 ^= e.z;
-			r1 ^= e.w;
-		}
-		fh = srol_n(fh, 32) ^ (((uint64_t)f1 << 32) | f0);
-		rh ^= srol_n(((uint64_t)r1 << 32) | r0, t + 32u * m);
-	}
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile(
+	    "{\n\t"
+	    ".reg .pred p;\n\t"
+	    "MBAR_WAIT:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@p bra MBAR_DONE;\n\t"
+	    "bra MBAR_WAIT;\n\t"
+	    "MBAR_DONE:\n\t"
+	    "}" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+
+// srol applied n times, for n given as (a, b) = (n % 31, n % 33): rotate the upper ring by a, the lower by b.
+__device__ __forceinline__ uint64_t srol_ab(uint64_t v, uint32_t a, uint32_t b)
+{
+	uint32_t hi = (uint32_t)(v >> 33);
+	uint64_t lo = v & 0x1FFFFFFFFull;
+	hi = ((hi << a) | (hi >> (31u - a))) & 0x7FFFFFFFu;
+	lo = ((lo << b) | (lo >> (33u - b))) & 0x1FFFFFFFFull;
+	return ((uint64_t)hi << 33) | lo;
+}
+
+struct HitLoad { // a queued k-mer with the packed words of its first 32-base block in flight
+	uint32_t p;
+	const uint32_t* __restrict__ b;
+	uint32_t x0, x1, x2;
+};
 
 // entry: slot (5 bits) | lane (5 bits) << 5 | position-in-body << 10
-__device__ __forceinline__ void process_hit(const WarpCtx& c, uint32_t e, uint32_t q0)
+__device__ __forceinline__ HitLoad hit_issue(const WarpCtx& c, uint32_t e, uint32_t q0)
 {
+	HitLoad h;
 	const uint32_t s = e & 31u, ln = (e >> 5) & 31u, tq = e >> 10;
 	const uint32_t rec = c.rb + s * 32u + ln;
-	const uint32_t p = q0 + tq + 1u - c.k;
-	const uint32_t* b = c.words + (uint64_t)rec * c.stride + 1;
-	uint64_t fh, rh;
-	hash_kmer(c, b, p, fh, rh);
-	sample_and_count(rh < fh ? rh : fh, c.ctr_k, c.rBits, c.sBits);
+	h.p = q0 + tq + 1u - c.k;
+	h.b = c.words + (uint64_t)rec * c.stride + 1;
+	const uint32_t wi = (h.p + (c.k & 31u)) >> 4;
+	h.x0 = __ldg(h.b + min(wi, c.nwords - 1));
+	h.x1 = __ldg(h.b + min(wi + 1, c.nwords - 1));
+	h.x2 = __ldg(h.b + min(wi + 2, c.nwords - 1));
+	return h;
 }
 
-// Compact the masks of one body (nq positions) into the queue and hash the hits.
-static __device__ __noinline__ void drain_body(const WarpCtx& c, const uint32_t* __restrict__ hw, uint32_t* __restrict__ queue, uint32_t nq,
-    uint32_t q0, uint32_t lane)
+// 32 bases (two packed words) through the byte tables: FB = XOR_i srol^(31-i) seed[c_i], RB = XOR_i srol^i seed[3-c_i]
+__device__ __forceinline__ void block_tables(const uint4* __restrict__ tab, uint32_t w0, uint32_t w1, uint32_t& f0, uint32_t& f1,
+    uint32_t& r0, uint32_t& r1)
+{
+	f0 = f1 = r0 = r1 = 0;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const uint32_t w = j < 4 ? w0 : w1;
+		const int sh = 8 * (j & 3) - 4; // byte j scaled by 16 (the entry size)
+		const uint32_t off = (sh < 0 ? (w << 4) : (w >> sh)) & 0xFF0u;
+		const uint4 e = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(tab) + j * 4096 + off);
+		f0 ^= e.x;
+		f1 ^= e.y;
+		r0 ^= e.z;
+		r1 ^= e.w;
+	}
+}
+
+// Full canonical hash of a queued k-mer and ntComp (ntcard.cpp:132-145).  k = t + 32*M: the t head bases
+// one at a time (NTF64/NTR64 base forms, nthash.hpp:220-239), then M blocks of 32 bases:
+//   fh = srol^32(fh) ^ FB_m        rh ^= srol^(t+32m) RB_m
+template <int S> __device__ __forceinline__ void hit_finish(const WarpCtx& c, const HitLoad& h)
+{
+	const uint32_t t = c.k & 31u, M = c.k >> 5;
+	uint32_t hh, hl; // canonical hash, high / low word
+	if (t == 0 && M == 1) { // k = 32: pure 32-bit path
+		const uint32_t sh = (h.p & 15u) * 2u;
+		uint32_t f0, f1, r0, r1;
+		block_tables(c.tab, __funnelshift_r(h.x0, h.x1, sh), __funnelshift_r(h.x1, h.x2, sh), f0, f1, r0, r1);
+		const bool rlt = r1 < f1 || (r1 == f1 && r0 < f0);
+		hh = rlt ? r1 : f1;
+		hl = rlt ? r0 : f0;
+	} else {
+		uint64_t fh = 0, rh = 0;
+		for (uint32_t i = 0; i < t; i++) {
+			const uint32_t code = base_at(h.b, h.p + i);
+			fh = srol(fh) ^ seed_of(code);
+			rh ^= srol_n(seed_of(3u - code), i);
+		}
+		uint32_t x0 = h.x0, x1 = h.x1, x2 = h.x2;
+		for (uint32_t m = 0; m < M; m++) {
+			const uint32_t o = h.p + t + 32u * m, sh = (o & 15u) * 2u;
+			if (m) {
+				const uint32_t wi = o >> 4;
+				x0 = __ldg(h.b + wi);
+				x1 = __ldg(h.b + wi + 1);
+				x2 = __ldg(h.b + min(wi + 2, c.nwords - 1));
+			}
+			uint32_t f0, f1, r0, r1;
+			block_tables(c.tab, __funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), f0, f1, r0, r1);
+			const uint64_t FB = ((uint64_t)f1 << 32) | f0, RB = ((uint64_t)r1 << 32) | r0;
+			fh = (m || t) ? (srol_ab(fh, 1, 32) ^ FB) : FB;
+			const uint32_t ra = (uint32_t)(c.rot_a >> (8 * m)) & 0xFFu, rb = (uint32_t)(c.rot_b >> (8 * m)) & 0xFFu;
+			rh ^= (ra | rb) ? srol_ab(RB, ra, rb) : RB;
+		}
+		const uint64_t hm = rh < fh ? rh : fh;
+		hh = (uint32_t)(hm >> 32);
+		hl = (uint32_t)hm;
+	}
+	// ntComp: both tests look at the top S+1 <= 32 bits; the bucket at the low rBits <= 30 bits
+	const bool t0 = (hh >> (31 - S)) == 1u;
+	const bool t1 = (hh >> (32 - S)) == ((1u << (S - 1)) - 1u);
+	if (t0 || t1) {
+		const uint32_t idx = ((t1 ? 1u : 0u) << c.rBits) | (hl & ((1u << c.rBits) - 1u));
+		atomicAdd(c.ctr_k + idx, 1u);
+	}
+}
+
+constexpr int kHitBatch = 4; // k-mers per lane whose loads are in flight together
+
+// The hit warp's work for one body: compact the masks (popc + warp scan) into the queue, then hash.
+template <int S>
+__device__ __forceinline__ void drain_body(const WarpCtx& c, const uint32_t* __restrict__ hw, uint32_t* __restrict__ queue,
+    uint32_t qcap, uint32_t nq, uint32_t q0, uint32_t lane)
 {
 	uint32_t cnt = 0;
 	for (uint32_t tq = 0; tq < nq; tq++)
@@ -109,17 +191,30 @@ static __device__ __noinline__ void drain_body(const WarpCtx& c, const uint32_t*
 			const uint32_t s = __ffs(w) - 1;
 			w &= w - 1;
 			const uint32_t e = s | (lane << 5) | (tq << 10);
-			if (off < kQueue)
+			if (off < qcap)
 				queue[off] = e;
 			else
-				process_hit(c, e, q0); // queue overflow (heavily skewed data): slow but exact
+				hit_finish<S>(c, hit_issue(c, e, q0)); // queue overflow (heavily skewed data): slow but exact
 			off++;
 		}
 	}
 	__syncwarp();
-	const uint32_t lim = min(total, kQueue);
-	for (uint32_t i = lane; i < lim; i += 32)
-		process_hit(c, queue[i], q0);
+	const uint32_t lim = min(total, qcap);
+	for (uint32_t base = 0; base < lim; base += 32 * kHitBatch) {
+		HitLoad h[kHitBatch];
+#pragma unroll
+		for (int u = 0; u < kHitBatch; u++) {
+			const uint32_t i = base + u * 32 + lane;
+			if (i < lim)
+				h[u] = hit_issue(c, queue[i], q0);
+		}
+#pragma unroll
+		for (int u = 0; u < kHitBatch; u++) {
+			const uint32_t i = base + u * 32 + lane;
+			if (i < lim)
+				hit_finish<S>(c, h[u]);
+		}
+	}
 	__syncwarp();
 }
 
@@ -145,22 +240,42 @@ template <int KM, int S> struct DevBody<KM, S, 31> {
 	static __device__ __forceinline__ void run(State&, const uint2* __restrict__, uint32_t* __restrict__, int, int, int) {}
 };
 
+// Per scan warp: hand-off of one body's masks to the partner hit warp.
+struct BodyDesc {
+	uint32_t rb, q0, nq, nwords; // nq == 0: no more work
+};
+
 template <int KM, int S>
-__global__ void __launch_bounds__(kWarpsMax * 32, 1) bitslice_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec,
+__global__ void __launch_bounds__(kPairsMax * 64, 1) bitslice_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec,
     BsLaunch L, const uint4* __restrict__ g_tab, const DevParams* __restrict__ P, uint32_t* __restrict__ ctr_k,
     unsigned long long* __restrict__ f1_k)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, npairs = blockDim.x >> 6;
+	const bool is_scan = warp < npairs;
+	const uint32_t pair = is_scan ? warp : warp - npairs;
 	uint4* tab = reinterpret_cast<uint4*>(smem_raw);
 	for (uint32_t i = threadIdx.x; i < 8 * 256; i += blockDim.x)
 		tab[i] = g_tab[i];
+	// per pair: [planes][masks x2][queue][desc x2][mbarriers x4]
 	const uint32_t plane_bytes = (1u + L.pos_cap) * 256u; // [slot 0 = zeros][position][lane] uint2
-	unsigned char* wbase = smem_raw + 8 * 256 * 16 + warp * (plane_bytes + 31 * 128 + kQueue * 4);
-	uint2* planes = reinterpret_cast<uint2*>(wbase);
-	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(wbase + plane_bytes);
-	uint32_t* queue = hwbuf + 31 * 32;
-	planes[lane] = make_uint2(0u, 0u);
+	const uint32_t pair_bytes = plane_bytes + 2 * kMaskBytes + L.queue_cap * 4 + kPairMisc;
+	unsigned char* pbase = smem_raw + kTabBytes + pair * pair_bytes;
+	uint2* planes = reinterpret_cast<uint2*>(pbase);
+	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(pbase + plane_bytes);          // [2][31][32]
+	uint32_t* queue = hwbuf + 2 * (kMaskBytes / 4);
+	BodyDesc* desc = reinterpret_cast<BodyDesc*>(queue + L.queue_cap);             // [2]
+	uint64_t* bar_full = reinterpret_cast<uint64_t*>(desc + 2);                    // [2]
+	uint64_t* bar_empty = bar_full + 2;                                            // [2]
+	if (is_scan) {
+		planes[lane] = make_uint2(0u, 0u);
+		if (lane == 0) {
+			mbar_init(&bar_full[0], 1);
+			mbar_init(&bar_full[1], 1);
+			mbar_init(&bar_empty[0], 1);
+			mbar_init(&bar_empty[1], 1);
+		}
+	}
 	__syncthreads();
 
 	WarpCtx c;
@@ -168,15 +283,43 @@ __global__ void __launch_bounds__(kWarpsMax * 32, 1) bitslice_kernel(const uint3
 	c.stride = stride;
 	c.k = L.k;
 	c.rBits = L.rBits;
-	c.sBits = S;
 	c.tab = tab;
+	c.rot_a = L.rot_a;
+	c.rot_b = L.rot_b;
 	c.ctr_k = ctr_k;
+
+	if (!is_scan) {
+		// ================= hit warp: consume the masks of each body =================
+		for (uint32_t it = 0;; it++) {
+			const uint32_t b = it & 1u;
+			mbar_wait(&bar_full[b], (it >> 1) & 1u);
+			const BodyDesc d = desc[b];
+			if (d.nq == 0)
+				break;
+			c.rb = d.rb;
+			c.nwords = d.nwords;
+			drain_body<S>(c, hwbuf + b * (kMaskBytes / 4), queue, L.queue_cap, d.nq, d.q0, lane);
+			if (lane == 0)
+				mbar_arrive(&bar_empty[b]);
+		}
+		return;
+	}
+
+	// ================= scan warp =================
 	const int k = (int)L.k;
 	unsigned long long f1_local = 0;
+	uint32_t it = 0; // bodies handed over so far
 	const uint32_t n_tiles = (n_rec + kTileRecs - 1) / kTileRecs;
-	for (uint32_t tile = blockIdx.x * nwarps + warp; tile < n_tiles; tile += gridDim.x * nwarps) {
+	for (uint32_t tile = blockIdx.x * npairs + pair; tile < n_tiles; tile += gridDim.x * npairs) {
 		const uint32_t rb = tile * kTileRecs;
-		c.rb = rb;
+		// warm L2 with the next tile of this warp while this one is processed (bulk async prefetch)
+		{
+			const uint64_t nrb = (uint64_t)(tile + gridDim.x * npairs) * kTileRecs;
+			if (lane == 0 && nrb + kTileRecs <= n_rec) {
+				const uint32_t bytes = kTileRecs * stride * 4u;
+				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(words + nrb * stride), "r"(bytes) : "memory");
+			}
+		}
 		// ---- record lengths; is the tile uniform? ----
 		uint32_t len0 = 0;
 		bool uniform = true;
@@ -191,7 +334,7 @@ __global__ void __launch_bounds__(kWarpsMax * 32, 1) bitslice_kernel(const uint3
 			uniform = __all_sync(0xFFFFFFFFu, uniform);
 			len0 = first_len;
 		}
-		if (!uniform || (len0 != 0xFFFFFFFFu && len0 > L.pos_cap)) {
+		if (!uniform || len0 > L.pos_cap) {
 			// general path, in place: each lane walks its own records with the 64-bit recurrence
 			const KTab& T = P->tab[L.ki];
 			uint32_t cnt = 0;
@@ -208,10 +351,11 @@ __global__ void __launch_bounds__(kWarpsMax * 32, 1) bitslice_kernel(const uint3
 		const int n = (int)len0;
 		if (n < k)
 			continue;
-		c.nwords = (uint32_t)(n + 15) >> 4;
+		const uint32_t nwords = (uint32_t)(n + 15) >> 4;
 		// ---- 1. transpose packed bases into bit planes ----
+		// (the partner may still be hashing k-mers of the previous tile: it reads global memory, not the planes)
 		{
-			const uint32_t ngroups = (c.nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
+			const uint32_t ngroups = (nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
 			for (uint32_t g = 0; g < ngroups; g++) {
 				uint4 v[32];
 #pragma unroll
@@ -220,7 +364,7 @@ __global__ void __launch_bounds__(kWarpsMax * 32, 1) bitslice_kernel(const uint3
 #pragma unroll
 				for (int i = 0; i < 4; i++) {
 					const int w = (int)(g * 4) + i - 1; // base word index
-					if (w < 0 || w >= (int)c.nwords)
+					if (w < 0 || w >= (int)nwords)
 						continue;
 					uint32_t A[32];
 #pragma unroll
@@ -235,7 +379,7 @@ __global__ void __launch_bounds__(kWarpsMax * 32, 1) bitslice_kernel(const uint3
 			}
 		}
 		__syncwarp();
-		// ---- 2./3. scan + hits ----
+		// ---- 2. scan; 3. hand each body's masks to the hit warp ----
 		State st;
 #pragma unroll
 		for (int j = 0; j < 31; j++) {
@@ -243,14 +387,35 @@ __global__ void __launch_bounds__(kWarpsMax * 32, 1) bitslice_kernel(const uint3
 			st.R[j] = L.R0[j];
 		}
 		for (int q0 = 0; q0 < n; q0 += 31) {
-			DevBody<KM, S, 0>::run(st, planes + lane, hwbuf + lane, q0, n, k);
-			__syncwarp();
 			const int nq = min(31, n - q0);
-			if (q0 + nq >= k) // some position of this body ends a full window
-				drain_body(c, hwbuf, queue, (uint32_t)nq, (uint32_t)q0, lane);
+			const bool has_windows = q0 + nq >= k; // some position of this body ends a full window
+			uint32_t b = it & 1u;
+			uint32_t* hw = hwbuf + b * (kMaskBytes / 4);
+			if (it >= 2) // the partner must have finished the previous use of this buffer (bodies without windows write it too)
+				mbar_wait(&bar_empty[b], ((it >> 1) - 1) & 1u);
+			DevBody<KM, S, 0>::run(st, planes + lane, hw + lane, q0, n, k);
+			if (has_windows) {
+				__syncwarp();
+				if (lane == 0) {
+					desc[b] = BodyDesc{ rb, (uint32_t)q0, (uint32_t)nq, nwords };
+					mbar_arrive(&bar_full[b]);
+				}
+				it++;
+			}
 		}
 		if (lane == 0)
 			f1_local += (unsigned long long)kTileRecs * (unsigned long long)(n - k + 1);
+	}
+	// tell the partner to stop
+	{
+		const uint32_t b = it & 1u;
+		if (it >= 2)
+			mbar_wait(&bar_empty[b], ((it >> 1) - 1) & 1u);
+		__syncwarp();
+		if (lane == 0) {
+			desc[b] = BodyDesc{ 0, 0, 0, 0 };
+			mbar_arrive(&bar_full[b]);
+		}
 	}
 	// totKmer (ntcard.cpp:155): warp-reduce then one atomic per warp
 #pragma unroll
@@ -267,7 +432,7 @@ cudaError_t launch_one(const BsArgs& a)
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes);
 	if (e != cudaSuccess)
 		return e;
-	kern<<<a.grid, a.warps * 32, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.d_tab, a.d_params, a.ctr_k, a.f1_k);
+	kern<<<a.grid, a.pairs * 64, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.d_tab, a.d_params, a.ctr_k, a.f1_k);
 	return cudaGetLastError();
 }
 

@@ -8,8 +8,10 @@ struct DevParams;
 namespace bs {
 
 struct BsLaunch {          // per-k launch constants, passed by value
-	uint32_t k, ki, rBits, pos_cap; // pos_cap: positions the shared-memory planes of one warp can hold
+	uint32_t k, ki, rBits, pos_cap; // pos_cap: positions the shared-memory planes of one scan warp can hold
+	uint32_t queue_cap;             // hit queue entries per pair
 	uint32_t F0[31], R0[31];        // initial bit-sliced state (bitslice_core.cuh init_state)
+	uint64_t rot_a, rot_b;          // byte m: (k%32 + 32m) % 31 and % 33 for block m of the hit path (k < 288)
 };
 
 struct BsArgs {
@@ -20,13 +22,14 @@ struct BsArgs {
 	const DevParams* d_params;
 	uint32_t* ctr_k;                // counters of this k: [2][2^rBits]
 	unsigned long long* f1_k;
-	unsigned grid, warps;
+	unsigned grid, pairs;           // CTAs; (scan warp, hit warp) pairs per CTA
 	size_t smem_bytes;
 	cudaStream_t stream;
 };
 
 constexpr size_t kTabBytes = 8 * 256 * 16;
-constexpr size_t kPerWarpFixed = 31 * 128 + 1024 * 4; // mask buffer + hit queue
+constexpr size_t kMaskBytes = 31 * 128;               // one body's masks: [31 positions][32 lanes] words
+constexpr size_t kPairMisc = 64;                      // 2 body descriptors + 4 mbarriers
 constexpr size_t kSmemMax = 232448;                   // 227 KB opt-in limit per CTA on sm_100
 
 // True when a kernel for (k mod 31, sBits) was compiled in.

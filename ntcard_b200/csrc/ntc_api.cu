@@ -145,7 +145,7 @@ void build_params(const ntc_ctx* c, ntc::DevParams* P)
 
 // Which k indices the bit-sliced kernel can take for this batch; plane capacity / warps per CTA in *cfg.
 struct BsConfig {
-	uint32_t kmask = 0, warps = 0, pos_cap = 0;
+	uint32_t kmask = 0, pairs = 0, pos_cap = 0, queue_cap = 0;
 	size_t smem = 0;
 };
 
@@ -156,21 +156,27 @@ BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 	    b.n_rec < 1024 || (reinterpret_cast<uintptr_t>(b.words) & 15u))
 		return cfg;
 	for (unsigned ki = 0; ki < c->nK; ki++)
-		if (ntc::bs::have_kernel(c->k[ki], c->sBits))
+		if (c->k[ki] < 288 && ntc::bs::have_kernel(c->k[ki], c->sBits))
 			cfg.kmask |= 1u << ki;
 	if (!cfg.kmask)
 		return cfg;
-	// planes of one warp hold pos_cap positions; 4 warps per CTA when records are short-read sized
+	// One CTA per SM: the byte tables plus, per (scan warp, hit warp) pair, bit planes for pos_cap positions,
+	// two mask buffers, the hit queue.  4 pairs when the records are short-read sized.
 	const uint32_t need = 16u * (b.stride - 1);
-	for (uint32_t warps = 4; warps >= 1; warps--) {
-		const size_t per_warp = (ntc::bs::kSmemMax - ntc::bs::kTabBytes) / warps;
-		const uint32_t cap = (uint32_t)((per_warp - ntc::bs::kPerWarpFixed) / 256) - 1;
-		// stride 12 (<= 176 bases) is the 150/151 bp short-read layout: keep 4 warps, longer records of such a
+	for (uint32_t pairs = 4; pairs >= 1; pairs--) {
+		const size_t per_pair = ((ntc::bs::kSmemMax - ntc::bs::kTabBytes) / pairs) & ~(size_t)255;
+		const size_t fixed = 2 * ntc::bs::kMaskBytes + ntc::bs::kPairMisc;
+		uint32_t queue_cap = pairs == 4 ? 640 : 1024; // expected 31*1024/64 = 496 sampled k-mers per body at s=7
+		if (per_pair < fixed + queue_cap * 4 + 512)
+			continue;
+		const uint32_t cap = (uint32_t)((per_pair - fixed - queue_cap * 4) / 256) - 1;
+		// stride 12 (<= 176 bases) is the 150/151 bp short-read layout: keep 4 pairs; longer records of such a
 		// batch take the in-kernel general path
-		if (cap >= need || (warps == 4 && need <= 176)) {
-			cfg.warps = warps;
+		if (cap >= need || (pairs == 4 && need <= 176 && cap >= 152)) {
+			cfg.pairs = pairs;
 			cfg.pos_cap = cap < need ? cap : need;
-			cfg.smem = ntc::bs::kTabBytes + warps * ((size_t)(1 + cfg.pos_cap) * 256 + ntc::bs::kPerWarpFixed);
+			cfg.queue_cap = queue_cap;
+			cfg.smem = ntc::bs::kTabBytes + pairs * ((size_t)(1 + cfg.pos_cap) * 256 + fixed + queue_cap * 4);
 			return cfg;
 		}
 	}
@@ -202,13 +208,14 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		a.n_rec = b.n_rec;
 		a.L = c->bs_launch[ki];
 		a.L.pos_cap = bs.pos_cap;
+		a.L.queue_cap = bs.queue_cap;
 		a.d_tab = c->d_bs_tab;
 		a.d_params = c->d_params;
 		a.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 		a.f1_k = c->d_f1 + ki;
-		a.warps = bs.warps;
+		a.pairs = bs.pairs;
 		const unsigned n_tiles = (b.n_rec + 1023) / 1024;
-		a.grid = std::min<unsigned>((unsigned)c->n_sm, (n_tiles + bs.warps - 1) / bs.warps);
+		a.grid = std::min<unsigned>((unsigned)c->n_sm, (n_tiles + bs.pairs - 1) / bs.pairs);
 		a.smem_bytes = bs.smem;
 		a.stream = c->stream;
 		CK(ntc::bs::launch(c->k[ki], c->sBits, a));
@@ -357,6 +364,11 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 			L.rBits = rBits;
 			L.pos_cap = 0;
 			ntc::bs::init_state(c->k[ki], L.F0, L.R0);
+			L.rot_a = L.rot_b = 0;
+			for (unsigned m = 0; m < 8; m++) {
+				L.rot_a |= (uint64_t)(((c->k[ki] & 31u) + 32u * m) % 31u) << (8 * m);
+				L.rot_b |= (uint64_t)(((c->k[ki] & 31u) + 32u * m) % 33u) << (8 * m);
+			}
 		}
 	}
 	for (int i = 0; i < NBUF; i++) {
