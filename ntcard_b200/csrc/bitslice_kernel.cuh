@@ -26,6 +26,8 @@
 namespace ntc {
 namespace bs {
 
+constexpr int kBlock = 4;    // scan positions per unrolled block (see DevBlock)
+constexpr int kBodyPos = 32; // positions per hand-off to a hit warp (4 blocks)
 constexpr int kPairsMax = 4;       // scan warps per CTA; each has one partner "hit" warp on the same SM sub-partition
 constexpr uint32_t kTileRecs = 1024;
 
@@ -63,6 +65,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 	    "}" ::"r"(smem_u32(bar)),
 	    "r"(parity)
 	    : "memory");
+}
+
+// Named barriers (bar.sync / bar.arrive) for the producer -> consumer direction: a waiting hit warp is
+// descheduled by the hardware and costs no issue slots (an mbarrier try_wait loop does: a third of all
+// issued instructions were idle hit warps polling).
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
+{
+	asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
+{
+	asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // srol applied n times, for n given as (a, b) = (n % 31, n % 33): rotate the upper ring by a, the lower by b.
@@ -164,110 +178,144 @@ template <int S> __device__ __forceinline__ void hit_finish(const WarpCtx& c, co
 	}
 }
 
-constexpr int kHitBatch = 4; // k-mers per lane whose loads are in flight together
+constexpr int kHitBatch = 4;  // k-mers per lane whose loads are in flight together
+constexpr int kHalfPos = 16;  // a body's masks are compacted and hashed in two halves
 
-// The hit warp's work for one body: compact the masks (popc + warp scan) into the queue, then hash.
-template <int S>
-__device__ __forceinline__ void drain_body(const WarpCtx& c, const uint32_t* __restrict__ hw, uint32_t* __restrict__ queue,
-    uint32_t qcap, uint32_t nq, uint32_t q0, uint32_t lane)
+// queue-overflow path, kept out of line
+template <int S> static __device__ __noinline__ void hit_slow(const WarpCtx& c, uint32_t e, uint32_t q0)
 {
-	uint32_t cnt = 0;
-	for (uint32_t tq = 0; tq < nq; tq++)
-		cnt += __popc(hw[tq * 32 + lane]);
-	uint32_t inc = cnt;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-		if ((int)lane >= d)
-			inc += v;
-	}
-	const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-	if (total == 0)
-		return;
-	uint32_t off = inc - cnt;
-	for (uint32_t tq = 0; tq < nq; tq++) {
-		uint32_t w = hw[tq * 32 + lane];
-		while (w) {
-			const uint32_t s = __ffs(w) - 1;
-			w &= w - 1;
-			const uint32_t e = s | (lane << 5) | (tq << 10);
-			if (off < qcap)
-				queue[off] = e;
-			else
-				hit_finish<S>(c, hit_issue(c, e, q0)); // queue overflow (heavily skewed data): slow but exact
-			off++;
-		}
-	}
-	__syncwarp();
-	const uint32_t lim = min(total, qcap);
-	for (uint32_t base = 0; base < lim; base += 32 * kHitBatch) {
-		HitLoad h[kHitBatch];
-#pragma unroll
-		for (int u = 0; u < kHitBatch; u++) {
-			const uint32_t i = base + u * 32 + lane;
-			if (i < lim)
-				h[u] = hit_issue(c, queue[i], q0);
-		}
-#pragma unroll
-		for (int u = 0; u < kHitBatch; u++) {
-			const uint32_t i = base + u * 32 + lane;
-			if (i < lim)
-				hit_finish<S>(c, h[u]);
-		}
-	}
-	__syncwarp();
+	hit_finish<S>(c, hit_issue(c, e, q0));
 }
 
-template <int KM, int S, int TQ> struct DevBody {
-	static __device__ __forceinline__ void run(State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ hw, int q0, int n, int k)
-	{
-		const int q = q0 + TQ;
-		if (q < n) {
-			const uint2 in = pl[(q + 1) * 32];
-			int oq = q - k + 1; // plane slot of the leaving base (position q-k), slot 0 = all-zero sentinel
-			oq = oq < 0 ? 0 : oq;
-			const uint2 out = pl[oq * 32];
-			step<KM, TQ>(st, in.x, in.y, out.x, out.y);
-			uint32_t m = 0;
-			if (q >= k - 1)
-				m = sampled_mask<TQ, S>(st);
-			hw[TQ * 32] = m;
-			DevBody<KM, S, TQ + 1>::run(st, pl, hw, q0, n, k);
+// A hit warp's work for one body: per half (16 positions) count the sampled k-mers (popc + warp prefix
+// sum), write them as a flat queue, then hash them kHitBatch per lane at a time.
+template <int S>
+__device__ __forceinline__ void drain_body(const WarpCtx& c, const uint32_t* __restrict__ hw, uint32_t* __restrict__ queue, uint32_t nq,
+    uint32_t q0, uint32_t lane)
+{
+#pragma unroll 1
+	for (uint32_t h0 = 0; h0 < nq; h0 += kHalfPos) {
+		const uint32_t h1 = min(h0 + kHalfPos, nq);
+		uint32_t cnt = 0;
+		for (uint32_t tq = h0; tq < h1; tq++)
+			cnt += __popc(hw[tq * 32 + lane]);
+		uint32_t inc = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+			if ((int)lane >= d)
+				inc += v;
 		}
+		const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+		if (total == 0)
+			continue;
+		uint32_t off = inc - cnt;
+		for (uint32_t tq = h0; tq < h1; tq++) {
+			uint32_t w = hw[tq * 32 + lane];
+			while (w) {
+				const uint32_t s = __ffs(w) - 1;
+				w &= w - 1;
+				const uint32_t e = s | (lane << 5) | (tq << 10);
+				if (off < kQueueCap)
+					queue[off] = e;
+				else
+					hit_slow<S>(c, e, q0); // queue overflow (skewed data): slow but exact
+				off++;
+			}
+		}
+		__syncwarp();
+		const uint32_t lim = min(total, (uint32_t)kQueueCap);
+#pragma unroll 1
+		for (uint32_t base = 0; base < lim; base += 32 * kHitBatch) {
+			HitLoad h[kHitBatch];
+#pragma unroll
+			for (int u = 0; u < kHitBatch; u++) {
+				const uint32_t i = base + u * 32 + lane;
+				if (i < lim)
+					h[u] = hit_issue(c, queue[i], q0);
+			}
+#pragma unroll
+			for (int u = 0; u < kHitBatch; u++) {
+				const uint32_t i = base + u * 32 + lane;
+				if (i < lim)
+					hit_finish<S>(c, h[u]);
+			}
+		}
+		__syncwarp();
+	}
+}
+
+// The scan is unrolled over kBlock positions only: after a block the 31+31 state registers are rotated
+// back into their home frame (register moves, which issue on the FMA pipe as IMAD.MOV and leave the
+// LOP3 pipe alone), so one ~14 KB block of code serves every position.  Unrolling the full ring
+// period (31) needs no moves but is a 52 KB loop, and four scan warps in different phases of it
+// starved on instruction fetch (43 % of their stall samples were no_instruction).
+
+template <int KM, int S, int U> struct DevBlock {
+	// Branch free on purpose: positions past the end of the read run on whatever the planes hold (their
+	// masks are never consumed: the hand-off carries the number of valid positions), so the compiler
+	// is free to hoist the shared-memory loads of all kBlock positions to the top of the block.
+	static __device__ __forceinline__ void run(State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ hw, int qb, int k)
+	{
+		const int q = qb + U;
+		const uint2 in = pl[(q + 1) * 32];
+		int oq = q - k + 1; // plane slot of the leaving base (position q-k), slot 0 = all-zero sentinel
+		oq = oq < 0 ? 0 : oq;
+		const uint2 out = pl[oq * 32];
+		step<KM, U>(st, in.x, in.y, out.x, out.y);
+		const uint32_t m = sampled_mask<U, S>(st);
+		hw[U * 32] = q >= k - 1 ? m : 0u;
+		DevBlock<KM, S, U + 1>::run(st, pl, hw, qb, k);
 	}
 };
-template <int KM, int S> struct DevBody<KM, S, 31> {
-	static __device__ __forceinline__ void run(State&, const uint2* __restrict__, uint32_t* __restrict__, int, int, int) {}
+template <int KM, int S> struct DevBlock<KM, S, kBlock> {
+	static __device__ __forceinline__ void run(State&, const uint2* __restrict__, uint32_t* __restrict__, int, int) {}
 };
+
+// After kBlock steps logical ring bit r sits in physical F[r - kBlock] / R[r + kBlock]: move it home.
+__device__ __forceinline__ void rotate_home(State& st)
+{
+	State t;
+#pragma unroll
+	for (int j = 0; j < 31; j++) {
+		t.F[j] = st.F[mod31(j - kBlock)];
+		t.R[j] = st.R[mod31(j + kBlock)];
+	}
+	st = t;
+}
 
 // Per scan warp: hand-off of one body's masks to the partner hit warp.
 struct BodyDesc {
 	uint32_t rb, q0, nq, nwords; // nq == 0: no more work
 };
 
+constexpr int kThreads = 384; // warpgroup 0: 4 scan warps; warpgroups 1 and 2: their hit warps for even / odd bodies
+constexpr int kScanRegs = 248, kHitRegs = 128; // 128*248 + 256*128 = 64512 <= 65536
+
 template <int KM, int S>
-__global__ void __launch_bounds__(kPairsMax * 64, 1) bitslice_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec,
+__global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec,
     BsLaunch L, const uint4* __restrict__ g_tab, const DevParams* __restrict__ P, uint32_t* __restrict__ ctr_k,
     unsigned long long* __restrict__ f1_k)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, npairs = blockDim.x >> 6;
-	const bool is_scan = warp < npairs;
-	const uint32_t pair = is_scan ? warp : warp - npairs;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t role = warp >> 2;  // 0 scan, 1 hit (buffer 0), 2 hit (buffer 1)
+	const uint32_t pair = warp & 3u;
+	const uint32_t npairs = L.pairs;
 	uint4* tab = reinterpret_cast<uint4*>(smem_raw);
 	for (uint32_t i = threadIdx.x; i < 8 * 256; i += blockDim.x)
 		tab[i] = g_tab[i];
-	// per pair: [planes][masks x2][queue][desc x2][mbarriers x4]
+	// per pair: [planes][masks x2][hit queue x2][desc x2][mbarriers x4]
 	const uint32_t plane_bytes = (1u + L.pos_cap) * 256u; // [slot 0 = zeros][position][lane] uint2
-	const uint32_t pair_bytes = plane_bytes + 2 * kMaskBytes + L.queue_cap * 4 + kPairMisc;
+	const uint32_t pair_bytes = plane_bytes + 2 * kMaskBytes + 2 * kQueueCap * 4 + kPairMisc;
 	unsigned char* pbase = smem_raw + kTabBytes + pair * pair_bytes;
 	uint2* planes = reinterpret_cast<uint2*>(pbase);
-	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(pbase + plane_bytes);          // [2][31][32]
-	uint32_t* queue = hwbuf + 2 * (kMaskBytes / 4);
-	BodyDesc* desc = reinterpret_cast<BodyDesc*>(queue + L.queue_cap);             // [2]
+	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(pbase + plane_bytes);          // [2][32][32]
+	uint32_t* queues = hwbuf + 2 * (kMaskBytes / 4);                              // [2][kQueueCap]
+	BodyDesc* desc = reinterpret_cast<BodyDesc*>(queues + 2 * kQueueCap);          // [2]
 	uint64_t* bar_full = reinterpret_cast<uint64_t*>(desc + 2);                    // [2]
 	uint64_t* bar_empty = bar_full + 2;                                            // [2]
-	if (is_scan) {
+	if (role == 0 && pair < npairs) {
 		planes[lane] = make_uint2(0u, 0u);
 		if (lane == 0) {
 			mbar_init(&bar_full[0], 1);
@@ -288,27 +336,35 @@ __global__ void __launch_bounds__(kPairsMax * 64, 1) bitslice_kernel(const uint3
 	c.rot_b = L.rot_b;
 	c.ctr_k = ctr_k;
 
-	if (!is_scan) {
-		// ================= hit warp: consume the masks of each body =================
-		for (uint32_t it = 0;; it++) {
-			const uint32_t b = it & 1u;
-			mbar_wait(&bar_full[b], (it >> 1) & 1u);
+	if (role != 0) {
+		// ================= hit warps: consume the masks of every other body =================
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHitRegs));
+		if (pair >= npairs)
+			return;
+		const uint32_t b = role - 1;
+		uint32_t* buf = hwbuf + b * (kMaskBytes / 4);
+		for (uint32_t u = 0;; u++) {
+			named_bar_sync(1 + pair * 2 + b, 64); // body ready (blocks in hardware, no polling)
 			const BodyDesc d = desc[b];
 			if (d.nq == 0)
 				break;
 			c.rb = d.rb;
 			c.nwords = d.nwords;
-			drain_body<S>(c, hwbuf + b * (kMaskBytes / 4), queue, L.queue_cap, d.nq, d.q0, lane);
+			drain_body<S>(c, buf, queues + b * kQueueCap, d.nq, d.q0, lane);
 			if (lane == 0)
 				mbar_arrive(&bar_empty[b]);
 		}
 		return;
 	}
 
-	// ================= scan warp =================
+	// ================= scan warps =================
+	asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kScanRegs));
+	if (pair >= npairs)
+		return;
 	const int k = (int)L.k;
 	unsigned long long f1_local = 0;
-	uint32_t it = 0; // bodies handed over so far
+	uint32_t uses[2] = { 0, 0 }; // hand-offs done per buffer
+	uint32_t it = 0;
 	const uint32_t n_tiles = (n_rec + kTileRecs - 1) / kTileRecs;
 	for (uint32_t tile = blockIdx.x * npairs + pair; tile < n_tiles; tile += gridDim.x * npairs) {
 		const uint32_t rb = tile * kTileRecs;
@@ -320,19 +376,20 @@ __global__ void __launch_bounds__(kPairsMax * 64, 1) bitslice_kernel(const uint3
 				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(words + nrb * stride), "r"(bytes) : "memory");
 			}
 		}
-		// ---- record lengths; is the tile uniform? ----
+		// ---- first 16 bytes of every record (length + 3 base words); is the tile uniform? ----
+		bool uniform = rb + kTileRecs <= n_rec;
+		uint4 v[32];
 		uint32_t len0 = 0;
-		bool uniform = true;
-		{
-			const uint32_t first_len = rb < n_rec ? __ldg(words + (uint64_t)rb * stride) : 0u;
-#pragma unroll 4
-			for (uint32_t s = 0; s < 32; s++) {
-				const uint32_t rec = rb + s * 32u + lane;
-				const uint32_t len = rec < n_rec ? __ldg(words + (uint64_t)rec * stride) : 0xFFFFFFFFu;
-				uniform = uniform && (len == first_len);
-			}
-			uniform = __all_sync(0xFFFFFFFFu, uniform);
-			len0 = first_len;
+		if (uniform) {
+#pragma unroll
+			for (int s = 0; s < 32; s++)
+				v[s] = __ldg(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride));
+			len0 = __shfl_sync(0xFFFFFFFFu, v[0].x, 0);
+			bool same = true;
+#pragma unroll
+			for (int s = 0; s < 32; s++)
+				same = same && (v[s].x == len0);
+			uniform = __all_sync(0xFFFFFFFFu, same);
 		}
 		if (!uniform || len0 > L.pos_cap) {
 			// general path, in place: each lane walks its own records with the 64-bit recurrence
@@ -353,69 +410,98 @@ __global__ void __launch_bounds__(kPairsMax * 64, 1) bitslice_kernel(const uint3
 			continue;
 		const uint32_t nwords = (uint32_t)(n + 15) >> 4;
 		// ---- 1. transpose packed bases into bit planes ----
-		// (the partner may still be hashing k-mers of the previous tile: it reads global memory, not the planes)
+		// (hit warps may still be hashing k-mers of the previous tile: they read global memory, not the planes)
 		{
 			const uint32_t ngroups = (nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
+#pragma unroll 1
 			for (uint32_t g = 0; g < ngroups; g++) {
-				uint4 v[32];
+				if (g) {
 #pragma unroll
-				for (int s = 0; s < 32; s++)
-					v[s] = __ldg(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride) + g);
-#pragma unroll
+					for (int s = 0; s < 32; s++)
+						v[s] = __ldg(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride) + g);
+				}
+#pragma unroll 1
 				for (int i = 0; i < 4; i++) {
 					const int w = (int)(g * 4) + i - 1; // base word index
 					if (w < 0 || w >= (int)nwords)
 						continue;
 					uint32_t A[32];
+					switch (i) {
+					case 0:
 #pragma unroll
-					for (int s = 0; s < 32; s++)
-						A[s] = i == 0 ? v[s].x : i == 1 ? v[s].y : i == 2 ? v[s].z : v[s].w;
+						for (int s = 0; s < 32; s++) A[s] = v[s].x;
+						break;
+					case 1:
+#pragma unroll
+						for (int s = 0; s < 32; s++) A[s] = v[s].y;
+						break;
+					case 2:
+#pragma unroll
+						for (int s = 0; s < 32; s++) A[s] = v[s].z;
+						break;
+					default:
+#pragma unroll
+						for (int s = 0; s < 32; s++) A[s] = v[s].w;
+						break;
+					}
 					transpose32(A);
+					uint2* dst = planes + (1 + 16 * w) * 32 + lane;
+					if (16 * w + 16 <= n) {
 #pragma unroll
-					for (int j = 0; j < 16; j++)
-						if (16 * w + j < n)
-							planes[(1 + 16 * w + j) * 32 + lane] = make_uint2(A[2 * j], A[2 * j + 1]);
+						for (int j = 0; j < 16; j++)
+							dst[j * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
+					} else {
+#pragma unroll
+						for (int j = 0; j < 16; j++)
+							if (16 * w + j < n)
+								dst[j * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
+					}
 				}
 			}
 		}
 		__syncwarp();
-		// ---- 2. scan; 3. hand each body's masks to the hit warp ----
+		// ---- 2. scan; 3. hand each body's masks to a hit warp ----
 		State st;
 #pragma unroll
 		for (int j = 0; j < 31; j++) {
 			st.F[j] = L.F0[j];
 			st.R[j] = L.R0[j];
 		}
-		for (int q0 = 0; q0 < n; q0 += 31) {
-			const int nq = min(31, n - q0);
+		for (int q0 = 0; q0 < n; q0 += kBodyPos) {
+			const int nq = min(kBodyPos, n - q0);
 			const bool has_windows = q0 + nq >= k; // some position of this body ends a full window
-			uint32_t b = it & 1u;
+			const uint32_t b = it & 1u;
 			uint32_t* hw = hwbuf + b * (kMaskBytes / 4);
-			if (it >= 2) // the partner must have finished the previous use of this buffer (bodies without windows write it too)
-				mbar_wait(&bar_empty[b], ((it >> 1) - 1) & 1u);
-			DevBody<KM, S, 0>::run(st, planes + lane, hw + lane, q0, n, k);
+			if (uses[b]) // the hit warp must have finished the previous use of this buffer (bodies without windows write it too)
+				mbar_wait(&bar_empty[b], (uses[b] - 1) & 1u);
+#pragma unroll 1
+			for (int qb = q0; qb < q0 + nq; qb += kBlock) {
+				DevBlock<KM, S, 0>::run(st, planes + lane, hw + (qb - q0) * 32 + lane, qb, k);
+				rotate_home(st);
+			}
 			if (has_windows) {
 				__syncwarp();
-				if (lane == 0) {
+				if (lane == 0)
 					desc[b] = BodyDesc{ rb, (uint32_t)q0, (uint32_t)nq, nwords };
-					mbar_arrive(&bar_full[b]);
-				}
+				__syncwarp();
+				named_bar_arrive(1 + pair * 2 + b, 64);
+				uses[b]++;
 				it++;
 			}
 		}
 		if (lane == 0)
 			f1_local += (unsigned long long)kTileRecs * (unsigned long long)(n - k + 1);
 	}
-	// tell the partner to stop
-	{
-		const uint32_t b = it & 1u;
-		if (it >= 2)
-			mbar_wait(&bar_empty[b], ((it >> 1) - 1) & 1u);
+	// tell both hit warps to stop
+#pragma unroll
+	for (uint32_t b = 0; b < 2; b++) {
+		if (uses[b])
+			mbar_wait(&bar_empty[b], (uses[b] - 1) & 1u);
 		__syncwarp();
-		if (lane == 0) {
+		if (lane == 0)
 			desc[b] = BodyDesc{ 0, 0, 0, 0 };
-			mbar_arrive(&bar_full[b]);
-		}
+		__syncwarp();
+		named_bar_arrive(1 + pair * 2 + b, 64);
 	}
 	// totKmer (ntcard.cpp:155): warp-reduce then one atomic per warp
 #pragma unroll
@@ -432,7 +518,7 @@ cudaError_t launch_one(const BsArgs& a)
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes);
 	if (e != cudaSuccess)
 		return e;
-	kern<<<a.grid, a.pairs * 64, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.d_tab, a.d_params, a.ctr_k, a.f1_k);
+	kern<<<a.grid, kThreads, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.d_tab, a.d_params, a.ctr_k, a.f1_k);
 	return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@ namespace bs {
 
 struct BsLaunch {          // per-k launch constants, passed by value
 	uint32_t k, ki, rBits, pos_cap; // pos_cap: positions the shared-memory planes of one scan warp can hold
-	uint32_t queue_cap;             // hit queue entries per pair
+	uint32_t pairs;                 // active scan warps per CTA (each with two hit warps)
 	uint32_t F0[31], R0[31];        // initial bit-sliced state (bitslice_core.cuh init_state)
 	uint64_t rot_a, rot_b;          // byte m: (k%32 + 32m) % 31 and % 33 for block m of the hit path (k < 288)
 };
@@ -28,8 +28,9 @@ struct BsArgs {
 };
 
 constexpr size_t kTabBytes = 8 * 256 * 16;
-constexpr size_t kMaskBytes = 31 * 128;               // one body's masks: [31 positions][32 lanes] words
+constexpr size_t kMaskBytes = 32 * 128;               // one body's masks: [32 positions][32 lanes] words
 constexpr size_t kPairMisc = 64;                      // 2 body descriptors + 4 mbarriers
+constexpr int kQueueCap = 288;                        // hit queue entries per hit warp: one HALF body (16 positions), expected 256 at s=7
 constexpr size_t kSmemMax = 232448;                   // 227 KB opt-in limit per CTA on sm_100
 
 // True when a kernel for (k mod 31, sBits) was compiled in.

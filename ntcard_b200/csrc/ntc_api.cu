@@ -145,7 +145,7 @@ void build_params(const ntc_ctx* c, ntc::DevParams* P)
 
 // Which k indices the bit-sliced kernel can take for this batch; plane capacity / warps per CTA in *cfg.
 struct BsConfig {
-	uint32_t kmask = 0, pairs = 0, pos_cap = 0, queue_cap = 0;
+	uint32_t kmask = 0, pairs = 0, pos_cap = 0;
 	size_t smem = 0;
 };
 
@@ -160,23 +160,19 @@ BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 			cfg.kmask |= 1u << ki;
 	if (!cfg.kmask)
 		return cfg;
-	// One CTA per SM: the byte tables plus, per (scan warp, hit warp) pair, bit planes for pos_cap positions,
-	// two mask buffers, the hit queue.  4 pairs when the records are short-read sized.
+	// One CTA per SM: the byte tables plus, per scan warp, bit planes for pos_cap positions and two
+	// mask/queue buffers (one per hit warp).  4 scan warps when the records are short-read sized.
 	const uint32_t need = 16u * (b.stride - 1);
 	for (uint32_t pairs = 4; pairs >= 1; pairs--) {
 		const size_t per_pair = ((ntc::bs::kSmemMax - ntc::bs::kTabBytes) / pairs) & ~(size_t)255;
-		const size_t fixed = 2 * ntc::bs::kMaskBytes + ntc::bs::kPairMisc;
-		uint32_t queue_cap = pairs == 4 ? 640 : 1024; // expected 31*1024/64 = 496 sampled k-mers per body at s=7
-		if (per_pair < fixed + queue_cap * 4 + 512)
-			continue;
-		const uint32_t cap = (uint32_t)((per_pair - fixed - queue_cap * 4) / 256) - 1;
-		// stride 12 (<= 176 bases) is the 150/151 bp short-read layout: keep 4 pairs; longer records of such a
-		// batch take the in-kernel general path
+		const size_t fixed = 2 * ntc::bs::kMaskBytes + 2 * ntc::bs::kQueueCap * 4 + ntc::bs::kPairMisc;
+		const uint32_t cap = (uint32_t)((per_pair - fixed) / 256) - 1;
+		// stride 12 (<= 176 bases) is the 150/151 bp short-read layout: keep 4 scan warps; longer records of
+		// such a batch take the in-kernel general path
 		if (cap >= need || (pairs == 4 && need <= 176 && cap >= 152)) {
 			cfg.pairs = pairs;
 			cfg.pos_cap = cap < need ? cap : need;
-			cfg.queue_cap = queue_cap;
-			cfg.smem = ntc::bs::kTabBytes + pairs * ((size_t)(1 + cfg.pos_cap) * 256 + fixed + queue_cap * 4);
+			cfg.smem = ntc::bs::kTabBytes + pairs * ((size_t)(1 + cfg.pos_cap) * 256 + fixed);
 			return cfg;
 		}
 	}
@@ -208,7 +204,7 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		a.n_rec = b.n_rec;
 		a.L = c->bs_launch[ki];
 		a.L.pos_cap = bs.pos_cap;
-		a.L.queue_cap = bs.queue_cap;
+		a.L.pairs = bs.pairs;
 		a.d_tab = c->d_bs_tab;
 		a.d_params = c->d_params;
 		a.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
