@@ -27,7 +27,8 @@ namespace ntc {
 namespace bs {
 
 constexpr int kBlock = 4;    // scan positions per unrolled block (see DevBlock)
-constexpr int kBodyPos = 32; // positions per hand-off to a hit warp (4 blocks)
+constexpr int kBodyPos = 16; // positions per hand-off to a hit warp (4 blocks)
+constexpr int kNumBuf = 4;   // mask buffers per scan warp: even ones drained by hit warp A, odd ones by hit warp B
 constexpr int kPairsMax = 4;       // scan warps per CTA; each has one partner "hit" warp on the same SM sub-partition
 constexpr uint32_t kTileRecs = 1024;
 
@@ -179,7 +180,6 @@ template <int S> __device__ __forceinline__ void hit_finish(const WarpCtx& c, co
 }
 
 constexpr int kHitBatch = 4;  // k-mers per lane whose loads are in flight together
-constexpr int kHalfPos = 16;  // a body's masks are compacted and hashed in two halves
 
 // queue-overflow path, kept out of line
 template <int S> static __device__ __noinline__ void hit_slow(const WarpCtx& c, uint32_t e, uint32_t q0)
@@ -187,62 +187,60 @@ template <int S> static __device__ __noinline__ void hit_slow(const WarpCtx& c, 
 	hit_finish<S>(c, hit_issue(c, e, q0));
 }
 
-// A hit warp's work for one body: per half (16 positions) count the sampled k-mers (popc + warp prefix
-// sum), write them as a flat queue, then hash them kHitBatch per lane at a time.
+// A hit warp's work for one hand-off unit (<= 16 positions): count the sampled k-mers (popc + warp prefix
+// sum), write them as a flat queue, then hash them kHitBatch per lane at a time.  Deliberately compact
+// code (loops, not unrolled): the instruction cache is shared with the scan warp on the same sub-partition,
+// and an unrolled variant of this function made the scan warp starve on instruction fetch.
 template <int S>
 __device__ __forceinline__ void drain_body(const WarpCtx& c, const uint32_t* __restrict__ hw, uint32_t* __restrict__ queue, uint32_t nq,
     uint32_t q0, uint32_t lane)
 {
-#pragma unroll 1
-	for (uint32_t h0 = 0; h0 < nq; h0 += kHalfPos) {
-		const uint32_t h1 = min(h0 + kHalfPos, nq);
-		uint32_t cnt = 0;
-		for (uint32_t tq = h0; tq < h1; tq++)
-			cnt += __popc(hw[tq * 32 + lane]);
-		uint32_t inc = cnt;
+	uint32_t cnt = 0;
+	for (uint32_t tq = 0; tq < nq; tq++)
+		cnt += __popc(hw[tq * 32 + lane]);
+	uint32_t inc = cnt;
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-			if ((int)lane >= d)
-				inc += v;
-		}
-		const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-		if (total == 0)
-			continue;
-		uint32_t off = inc - cnt;
-		for (uint32_t tq = h0; tq < h1; tq++) {
-			uint32_t w = hw[tq * 32 + lane];
-			while (w) {
-				const uint32_t s = __ffs(w) - 1;
-				w &= w - 1;
-				const uint32_t e = s | (lane << 5) | (tq << 10);
-				if (off < kQueueCap)
-					queue[off] = e;
-				else
-					hit_slow<S>(c, e, q0); // queue overflow (skewed data): slow but exact
-				off++;
-			}
-		}
-		__syncwarp();
-		const uint32_t lim = min(total, (uint32_t)kQueueCap);
-#pragma unroll 1
-		for (uint32_t base = 0; base < lim; base += 32 * kHitBatch) {
-			HitLoad h[kHitBatch];
-#pragma unroll
-			for (int u = 0; u < kHitBatch; u++) {
-				const uint32_t i = base + u * 32 + lane;
-				if (i < lim)
-					h[u] = hit_issue(c, queue[i], q0);
-			}
-#pragma unroll
-			for (int u = 0; u < kHitBatch; u++) {
-				const uint32_t i = base + u * 32 + lane;
-				if (i < lim)
-					hit_finish<S>(c, h[u]);
-			}
-		}
-		__syncwarp();
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+		if ((int)lane >= d)
+			inc += v;
 	}
+	const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+	if (total == 0)
+		return;
+	uint32_t off = inc - cnt;
+	for (uint32_t tq = 0; tq < nq; tq++) {
+		uint32_t w = hw[tq * 32 + lane];
+		while (w) {
+			const uint32_t s = __ffs(w) - 1;
+			w &= w - 1;
+			const uint32_t e = s | (lane << 5) | (tq << 10);
+			if (off < kQueueCap)
+				queue[off] = e;
+			else
+				hit_slow<S>(c, e, q0); // queue overflow (skewed data): slow but exact
+			off++;
+		}
+	}
+	__syncwarp();
+	const uint32_t lim = min(total, (uint32_t)kQueueCap);
+#pragma unroll 1
+	for (uint32_t base = 0; base < lim; base += 32 * kHitBatch) {
+		HitLoad h[kHitBatch];
+#pragma unroll
+		for (int u = 0; u < kHitBatch; u++) {
+			const uint32_t i = base + u * 32 + lane;
+			if (i < lim)
+				h[u] = hit_issue(c, queue[i], q0);
+		}
+#pragma unroll
+		for (int u = 0; u < kHitBatch; u++) {
+			const uint32_t i = base + u * 32 + lane;
+			if (i < lim)
+				hit_finish<S>(c, h[u]);
+		}
+	}
+	__syncwarp();
 }
 
 // The scan is unrolled over kBlock positions only: after a block the 31+31 state registers are rotated
@@ -290,7 +288,7 @@ struct BodyDesc {
 };
 
 constexpr int kThreads = 384; // warpgroup 0: 4 scan warps; warpgroups 1 and 2: their hit warps for even / odd bodies
-constexpr int kScanRegs = 248, kHitRegs = 128; // 128*248 + 256*128 = 64512 <= 65536
+constexpr int kScanRegs = 248, kHitRegs = 128; // 128*248 + 256*128 = 64512 = the launch allocation (384*168); asking for all 65536 never completes
 
 template <int KM, int S>
 __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec,
@@ -307,22 +305,17 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		tab[i] = g_tab[i];
 	// per pair: [planes][masks x2][hit queue x2][desc x2][mbarriers x4]
 	const uint32_t plane_bytes = (1u + L.pos_cap) * 256u; // [slot 0 = zeros][position][lane] uint2
-	const uint32_t pair_bytes = plane_bytes + 2 * kMaskBytes + 2 * kQueueCap * 4 + kPairMisc;
+	const uint32_t pair_bytes = plane_bytes + kNumBuf * kMaskBytes + 2 * kQueueCap * 4 + kPairMisc;
 	unsigned char* pbase = smem_raw + kTabBytes + pair * pair_bytes;
 	uint2* planes = reinterpret_cast<uint2*>(pbase);
-	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(pbase + plane_bytes);          // [2][32][32]
-	uint32_t* queues = hwbuf + 2 * (kMaskBytes / 4);                              // [2][kQueueCap]
-	BodyDesc* desc = reinterpret_cast<BodyDesc*>(queues + 2 * kQueueCap);          // [2]
-	uint64_t* bar_full = reinterpret_cast<uint64_t*>(desc + 2);                    // [2]
-	uint64_t* bar_empty = bar_full + 2;                                            // [2]
+	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(pbase + plane_bytes);          // [kNumBuf][16][32]
+	uint32_t* queues = hwbuf + kNumBuf * (kMaskBytes / 4);                        // [2][kQueueCap]
+	BodyDesc* desc = reinterpret_cast<BodyDesc*>(queues + 2 * kQueueCap);          // [kNumBuf]
+	uint64_t* bar_empty = reinterpret_cast<uint64_t*>(desc + kNumBuf);             // [kNumBuf]
 	if (role == 0 && pair < npairs) {
 		planes[lane] = make_uint2(0u, 0u);
-		if (lane == 0) {
-			mbar_init(&bar_full[0], 1);
-			mbar_init(&bar_full[1], 1);
-			mbar_init(&bar_empty[0], 1);
-			mbar_init(&bar_empty[1], 1);
-		}
+		if (lane < kNumBuf)
+			mbar_init(&bar_empty[lane], 1);
 	}
 	__syncthreads();
 
@@ -341,16 +334,16 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHitRegs));
 		if (pair >= npairs)
 			return;
-		const uint32_t b = role - 1;
-		uint32_t* buf = hwbuf + b * (kMaskBytes / 4);
+		const uint32_t hw_id = role - 1; // hit warp A drains buffers 0,2; B drains 1,3
 		for (uint32_t u = 0;; u++) {
-			named_bar_sync(1 + pair * 2 + b, 64); // body ready (blocks in hardware, no polling)
+			const uint32_t b = hw_id + 2u * (u & 1u);
+			named_bar_sync(pair * kNumBuf + b, 64); // unit ready (blocks in hardware, no polling)
 			const BodyDesc d = desc[b];
 			if (d.nq == 0)
 				break;
 			c.rb = d.rb;
 			c.nwords = d.nwords;
-			drain_body<S>(c, buf, queues + b * kQueueCap, d.nq, d.q0, lane);
+			drain_body<S>(c, hwbuf + b * (kMaskBytes / 4), queues + hw_id * kQueueCap, d.nq, d.q0, lane);
 			if (lane == 0)
 				mbar_arrive(&bar_empty[b]);
 		}
@@ -363,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		return;
 	const int k = (int)L.k;
 	unsigned long long f1_local = 0;
-	uint32_t uses[2] = { 0, 0 }; // hand-offs done per buffer
+	uint32_t uses[kNumBuf] = { 0, 0, 0, 0 }; // hand-offs done per buffer
 	uint32_t it = 0;
 	const uint32_t n_tiles = (n_rec + kTileRecs - 1) / kTileRecs;
 	for (uint32_t tile = blockIdx.x * npairs + pair; tile < n_tiles; tile += gridDim.x * npairs) {
@@ -470,10 +463,11 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		for (int q0 = 0; q0 < n; q0 += kBodyPos) {
 			const int nq = min(kBodyPos, n - q0);
 			const bool has_windows = q0 + nq >= k; // some position of this body ends a full window
-			const uint32_t b = it & 1u;
+			const uint32_t b = it & (kNumBuf - 1);
 			uint32_t* hw = hwbuf + b * (kMaskBytes / 4);
-			if (uses[b]) // the hit warp must have finished the previous use of this buffer (bodies without windows write it too)
-				mbar_wait(&bar_empty[b], (uses[b] - 1) & 1u);
+			const uint32_t ub = b == 0 ? uses[0] : b == 1 ? uses[1] : b == 2 ? uses[2] : uses[3];
+			if (ub) // the hit warp must have finished the previous use of this buffer (units without windows write it too)
+				mbar_wait(&bar_empty[b], (ub - 1) & 1u);
 #pragma unroll 1
 			for (int qb = q0; qb < q0 + nq; qb += kBlock) {
 				DevBlock<KM, S, 0>::run(st, planes + lane, hw + (qb - q0) * 32 + lane, qb, k);
@@ -484,24 +478,28 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 				if (lane == 0)
 					desc[b] = BodyDesc{ rb, (uint32_t)q0, (uint32_t)nq, nwords };
 				__syncwarp();
-				named_bar_arrive(1 + pair * 2 + b, 64);
-				uses[b]++;
+				named_bar_arrive(pair * kNumBuf + b, 64);
+#pragma unroll
+				for (int i = 0; i < kNumBuf; i++)
+					uses[i] += (uint32_t)i == b;
 				it++;
 			}
 		}
 		if (lane == 0)
 			f1_local += (unsigned long long)kTileRecs * (unsigned long long)(n - k + 1);
 	}
-	// tell both hit warps to stop
-#pragma unroll
-	for (uint32_t b = 0; b < 2; b++) {
-		if (uses[b])
-			mbar_wait(&bar_empty[b], (uses[b] - 1) & 1u);
+	// tell both hit warps to stop: the next two units (one per hit warp) carry nq = 0
+#pragma unroll 1
+	for (uint32_t e = 0; e < 2; e++, it++) {
+		const uint32_t b = it & (kNumBuf - 1);
+		const uint32_t ub = b == 0 ? uses[0] : b == 1 ? uses[1] : b == 2 ? uses[2] : uses[3];
+		if (ub)
+			mbar_wait(&bar_empty[b], (ub - 1) & 1u);
 		__syncwarp();
 		if (lane == 0)
 			desc[b] = BodyDesc{ 0, 0, 0, 0 };
 		__syncwarp();
-		named_bar_arrive(1 + pair * 2 + b, 64);
+		named_bar_arrive(pair * kNumBuf + b, 64);
 	}
 	// totKmer (ntcard.cpp:155): warp-reduce then one atomic per warp
 #pragma unroll

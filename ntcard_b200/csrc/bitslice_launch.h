@@ -28,8 +28,9 @@ struct BsArgs {
 };
 
 constexpr size_t kTabBytes = 8 * 256 * 16;
-constexpr size_t kMaskBytes = 32 * 128;               // one body's masks: [32 positions][32 lanes] words
-constexpr size_t kPairMisc = 64;                      // 2 body descriptors + 4 mbarriers
+constexpr size_t kMaskBytes = 16 * 128;               // one hand-off unit's masks: [16 positions][32 lanes] words
+constexpr size_t kPairMisc = 128;                     // 4 unit descriptors + 4 mbarriers
+constexpr size_t kNumMaskBuf = 4;
 constexpr int kQueueCap = 288;                        // hit queue entries per hit warp: one HALF body (16 positions), expected 256 at s=7
 constexpr size_t kSmemMax = 232448;                   // 227 KB opt-in limit per CTA on sm_100
 

@@ -165,7 +165,7 @@ BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 	const uint32_t need = 16u * (b.stride - 1);
 	for (uint32_t pairs = 4; pairs >= 1; pairs--) {
 		const size_t per_pair = ((ntc::bs::kSmemMax - ntc::bs::kTabBytes) / pairs) & ~(size_t)255;
-		const size_t fixed = 2 * ntc::bs::kMaskBytes + 2 * ntc::bs::kQueueCap * 4 + ntc::bs::kPairMisc;
+		const size_t fixed = ntc::bs::kNumMaskBuf * ntc::bs::kMaskBytes + 2 * ntc::bs::kQueueCap * 4 + ntc::bs::kPairMisc;
 		const uint32_t cap = (uint32_t)((per_pair - fixed) / 256) - 1;
 		// stride 12 (<= 176 bases) is the 150/151 bp short-read layout: keep 4 scan warps; longer records of
 		// such a batch take the in-kernel general path
