@@ -101,6 +101,14 @@ int ntc_counters_device(ntc_ctx* ctx, void** d_counters, size_t* n_counters);
 int ntc_totals(ntc_ctx* ctx, uint64_t* totKmer /* [nK] */); /* syncs */
 int ntc_set_totals(ntc_ctx* ctx, const uint64_t* totKmer);  /* after an all-reduce of F1 */
 
+/* Counter-value histogram (values >= 1 only; entry 0 of every table is left 0) of the range
+ * [first, first+n) of the flat counter array, read from the DEVICE pointer d_counters (which points at
+ * element `first`): the slice a rank owns after a reduce-scatter of the sketch.  Values are narrowed
+ * mod 2^16 first.  p_hist: [nK][2][65536] uint32, host.  After summing the histograms of all slices the
+ * caller sets p[t][0] = 2^rBits - sum_{v>=1} p[t][v].  first and n must be multiples of
+ * min(65536, 2^rBits). */
+int ntc_hist_range(ntc_ctx* ctx, const void* d_counters, uint64_t first, uint64_t n, uint32_t* p_hist);
+
 /* Finish: wait for the device, narrow counters mod 2^16 (the reference's
  * uint16_t ++ wraps, ntcard.cpp:133,143) and return
  *   t_Counter : [nK][2][2^rBits] uint16, host, caller-owned, may be NULL

@@ -19,7 +19,7 @@ KERNEL_AUTO, KERNEL_ROLL64, KERNEL_BITSLICE = 0, 1, 2
 # every symbol include/ntcard_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_submit", "ntc_submit_device", "ntc_wait",
-    "ntc_sync", "ntc_counters_device", "ntc_totals", "ntc_set_totals", "ntc_finish", "ntc_estimate",
+    "ntc_sync", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_set_totals", "ntc_finish", "ntc_estimate",
     "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
     "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_device_count",
     "ntc_last_error", "ntc_version",
@@ -52,6 +52,7 @@ def _load():
         "ntc_totals": (C.c_int, [vp, u64p]),
         "ntc_set_totals": (C.c_int, [vp, u64p]),
         "ntc_finish": (C.c_int, [vp, vp, u64p, vp]),
+        "ntc_hist_range": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp]),
         "ntc_estimate": (C.c_int, [vp, vp, C.c_uint, C.c_uint, C.c_uint, dblp, dblp]),
         "ntc_host_alloc": (vp, [C.c_size_t]),
         "ntc_host_free": (None, [vp]),
@@ -264,6 +265,13 @@ class Sketch:
         _check(lib.ntc_finish(self.h, t.ctypes.data if counters else None, tot.ctypes.data_as(C.POINTER(C.c_uint64)),
                               p.ctypes.data if hist else None))
         return t, tot, p
+
+    def hist_range(self, d_counters, first, n):
+        """Counter-value histogram (v >= 1) of the slice [first, first+n) of the flat counters held at the
+        device pointer d_counters (e.g. this rank's reduce-scatter output).  Returns uint32 [nK,2,65536]."""
+        p = np.zeros((self.nK, 2, 65536), dtype=np.uint32)
+        _check(lib.ntc_hist_range(self.h, d_counters, first, n, p.ctypes.data))
+        return p
 
     def gen_packed_device(self, seed, first, n, L, mode, U, stride, d_words):
         _check(lib.ntc_gen_packed_device(self.h, seed, first, n, L, mode, U, stride, d_words))

@@ -26,6 +26,7 @@ cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_p
     int n_sm, cudaStream_t st);
 cudaError_t launch_narrow_hist(const uint32_t* d_counters, uint32_t n_tables, uint64_t n_per_table, uint16_t* d_narrow,
     uint32_t* d_phist, cudaStream_t st);
+cudaError_t launch_hist_range(const uint32_t* d_src, uint64_t first, uint64_t n, uint32_t rBits, uint32_t* d_phist, cudaStream_t st);
 cudaError_t launch_gen_packed(uint64_t S, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U, uint32_t stride,
     uint32_t* d_words, cudaStream_t st);
 

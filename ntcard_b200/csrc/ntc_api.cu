@@ -629,6 +629,28 @@ int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_h
 	return NTC_OK;
 }
 
+int ntc_hist_range(ntc_ctx* c, const void* d_counters, uint64_t first, uint64_t n, uint32_t* p_hist)
+{
+	if (!c || !d_counters || !p_hist || first + n > c->n_counters)
+		return set_err(NTC_EINVAL, "ntc_hist_range: bad argument");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	const uint32_t n_tables = c->nK * NTC_NSAMP;
+	const size_t hist_bytes = (size_t)n_tables * 65536 * sizeof(uint32_t);
+	if (!c->d_phist)
+		CK(cudaMalloc((void**)&c->d_phist, hist_bytes));
+	CK(cudaMemsetAsync(c->d_phist, 0, hist_bytes, c->stream));
+	cudaError_t e = ntc::launch_hist_range((const uint32_t*)d_counters, first, n, c->rBits, c->d_phist, c->stream);
+	if (e == cudaErrorInvalidValue)
+		return set_err(NTC_EINVAL, "ntc_hist_range: first and n must be multiples of min(65536, 2^rBits)");
+	CK(e);
+	c->n_launches++;
+	CK(cudaMemcpyAsync(p_hist, c->d_phist, hist_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return NTC_OK;
+}
+
 void* ntc_host_alloc(size_t bytes)
 {
 	void* p = nullptr;

@@ -129,6 +129,33 @@ __global__ void __launch_bounds__(256) narrow_hist_kernel(const uint32_t* __rest
 				atomicAdd(&ph[i], sh[i]);
 }
 
+// Histogram of an arbitrary chunk-aligned range [first, first+n) of the flat counter array (the slice a
+// rank owns after a reduce-scatter).  src points at element `first`.
+__global__ void __launch_bounds__(256) hist_range_kernel(const uint32_t* __restrict__ src, uint64_t first, uint64_t n, uint32_t rBits,
+    uint32_t chunk, uint32_t* __restrict__ p_hist)
+{
+	__shared__ uint32_t sh[HIST_SMEM_BINS];
+	for (uint32_t i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+		sh[i] = 0;
+	__syncthreads();
+	const uint64_t c0 = (uint64_t)blockIdx.x * chunk;
+	const uint64_t c1 = min(c0 + chunk, n);
+	uint32_t* ph = p_hist + ((first + c0) >> rBits) * 65536; // the chunk lies inside one table
+	for (uint64_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+		const uint32_t v = src[i] & 0xFFFFu;
+		if (v) {
+			if (v < HIST_SMEM_BINS)
+				atomicAdd(&sh[v], 1u);
+			else
+				atomicAdd(&ph[v], 1u);
+		}
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+		if (sh[i])
+			atomicAdd(&ph[i], sh[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // synthetic reads: word w (32 bases) of read i under seed S is mix64((S<<48)^(i<<12)^w),
 // base j of the word = (v >> 2j) & 3 -- which already IS the 2-bit packing.
@@ -231,6 +258,18 @@ cudaError_t launch_narrow_hist(const uint32_t* d_counters, uint32_t n_tables, ui
 	const uint32_t chunk = (uint32_t)(n_per_table < 65536 ? n_per_table : 65536);
 	const uint64_t chunks_per_table = (n_per_table + chunk - 1) / chunk;
 	narrow_hist_kernel<<<(unsigned)(n_tables * chunks_per_table), 256, 0, st>>>(d_counters, n_per_table, chunk, d_narrow, d_phist);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_hist_range(const uint32_t* d_src, uint64_t first, uint64_t n, uint32_t rBits, uint32_t* d_phist, cudaStream_t st)
+{
+	const uint64_t per_table = (uint64_t)1 << rBits;
+	const uint32_t chunk = (uint32_t)(per_table < 65536 ? per_table : 65536);
+	if (n == 0)
+		return cudaSuccess;
+	if (first % chunk || n % chunk)
+		return cudaErrorInvalidValue;
+	hist_range_kernel<<<(unsigned)(n / chunk), 256, 0, st>>>(d_src, first, n, rBits, chunk, d_phist);
 	return cudaGetLastError();
 }
 

@@ -36,3 +36,25 @@ def all_reduce_sketch(counters: torch.Tensor, totals) -> np.ndarray:
 def narrow_counters(counters_u32: np.ndarray) -> np.ndarray:
     """uint32 -> uint16 mod 2^16: the reference's `uint16_t ++` wrap (ntcard.cpp:133,143)."""
     return (counters_u32 & 0xFFFF).astype(np.uint16)
+
+
+def reduce_scatter_hist(sketch, counters: torch.Tensor, rBits: int):
+    """The cheaper reduction when only F0 / f_i are wanted: compEst needs the counter-VALUE histogram, not
+    the table.  reduce-scatter the uint32 counters (each rank receives the summed 1/N slice: half the wire
+    traffic of an all-reduce), histogram the narrowed slice on the device, all-reduce the 512 KiB/k
+    histograms.  Returns p_hist uint32 [nK, 2, 65536] (identical on all ranks), ready for estimate()."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    n = counters.numel()
+    if world == 1:
+        p = sketch.hist_range(counters.data_ptr(), 0, n)
+    else:
+        rank = dist.get_rank()
+        assert n % world == 0
+        mine = torch.empty(n // world, dtype=counters.dtype, device=counters.device)
+        dist.reduce_scatter_tensor(mine, counters, op=dist.ReduceOp.SUM)
+        p = sketch.hist_range(mine.data_ptr(), rank * (n // world), n // world)
+        pt = torch.from_numpy(p.astype(np.int64)).to(counters.device)
+        dist.all_reduce(pt, op=dist.ReduceOp.SUM)
+        p = pt.cpu().numpy().astype(np.uint32)
+    p[:, :, 0] = (1 << rBits) - p[:, :, 1:].sum(axis=2, dtype=np.uint64).astype(np.uint32)
+    return p

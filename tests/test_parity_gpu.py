@@ -264,3 +264,27 @@ def test_bitslice_refuses_unsupported():
         words = nt.gen_packed(1, 0, 2048, 150, 0, 0, 12)
         with pytest.raises(nt.NtcError):
             sk.submit(words, None, 2048, 12)
+
+
+def test_hist_range_matches_bincount(oracle):
+    """ntc_hist_range (the per-rank histogram of a reduce-scattered slice) against numpy on the same counters."""
+    import torch
+    a = oracle.gen_reads(8, 0, 20000, 150, 1, 4000)
+    reads = [bytes(a[i * 150:(i + 1) * 150]) for i in range(20000)]
+    rBits = 18
+    with nt.Sketch([20, 32], rBits=rBits, sBits=3) as sk:
+        sk.submit_reads(reads)
+        sk.sync()
+        ptr, n = sk.counters_device()
+        t, _, p_full = sk.finish(counters=True, hist=True)
+        parts = np.zeros_like(p_full)
+        world = 4
+        for r in range(world):
+            parts += sk.hist_range(ptr + 4 * r * (n // world), r * (n // world), n // world)
+        parts[:, :, 0] = (1 << rBits) - parts[:, :, 1:].sum(axis=2)
+        assert np.array_equal(parts, p_full)
+        for ki in range(2):
+            for tb in range(2):
+                assert np.array_equal(p_full[ki, tb], np.bincount(t[ki, tb], minlength=65536))
+        with pytest.raises(nt.NtcError):
+            sk.hist_range(ptr, 100, 1000)   # not chunk aligned
