@@ -41,6 +41,7 @@ struct WarpCtx {
 	const uint4* tab;   // shared: [8][256] {FB.lo, FB.hi, RB.lo, RB.hi}
 	uint64_t rot_a, rot_b; // byte m: (t + 32m) % 31 and % 33 (rotation of RB_m)
 	uint32_t* __restrict__ ctr_k;
+	uint64_t red_policy;   // L2 evict_first cache policy for the sketch increments
 };
 
 // ---- mbarrier helpers (shared::cta) -----------------------------------------------------------------
@@ -175,7 +176,9 @@ template <int S> __device__ __forceinline__ void hit_finish(const WarpCtx& c, co
 	const bool t1 = (hh >> (32 - S)) == ((1u << (S - 1)) - 1u);
 	if (t0 || t1) {
 		const uint32_t idx = ((t1 ? 1u : 0u) << c.rBits) | (hl & ((1u << c.rBits) - 1u));
-		atomicAdd(c.ctr_k + idx, 1u);
+		// fire-and-forget increment; the sketch sector is streaming data (one touch), so let it leave L2 first and
+		// keep the packed reads of the tiles in flight resident (the hit path re-reads them)
+		asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(c.ctr_k + idx), "r"(1u), "l"(c.red_policy) : "memory");
 	}
 }
 
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 	c.rot_a = L.rot_a;
 	c.rot_b = L.rot_b;
 	c.ctr_k = ctr_k;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.red_policy));
 
 	if (role != 0) {
 		// ================= hit warps: consume the masks of every other body =================
@@ -361,14 +365,6 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 	const uint32_t n_tiles = (n_rec + kTileRecs - 1) / kTileRecs;
 	for (uint32_t tile = blockIdx.x * npairs + pair; tile < n_tiles; tile += gridDim.x * npairs) {
 		const uint32_t rb = tile * kTileRecs;
-		// warm L2 with the next tile of this warp while this one is processed (bulk async prefetch)
-		{
-			const uint64_t nrb = (uint64_t)(tile + gridDim.x * npairs) * kTileRecs;
-			if (lane == 0 && nrb + kTileRecs <= n_rec) {
-				const uint32_t bytes = kTileRecs * stride * 4u;
-				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(words + nrb * stride), "r"(bytes) : "memory");
-			}
-		}
 		// ---- first 16 bytes of every record (length + 3 base words); is the tile uniform? ----
 		bool uniform = rb + kTileRecs <= n_rec;
 		uint4 v[32];
@@ -462,6 +458,15 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		}
 		for (int q0 = 0; q0 < n; q0 += kBodyPos) {
 			const int nq = min(kBodyPos, n - q0);
+			if (q0 <= n / 2 && n / 2 < q0 + kBodyPos) {
+				// half way through: warm L2 with this warp's next tile (bulk async prefetch). Earlier is too early -- at
+				// ~90 us per tile the lines would be evicted again by the sketch traffic before they are used.
+				const uint64_t nrb = (uint64_t)(tile + gridDim.x * npairs) * kTileRecs;
+				if (lane == 0 && nrb + kTileRecs <= n_rec) {
+					const uint32_t bytes = kTileRecs * stride * 4u;
+					asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(words + nrb * stride), "r"(bytes) : "memory");
+				}
+			}
 			const bool has_windows = q0 + nq >= k; // some position of this body ends a full window
 			const uint32_t b = it & (kNumBuf - 1);
 			uint32_t* hw = hwbuf + b * (kMaskBytes / 4);
