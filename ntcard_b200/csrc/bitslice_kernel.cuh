@@ -28,7 +28,6 @@ namespace bs {
 
 constexpr int kBlock = 4;    // scan positions per unrolled block (see DevBlock)
 constexpr int kBodyPos = 16; // positions per hand-off to a hit warp (4 blocks)
-constexpr int kNumBuf = 4;   // mask buffers per scan warp: even ones drained by hit warp A, odd ones by hit warp B
 constexpr int kPairsMax = 4;       // scan warps per CTA; each has one partner "hit" warp on the same SM sub-partition
 constexpr uint32_t kTileRecs = 1024;
 
@@ -42,6 +41,7 @@ struct WarpCtx {
 	uint64_t rot_a, rot_b; // byte m: (t + 32m) % 31 and % 33 (rotation of RB_m)
 	uint32_t* __restrict__ ctr_k;
 	uint64_t red_policy;   // L2 evict_first cache policy for the sketch increments
+	uint64_t keep_policy;  // L2 evict_last cache policy for the packed reads
 };
 
 // ---- mbarrier helpers (shared::cta) -----------------------------------------------------------------
@@ -69,6 +69,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 	    : "memory");
 }
 
+// Consumer-side wait: poll, and sleep between polls -- an idle hit warp must not eat the issue slots of the scan
+// warp it shares a sub-partition with (a bare try_wait loop there was a third of all issued instructions).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	for (;;) {
+		asm volatile(
+		    "{\n\t"
+		    ".reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t"
+		    "}"
+		    : "=r"(done)
+		    : "r"(smem_u32(bar)), "r"(parity)
+		    : "memory");
+		if (done)
+			break;
+		__nanosleep(128);
+	}
+}
+
 // Named barriers (bar.sync / bar.arrive) for the producer -> consumer direction: a waiting hit warp is
 // descheduled by the hardware and costs no issue slots (an mbarrier try_wait loop does: a third of all
 // issued instructions were idle hit warps polling).
@@ -79,6 +100,23 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
 {
 	asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 128-bit / 32-bit loads of the packed reads with an L2 evict_last hint: the hit path comes back to these lines
+// ~100 us later, after gigabytes of sketch sectors have streamed through L2.
+__device__ __forceinline__ uint4 ldg_keep_v4(const uint4* p, uint64_t policy)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+	             : "l"(p), "l"(policy));
+	return r;
+}
+__device__ __forceinline__ uint32_t ldg_keep_u32(const uint32_t* p, uint64_t policy)
+{
+	uint32_t r;
+	asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+	return r;
 }
 
 // srol applied n times, for n given as (a, b) = (n % 31, n % 33): rotate the upper ring by a, the lower by b.
@@ -106,9 +144,9 @@ __device__ __forceinline__ HitLoad hit_issue(const WarpCtx& c, uint32_t e, uint3
 	h.p = q0 + tq + 1u - c.k;
 	h.b = c.words + (uint64_t)rec * c.stride + 1;
 	const uint32_t wi = (h.p + (c.k & 31u)) >> 4;
-	h.x0 = __ldg(h.b + min(wi, c.nwords - 1));
-	h.x1 = __ldg(h.b + min(wi + 1, c.nwords - 1));
-	h.x2 = __ldg(h.b + min(wi + 2, c.nwords - 1));
+	h.x0 = ldg_keep_u32(h.b + min(wi, c.nwords - 1), c.keep_policy);
+	h.x1 = ldg_keep_u32(h.b + min(wi + 1, c.nwords - 1), c.keep_policy);
+	h.x2 = ldg_keep_u32(h.b + min(wi + 2, c.nwords - 1), c.keep_policy);
 	return h;
 }
 
@@ -199,6 +237,7 @@ __device__ __forceinline__ void drain_body(const WarpCtx& c, const uint32_t* __r
     uint32_t q0, uint32_t lane)
 {
 	uint32_t cnt = 0;
+#pragma unroll 4
 	for (uint32_t tq = 0; tq < nq; tq++)
 		cnt += __popc(hw[tq * 32 + lane]);
 	uint32_t inc = cnt;
@@ -254,23 +293,23 @@ __device__ __forceinline__ void drain_body(const WarpCtx& c, const uint32_t* __r
 
 template <int KM, int S, int U> struct DevBlock {
 	// Branch free on purpose: positions past the end of the read run on whatever the planes hold (their
-	// masks are never consumed: the hand-off carries the number of valid positions), so the compiler
-	// is free to hoist the shared-memory loads of all kBlock positions to the top of the block.
-	static __device__ __forceinline__ void run(State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ hw, int qb, int k)
+	// masks are never consumed: the hand-off carries the number of valid positions).
+	// Planes live in a ring of rmask+1 positions (slot = position mod ring size); slot rmask+1 is all zero and
+	// stands for the virtual bases before the read (window not full yet).
+	static __device__ __forceinline__ void run(State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ hw, int qb, int k, int rmask)
 	{
 		const int q = qb + U;
-		const uint2 in = pl[(q + 1) * 32];
-		int oq = q - k + 1; // plane slot of the leaving base (position q-k), slot 0 = all-zero sentinel
-		oq = oq < 0 ? 0 : oq;
-		const uint2 out = pl[oq * 32];
+		const uint2 in = pl[(q & rmask) * 32];
+		const int oq = q - k;
+		const uint2 out = pl[(oq < 0 ? rmask + 1 : (oq & rmask)) * 32];
 		step<KM, U>(st, in.x, in.y, out.x, out.y);
 		const uint32_t m = sampled_mask<U, S>(st);
 		hw[U * 32] = q >= k - 1 ? m : 0u;
-		DevBlock<KM, S, U + 1>::run(st, pl, hw, qb, k);
+		DevBlock<KM, S, U + 1>::run(st, pl, hw, qb, k, rmask);
 	}
 };
 template <int KM, int S> struct DevBlock<KM, S, kBlock> {
-	static __device__ __forceinline__ void run(State&, const uint2* __restrict__, uint32_t* __restrict__, int, int) {}
+	static __device__ __forceinline__ void run(State&, const uint2* __restrict__, uint32_t* __restrict__, int, int, int) {}
 };
 
 // After kBlock steps logical ring bit r sits in physical F[r - kBlock] / R[r + kBlock]: move it home.
@@ -290,8 +329,9 @@ struct BodyDesc {
 	uint32_t rb, q0, nq, nwords; // nq == 0: no more work
 };
 
-constexpr int kThreads = 384; // warpgroup 0: 4 scan warps; warpgroups 1 and 2: their hit warps for even / odd bodies
-constexpr int kScanRegs = 248, kHitRegs = 128; // 128*248 + 256*128 = 64512 = the launch allocation (384*168); asking for all 65536 never completes
+constexpr int kHitWarps = 3;                        // hit warps per scan warp (hand-off unit i goes to hit warp i % 3)
+constexpr int kThreads = 128 * (1 + kHitWarps);     // warpgroup 0: 4 scan warps; warpgroups 1..3: their hit warps
+constexpr int kScanRegs = 240, kHitRegs = 88;       // 128*240 + 384*88 = 64512 of the 65536 registers (asking for all of them never completes)
 
 template <int KM, int S>
 __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec,
@@ -300,25 +340,29 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	const uint32_t role = warp >> 2;  // 0 scan, 1 hit (buffer 0), 2 hit (buffer 1)
+	const uint32_t role = warp >> 2;  // 0 scan, 1..kHitWarps hit
 	const uint32_t pair = warp & 3u;
-	const uint32_t npairs = L.pairs;
+	const uint32_t npairs = L.pairs, NB = L.nbuf;
+	const int rmask = (int)L.ring - 1;
 	uint4* tab = reinterpret_cast<uint4*>(smem_raw);
 	for (uint32_t i = threadIdx.x; i < 8 * 256; i += blockDim.x)
 		tab[i] = g_tab[i];
-	// per pair: [planes][masks x2][hit queue x2][desc x2][mbarriers x4]
-	const uint32_t plane_bytes = (1u + L.pos_cap) * 256u; // [slot 0 = zeros][position][lane] uint2
-	const uint32_t pair_bytes = plane_bytes + kNumBuf * kMaskBytes + 2 * kQueueCap * 4 + kPairMisc;
+	// per pair: [plane ring + zero slot][masks x NB][hit queue x2][desc x NB][full mbarriers x NB][empty mbarriers x NB]
+	const uint32_t plane_bytes = (L.ring + 1u) * 256u; // [position mod ring][lane] uint2; slot `ring` = zeros
+	const uint32_t pair_bytes = plane_bytes + NB * kMaskBytes + kHitWarps * kQueueCap * 4 + NB * 32;
 	unsigned char* pbase = smem_raw + kTabBytes + pair * pair_bytes;
 	uint2* planes = reinterpret_cast<uint2*>(pbase);
-	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(pbase + plane_bytes);          // [kNumBuf][16][32]
-	uint32_t* queues = hwbuf + kNumBuf * (kMaskBytes / 4);                        // [2][kQueueCap]
-	BodyDesc* desc = reinterpret_cast<BodyDesc*>(queues + 2 * kQueueCap);          // [kNumBuf]
-	uint64_t* bar_empty = reinterpret_cast<uint64_t*>(desc + kNumBuf);             // [kNumBuf]
+	uint32_t* hwbuf = reinterpret_cast<uint32_t*>(pbase + plane_bytes);          // [NB][16][32]
+	uint32_t* queues = hwbuf + NB * (kMaskBytes / 4);                             // [kHitWarps][kQueueCap]
+	BodyDesc* desc = reinterpret_cast<BodyDesc*>(queues + kHitWarps * kQueueCap);  // [NB]
+	uint64_t* bar_full = reinterpret_cast<uint64_t*>(desc + NB);                   // [NB]
+	uint64_t* bar_empty = bar_full + NB;                                           // [NB]
 	if (role == 0 && pair < npairs) {
-		planes[lane] = make_uint2(0u, 0u);
-		if (lane < kNumBuf)
+		planes[L.ring * 32 + lane] = make_uint2(0u, 0u);
+		if (lane < NB) {
+			mbar_init(&bar_full[lane], 1);
 			mbar_init(&bar_empty[lane], 1);
+		}
 	}
 	__syncthreads();
 
@@ -332,16 +376,17 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 	c.rot_b = L.rot_b;
 	c.ctr_k = ctr_k;
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.red_policy));
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(c.keep_policy));
 
 	if (role != 0) {
-		// ================= hit warps: consume the masks of every other body =================
+		// ================= hit warps: consume the masks of every other hand-off unit =================
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kHitRegs));
 		if (pair >= npairs)
 			return;
-		const uint32_t hw_id = role - 1; // hit warp A drains buffers 0,2; B drains 1,3
-		for (uint32_t u = 0;; u++) {
-			const uint32_t b = hw_id + 2u * (u & 1u);
-			named_bar_sync(pair * kNumBuf + b, 64); // unit ready (blocks in hardware, no polling)
+		const uint32_t hw_id = role - 1;
+		for (uint32_t it = hw_id;; it += kHitWarps) {
+			const uint32_t b = it % NB;
+			mbar_wait_sleep(&bar_full[b], (it / NB) & 1u);
 			const BodyDesc d = desc[b];
 			if (d.nq == 0)
 				break;
@@ -360,8 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		return;
 	const int k = (int)L.k;
 	unsigned long long f1_local = 0;
-	uint32_t uses[kNumBuf] = { 0, 0, 0, 0 }; // hand-offs done per buffer
-	uint32_t it = 0;
+	uint32_t it = 0; // hand-offs so far; unit `it` uses mask buffer it % NB and hit warp it & 1
 	const uint32_t n_tiles = (n_rec + kTileRecs - 1) / kTileRecs;
 	for (uint32_t tile = blockIdx.x * npairs + pair; tile < n_tiles; tile += gridDim.x * npairs) {
 		const uint32_t rb = tile * kTileRecs;
@@ -372,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		if (uniform) {
 #pragma unroll
 			for (int s = 0; s < 32; s++)
-				v[s] = __ldg(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride));
+				v[s] = ldg_keep_v4(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride), c.keep_policy);
 			len0 = __shfl_sync(0xFFFFFFFFu, v[0].x, 0);
 			bool same = true;
 #pragma unroll
@@ -380,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 				same = same && (v[s].x == len0);
 			uniform = __all_sync(0xFFFFFFFFu, same);
 		}
-		if (!uniform || len0 > L.pos_cap) {
+		if (!uniform) {
 			// general path, in place: each lane walks its own records with the 64-bit recurrence
 			const KTab& T = P->tab[L.ki];
 			uint32_t cnt = 0;
@@ -398,113 +442,95 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 		if (n < k)
 			continue;
 		const uint32_t nwords = (uint32_t)(n + 15) >> 4;
-		// ---- 1. transpose packed bases into bit planes ----
-		// (hit warps may still be hashing k-mers of the previous tile: they read global memory, not the planes)
-		{
-			const uint32_t ngroups = (nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
-#pragma unroll 1
-			for (uint32_t g = 0; g < ngroups; g++) {
-				if (g) {
-#pragma unroll
-					for (int s = 0; s < 32; s++)
-						v[s] = __ldg(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride) + g);
-				}
-#pragma unroll 1
-				for (int i = 0; i < 4; i++) {
-					const int w = (int)(g * 4) + i - 1; // base word index
-					if (w < 0 || w >= (int)nwords)
-						continue;
-					uint32_t A[32];
-					switch (i) {
-					case 0:
-#pragma unroll
-						for (int s = 0; s < 32; s++) A[s] = v[s].x;
-						break;
-					case 1:
-#pragma unroll
-						for (int s = 0; s < 32; s++) A[s] = v[s].y;
-						break;
-					case 2:
-#pragma unroll
-						for (int s = 0; s < 32; s++) A[s] = v[s].z;
-						break;
-					default:
-#pragma unroll
-						for (int s = 0; s < 32; s++) A[s] = v[s].w;
-						break;
-					}
-					transpose32(A);
-					uint2* dst = planes + (1 + 16 * w) * 32 + lane;
-					if (16 * w + 16 <= n) {
-#pragma unroll
-						for (int j = 0; j < 16; j++)
-							dst[j * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
-					} else {
-#pragma unroll
-						for (int j = 0; j < 16; j++)
-							if (16 * w + j < n)
-								dst[j * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
-					}
-				}
-			}
-		}
-		__syncwarp();
-		// ---- 2. scan; 3. hand each body's masks to a hit warp ----
+		const uint32_t ngroups = (nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
 		State st;
 #pragma unroll
 		for (int j = 0; j < 31; j++) {
 			st.F[j] = L.F0[j];
 			st.R[j] = L.R0[j];
 		}
-		for (int q0 = 0; q0 < n; q0 += kBodyPos) {
-			const int nq = min(kBodyPos, n - q0);
-			if (q0 <= n / 2 && n / 2 < q0 + kBodyPos) {
-				// half way through: warm L2 with this warp's next tile (bulk async prefetch). Earlier is too early -- at
-				// ~90 us per tile the lines would be evicted again by the sketch traffic before they are used.
+		// One column = one packed word of every record = 16 positions: transpose it into the plane ring, scan it,
+		// hand its masks over.  The next 16 bytes of every record are requested right after the last word of the
+		// current 16 bytes has been taken out of v[], so the loads fly during a whole column's scan.
+#pragma unroll 1
+		for (uint32_t w = 0; w < nwords; w++) {
+			const uint32_t g = (w + 1) >> 2, i = (w + 1) & 3u;
+			uint32_t A[32];
+			switch (i) {
+			case 0:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].x;
+				break;
+			case 1:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].y;
+				break;
+			case 2:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].z;
+				break;
+			default:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].w;
+				break;
+			}
+			if (i == 3 && g + 1 < ngroups) {
+#pragma unroll
+				for (int s = 0; s < 32; s++)
+					v[s] = ldg_keep_v4(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride) + (g + 1), c.keep_policy);
+			}
+			if (w == nwords / 2) {
+				// half way through: warm L2 with this warp's next tile (bulk async prefetch); earlier is too early, the
+				// lines would be evicted again by the sketch traffic before they are used
 				const uint64_t nrb = (uint64_t)(tile + gridDim.x * npairs) * kTileRecs;
 				if (lane == 0 && nrb + kTileRecs <= n_rec) {
 					const uint32_t bytes = kTileRecs * stride * 4u;
 					asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(words + nrb * stride), "r"(bytes) : "memory");
 				}
 			}
-			const bool has_windows = q0 + nq >= k; // some position of this body ends a full window
-			const uint32_t b = it & (kNumBuf - 1);
+			transpose32(A);
+			const int q0 = (int)(16u * w);
+			{
+				uint2* dst = planes + (q0 & rmask) * 32 + lane; // a column never wraps: the ring size is a multiple of 16
+#pragma unroll
+				for (int j = 0; j < 16; j++)
+					dst[j * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
+			}
+			__syncwarp();
+			const int nq = min(kBodyPos, n - q0);
+			const bool has_windows = q0 + nq >= k; // some position of this column ends a full window
+			const uint32_t b = it % NB;
 			uint32_t* hw = hwbuf + b * (kMaskBytes / 4);
-			const uint32_t ub = b == 0 ? uses[0] : b == 1 ? uses[1] : b == 2 ? uses[2] : uses[3];
-			if (ub) // the hit warp must have finished the previous use of this buffer (units without windows write it too)
-				mbar_wait(&bar_empty[b], (ub - 1) & 1u);
+			if (it >= NB) // the hit warp must have drained the previous use of this buffer (columns without windows write it too)
+				mbar_wait(&bar_empty[b], ((it / NB) - 1) & 1u);
 #pragma unroll 1
 			for (int qb = q0; qb < q0 + nq; qb += kBlock) {
-				DevBlock<KM, S, 0>::run(st, planes + lane, hw + (qb - q0) * 32 + lane, qb, k);
+				DevBlock<KM, S, 0>::run(st, planes + lane, hw + (qb - q0) * 32 + lane, qb, k, rmask);
 				rotate_home(st);
 			}
 			if (has_windows) {
 				__syncwarp();
-				if (lane == 0)
+				if (lane == 0) {
 					desc[b] = BodyDesc{ rb, (uint32_t)q0, (uint32_t)nq, nwords };
-				__syncwarp();
-				named_bar_arrive(pair * kNumBuf + b, 64);
-#pragma unroll
-				for (int i = 0; i < kNumBuf; i++)
-					uses[i] += (uint32_t)i == b;
+					mbar_arrive(&bar_full[b]);
+				}
 				it++;
 			}
 		}
 		if (lane == 0)
 			f1_local += (unsigned long long)kTileRecs * (unsigned long long)(n - k + 1);
 	}
-	// tell both hit warps to stop: the next two units (one per hit warp) carry nq = 0
+	// tell the hit warps to stop: the next kHitWarps units (one per hit warp) carry nq = 0
 #pragma unroll 1
-	for (uint32_t e = 0; e < 2; e++, it++) {
-		const uint32_t b = it & (kNumBuf - 1);
-		const uint32_t ub = b == 0 ? uses[0] : b == 1 ? uses[1] : b == 2 ? uses[2] : uses[3];
-		if (ub)
-			mbar_wait(&bar_empty[b], (ub - 1) & 1u);
+	for (uint32_t e = 0; e < kHitWarps; e++, it++) {
+		const uint32_t b = it % NB;
+		if (it >= NB)
+			mbar_wait(&bar_empty[b], ((it / NB) - 1) & 1u);
 		__syncwarp();
-		if (lane == 0)
+		if (lane == 0) {
 			desc[b] = BodyDesc{ 0, 0, 0, 0 };
-		__syncwarp();
-		named_bar_arrive(pair * kNumBuf + b, 64);
+			mbar_arrive(&bar_full[b]);
+		}
 	}
 	// totKmer (ntcard.cpp:155): warp-reduce then one atomic per warp
 #pragma unroll

@@ -8,7 +8,9 @@ struct DevParams;
 namespace bs {
 
 struct BsLaunch {          // per-k launch constants, passed by value
-	uint32_t k, ki, rBits, pos_cap; // pos_cap: positions the shared-memory planes of one scan warp can hold
+	uint32_t k, ki, rBits;
+	uint32_t ring;                  // positions in a scan warp's shared-memory plane ring (power of two >= k + 16)
+	uint32_t nbuf;                  // mask buffers (hand-off units in flight) per scan warp
 	uint32_t pairs;                 // active scan warps per CTA (each with two hit warps)
 	uint32_t F0[31], R0[31];        // initial bit-sliced state (bitslice_core.cuh init_state)
 	uint64_t rot_a, rot_b;          // byte m: (k%32 + 32m) % 31 and % 33 for block m of the hit path (k < 288)
@@ -29,8 +31,7 @@ struct BsArgs {
 
 constexpr size_t kTabBytes = 8 * 256 * 16;
 constexpr size_t kMaskBytes = 16 * 128;               // one hand-off unit's masks: [16 positions][32 lanes] words
-constexpr size_t kPairMisc = 128;                     // 4 unit descriptors + 4 mbarriers
-constexpr size_t kNumMaskBuf = 4;
+constexpr int kHitWarpsPerScan = 3;                   // must equal bs::kHitWarps in bitslice_kernel.cuh
 constexpr int kQueueCap = 288;                        // hit queue entries per hit warp: one HALF body (16 positions), expected 256 at s=7
 constexpr size_t kSmemMax = 232448;                   // 227 KB opt-in limit per CTA on sm_100
 

@@ -145,9 +145,32 @@ void build_params(const ntc_ctx* c, ntc::DevParams* P)
 
 // Which k indices the bit-sliced kernel can take for this batch; plane capacity / warps per CTA in *cfg.
 struct BsConfig {
-	uint32_t kmask = 0, pairs = 0, pos_cap = 0;
-	size_t smem = 0;
+	uint32_t kmask = 0;
+	uint32_t pairs[NTC_MAX_K] = {}, ring[NTC_MAX_K] = {}, nbuf[NTC_MAX_K] = {};
+	size_t smem[NTC_MAX_K] = {};
 };
+
+// Shared memory of one CTA of the bit-sliced kernel for a given k: the byte tables plus, per scan warp, a plane ring of
+// `ring` positions (power of two >= k + 16, + 1 zero slot), nbuf mask buffers, two hit queues, descriptors + mbarriers.
+bool bitslice_shape(unsigned k, uint32_t* pairs, uint32_t* ring, uint32_t* nbuf, size_t* smem)
+{
+	uint32_t r = 64;
+	while (r < k + 16)
+		r <<= 1;
+	for (uint32_t p = 4; p >= 1; p--)
+		for (uint32_t nb = 8; nb >= 4; nb -= 4) {
+			const size_t per_pair = (size_t)(r + 1) * 256 + nb * ntc::bs::kMaskBytes + ntc::bs::kHitWarpsPerScan * ntc::bs::kQueueCap * 4 + nb * 32;
+			const size_t total = ntc::bs::kTabBytes + p * per_pair;
+			if (total <= ntc::bs::kSmemMax) {
+				*pairs = p;
+				*ring = r;
+				*nbuf = nb;
+				*smem = total;
+				return true;
+			}
+		}
+	return false;
+}
 
 BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 {
@@ -156,27 +179,9 @@ BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 	    b.n_rec < 1024 || (reinterpret_cast<uintptr_t>(b.words) & 15u))
 		return cfg;
 	for (unsigned ki = 0; ki < c->nK; ki++)
-		if (c->k[ki] < 288 && ntc::bs::have_kernel(c->k[ki], c->sBits))
+		if (c->k[ki] < 288 && ntc::bs::have_kernel(c->k[ki], c->sBits) &&
+		    bitslice_shape(c->k[ki], &cfg.pairs[ki], &cfg.ring[ki], &cfg.nbuf[ki], &cfg.smem[ki]))
 			cfg.kmask |= 1u << ki;
-	if (!cfg.kmask)
-		return cfg;
-	// One CTA per SM: the byte tables plus, per scan warp, bit planes for pos_cap positions and two
-	// mask/queue buffers (one per hit warp).  4 scan warps when the records are short-read sized.
-	const uint32_t need = 16u * (b.stride - 1);
-	for (uint32_t pairs = 4; pairs >= 1; pairs--) {
-		const size_t per_pair = ((ntc::bs::kSmemMax - ntc::bs::kTabBytes) / pairs) & ~(size_t)255;
-		const size_t fixed = ntc::bs::kNumMaskBuf * ntc::bs::kMaskBytes + 2 * ntc::bs::kQueueCap * 4 + ntc::bs::kPairMisc;
-		const uint32_t cap = (uint32_t)((per_pair - fixed) / 256) - 1;
-		// stride 12 (<= 176 bases) is the 150/151 bp short-read layout: keep 4 scan warps; longer records of
-		// such a batch take the in-kernel general path
-		if (cap >= need || (pairs == 4 && need <= 176 && cap >= 152)) {
-			cfg.pairs = pairs;
-			cfg.pos_cap = cap < need ? cap : need;
-			cfg.smem = ntc::bs::kTabBytes + pairs * ((size_t)(1 + cfg.pos_cap) * 256 + fixed);
-			return cfg;
-		}
-	}
-	cfg.kmask = 0; // records too long for the shared-memory planes
 	return cfg;
 }
 
@@ -203,16 +208,17 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		a.stride = b.stride;
 		a.n_rec = b.n_rec;
 		a.L = c->bs_launch[ki];
-		a.L.pos_cap = bs.pos_cap;
-		a.L.pairs = bs.pairs;
+		a.L.ring = bs.ring[ki];
+		a.L.nbuf = bs.nbuf[ki];
+		a.L.pairs = bs.pairs[ki];
 		a.d_tab = c->d_bs_tab;
 		a.d_params = c->d_params;
 		a.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 		a.f1_k = c->d_f1 + ki;
-		a.pairs = bs.pairs;
+		a.pairs = bs.pairs[ki];
 		const unsigned n_tiles = (b.n_rec + 1023) / 1024;
-		a.grid = std::min<unsigned>((unsigned)c->n_sm, (n_tiles + bs.pairs - 1) / bs.pairs);
-		a.smem_bytes = bs.smem;
+		a.grid = std::min<unsigned>((unsigned)c->n_sm, (n_tiles + bs.pairs[ki] - 1) / bs.pairs[ki]);
+		a.smem_bytes = bs.smem[ki];
 		a.stream = c->stream;
 		CK(ntc::bs::launch(c->k[ki], c->sBits, a));
 		c->n_launches += 1;
@@ -358,7 +364,7 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 			L.k = c->k[ki];
 			L.ki = ki;
 			L.rBits = rBits;
-			L.pos_cap = 0;
+			L.ring = L.nbuf = L.pairs = 0;
 			ntc::bs::init_state(c->k[ki], L.F0, L.R0);
 			L.rot_a = L.rot_b = 0;
 			for (unsigned m = 0; m < 8; m++) {
