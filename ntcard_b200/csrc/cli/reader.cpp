@@ -113,14 +113,26 @@ bool LineReader::next(const char** line, size_t* len)
 BatchSubmitter::BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer)
     : ctx_(ctx), min_len_(min_len), mu_(submit_mu)
 {
-	for (auto& b : buf_)
-		alloc(b, words_per_buffer, words_per_buffer / 4);
+	for (auto& b : uni_.buf)
+		alloc(b, words_per_buffer, 1);
+	for (auto& b : rag_.buf)
+		alloc(b, words_per_buffer / 4, words_per_buffer / 16);
+	tmp_words_.resize(1 << 16);
+	tmp_off_.resize((1 << 14) + 1);
 }
 
 BatchSubmitter::~BatchSubmitter()
 {
-	for (auto& b : buf_)
+	for (auto& b : uni_.buf)
 		release(b);
+	for (auto& b : rag_.buf)
+		release(b);
+}
+
+static void die_ntc()
+{
+	std::cerr << "ntCard: " << ntc_last_error() << "\n";
+	exit(EXIT_FAILURE);
 }
 
 void BatchSubmitter::alloc(Buf& b, size_t words, size_t recs)
@@ -144,69 +156,100 @@ void BatchSubmitter::release(Buf& b)
 	b.words = b.off = nullptr;
 }
 
-void BatchSubmitter::add(const char* seq, size_t len)
+void BatchSubmitter::flush_stream(Stream& st)
 {
-	if (len < min_len_)
-		return; // no window fits (ntHashIterator.hpp:61-64)
-	for (int attempt = 0; attempt < 3; attempt++) {
-		Buf& b = buf_[cur_];
-		const uint64_t so[2] = { 0, (uint64_t)len };
-		size_t consumed = 0;
-		int rc = ntc_pack_seqs(seq, so, 1, min_len_, b.words, b.cap_words, &b.n_words, b.off, b.cap_rec, &b.n_rec, &consumed);
-		if (rc == NTC_OK)
-			return;
-		if (rc != NTC_ENOMEM) {
-			std::cerr << "ntCard: " << ntc_last_error() << "\n";
-			exit(EXIT_FAILURE);
-		}
-		if (b.n_rec > 0) {
-			flush(); // full: submit and continue in the other buffer
-			continue;
-		}
-		// a single sequence larger than an empty buffer (e.g. a chromosome): grow this buffer
-		size_t need_w = ntc_pack_bound(1, len), need_r = len / (min_len_ ? min_len_ : 1) + 2;
-		if (b.ticket && ntc_wait(ctx_, b.ticket)) {
-			std::cerr << "ntCard: " << ntc_last_error() << "\n";
-			exit(EXIT_FAILURE);
-		}
-		release(b);
-		alloc(b, need_w > b.cap_words ? need_w : b.cap_words, need_r > b.cap_rec ? need_r : b.cap_rec);
-	}
-	std::cerr << "ntCard: internal error: sequence does not fit the batch buffer\n";
-	exit(EXIT_FAILURE);
-}
-
-void BatchSubmitter::flush()
-{
-	Buf& b = buf_[cur_];
+	Buf& b = st.buf[st.cur];
 	if (b.n_rec > 0) {
 		std::lock_guard<std::mutex> lk(*mu_);
-		if (ntc_submit(ctx_, b.words, b.n_words, b.off, b.n_rec, 0, &b.ticket)) {
-			std::cerr << "ntCard: submit failed: " << ntc_last_error() << "\n";
-			exit(EXIT_FAILURE);
-		}
+		const int rc = st.stride ? ntc_submit(ctx_, b.words, b.n_words, NULL, b.n_rec, st.stride, &b.ticket)
+		                         : ntc_submit(ctx_, b.words, b.n_words, b.off, b.n_rec, 0, &b.ticket);
+		if (rc)
+			die_ntc();
 	}
-	cur_ ^= 1;
-	Buf& n = buf_[cur_];
+	st.cur ^= 1;
+	Buf& n = st.buf[st.cur];
 	if (n.ticket) { // the DMA engine may still be reading the buffer we are about to refill
 		std::lock_guard<std::mutex> lk(*mu_);
-		if (ntc_wait(ctx_, n.ticket)) {
-			std::cerr << "ntCard: " << ntc_last_error() << "\n";
-			exit(EXIT_FAILURE);
-		}
+		if (ntc_wait(ctx_, n.ticket))
+			die_ntc();
 		n.ticket = 0;
 	}
 	n.n_words = n.n_rec = 0;
 }
 
+void BatchSubmitter::append(Stream& st, const uint32_t* rec, size_t nwords)
+{
+	const size_t need = st.stride ? st.stride : nwords;
+	for (int attempt = 0; attempt < 2; attempt++) {
+		Buf& b = st.buf[st.cur];
+		if (b.n_words + need <= b.cap_words && (st.stride || b.n_rec + 1 <= b.cap_rec)) {
+			memcpy(b.words + b.n_words, rec, nwords * sizeof(uint32_t));
+			if (need > nwords)
+				memset(b.words + b.n_words + nwords, 0, (need - nwords) * sizeof(uint32_t));
+			if (!st.stride) {
+				b.off[b.n_rec] = (uint32_t)b.n_words;
+				b.off[b.n_rec + 1] = (uint32_t)(b.n_words + need);
+			}
+			b.n_words += need;
+			b.n_rec++;
+			return;
+		}
+		if (b.n_rec > 0) {
+			flush_stream(st);
+			continue;
+		}
+		// a single record larger than an empty buffer (e.g. a chromosome): grow this buffer
+		if (b.ticket && ntc_wait(ctx_, b.ticket))
+			die_ntc();
+		release(b);
+		alloc(b, need + (need >> 2), b.cap_rec);
+	}
+	std::cerr << "ntCard: internal error: record does not fit the batch buffer\n";
+	exit(EXIT_FAILURE);
+}
+
+void BatchSubmitter::add(const char* seq, size_t len)
+{
+	if (len < min_len_)
+		return; // no window fits (ntHashIterator.hpp:61-64)
+	const size_t bound = ntc_pack_bound(1, len);
+	if (tmp_words_.size() < bound)
+		tmp_words_.resize(bound);
+	const size_t rec_bound = len / (min_len_ ? min_len_ : 1) + 2;
+	if (tmp_off_.size() < rec_bound + 1)
+		tmp_off_.resize(rec_bound + 1);
+	const uint64_t so[2] = { 0, (uint64_t)len };
+	size_t nw = 0, nr = 0, consumed = 0;
+	if (ntc_pack_seqs(seq, so, 1, min_len_, tmp_words_.data(), tmp_words_.size(), &nw, tmp_off_.data(), tmp_off_.size() - 1, &nr, &consumed))
+		die_ntc();
+	for (size_t i = 0; i < nr; i++) {
+		const uint32_t* rec = tmp_words_.data() + tmp_off_[i];
+		const size_t nwords = tmp_off_[i + 1] - tmp_off_[i];
+		const uint32_t padded = (uint32_t)((nwords + 3) & ~(size_t)3);
+		if (uni_.stride == 0 && padded <= 64)
+			uni_.stride = padded; // the first record fixes the common size (reads of one run share a length)
+		if (padded == uni_.stride)
+			append(uni_, rec, nwords);
+		else
+			append(rag_, rec, nwords);
+	}
+}
+
+void BatchSubmitter::flush()
+{
+	flush_stream(uni_);
+	flush_stream(rag_);
+}
+
 void BatchSubmitter::finish()
 {
 	std::lock_guard<std::mutex> lk(*mu_);
-	for (auto& b : buf_)
-		if (b.ticket) {
-			ntc_wait(ctx_, b.ticket);
-			b.ticket = 0;
-		}
+	for (Stream* st : { &uni_, &rag_ })
+		for (auto& b : st->buf)
+			if (b.ticket) {
+				ntc_wait(ctx_, b.ticket);
+				b.ticket = 0;
+			}
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "ntcard_b200.h"
 
@@ -31,13 +32,16 @@ private:
 	bool eof_ = false;
 };
 
-// Packs sequences into two pinned buffers alternately and submits full ones (asynchronously).
+// Packs sequences into pinned buffers and submits full ones (asynchronously).  Records are routed into two
+// streams, each double buffered: records whose padded size equals that of the first record seen (the common
+// read length, e.g. 150 bp -> 12 words) go into a UNIFORM-STRIDE batch, which the device runs through the
+// bit-sliced kernel; everything else (segments cut short by an N, odd lengths) goes into a ragged batch.
 class BatchSubmitter {
 public:
 	BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer = (size_t)8 << 20);
 	~BatchSubmitter();
 	void add(const char* seq, size_t len); // == one ntRead(seq, ...) call of the reference
-	void flush();                           // submit what is buffered
+	void flush();                           // submit what is buffered (both streams)
 	void finish();                          // wait until the device no longer needs our buffers
 
 private:
@@ -48,13 +52,20 @@ private:
 		size_t n_words = 0, n_rec = 0;
 		uint64_t ticket = 0;
 	};
+	struct Stream {
+		Buf buf[2];
+		int cur = 0;
+		uint32_t stride = 0; // > 0: uniform-stride stream
+	};
 	void alloc(Buf& b, size_t words, size_t recs);
 	void release(Buf& b);
+	void flush_stream(Stream& st);
+	void append(Stream& st, const uint32_t* rec, size_t nwords);
 	ntc_ctx* ctx_;
 	unsigned min_len_;
 	std::mutex* mu_;
-	Buf buf_[2];
-	int cur_ = 0;
+	Stream uni_, rag_;
+	std::vector<uint32_t> tmp_words_, tmp_off_;
 };
 
 // Sniff the format on the first line and feed every sequence of the file to `sub`.
