@@ -42,6 +42,7 @@ struct WarpCtx {
 	uint32_t* __restrict__ ctr_k;
 	uint64_t red_policy;   // L2 evict_first cache policy for the sketch increments
 	uint64_t keep_policy;  // L2 evict_last cache policy for the packed reads
+	uint32_t nored;
 };
 
 // ---- mbarrier helpers (shared::cta) -----------------------------------------------------------------
@@ -212,7 +213,7 @@ template <int S> __device__ __forceinline__ void hit_finish(const WarpCtx& c, co
 	// ntComp: both tests look at the top S+1 <= 32 bits; the bucket at the low rBits <= 30 bits
 	const bool t0 = (hh >> (31 - S)) == 1u;
 	const bool t1 = (hh >> (32 - S)) == ((1u << (S - 1)) - 1u);
-	if (t0 || t1) {
+	if ((t0 || t1) && !c.nored) {
 		const uint32_t idx = ((t1 ? 1u : 0u) << c.rBits) | (hl & ((1u << c.rBits) - 1u));
 		// fire-and-forget increment; the sketch sector is streaming data (one touch), so let it leave L2 first and
 		// keep the packed reads of the tiles in flight resident (the hit path re-reads them)
@@ -296,7 +297,7 @@ template <int KM, int S, int U> struct DevBlock {
 	// masks are never consumed: the hand-off carries the number of valid positions).
 	// Planes live in a ring of rmask+1 positions (slot = position mod ring size); slot rmask+1 is all zero and
 	// stands for the virtual bases before the read (window not full yet).
-	static __device__ __forceinline__ void run(State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ hw, int qb, int k, int rmask)
+	static __device__ __forceinline__ void run(State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ hw, int qb, int k, int rmask, uint32_t vmask)
 	{
 		const int q = qb + U;
 		const uint2 in = pl[(q & rmask) * 32];
@@ -304,12 +305,12 @@ template <int KM, int S, int U> struct DevBlock {
 		const uint2 out = pl[(oq < 0 ? rmask + 1 : (oq & rmask)) * 32];
 		step<KM, U>(st, in.x, in.y, out.x, out.y);
 		const uint32_t m = sampled_mask<U, S>(st);
-		hw[U * 32] = q >= k - 1 ? m : 0u;
-		DevBlock<KM, S, U + 1>::run(st, pl, hw, qb, k, rmask);
+		hw[U * 32] = q >= k - 1 ? (m & vmask) : 0u;
+		DevBlock<KM, S, U + 1>::run(st, pl, hw, qb, k, rmask, vmask);
 	}
 };
 template <int KM, int S> struct DevBlock<KM, S, kBlock> {
-	static __device__ __forceinline__ void run(State&, const uint2* __restrict__, uint32_t* __restrict__, int, int, int) {}
+	static __device__ __forceinline__ void run(State&, const uint2* __restrict__, uint32_t* __restrict__, int, int, int, uint32_t) {}
 };
 
 // After kBlock steps logical ring bit r sits in physical F[r - kBlock] / R[r + kBlock]: move it home.
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 	c.rot_a = L.rot_a;
 	c.rot_b = L.rot_b;
 	c.ctr_k = ctr_k;
+	c.nored = L.dbg & 2u;
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(c.red_policy));
 	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(c.keep_policy));
 
@@ -392,7 +394,8 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 				break;
 			c.rb = d.rb;
 			c.nwords = d.nwords;
-			drain_body<S>(c, hwbuf + b * (kMaskBytes / 4), queues + hw_id * kQueueCap, d.nq, d.q0, lane);
+			if (!(L.dbg & 1u))
+				drain_body<S>(c, hwbuf + b * (kMaskBytes / 4), queues + hw_id * kQueueCap, d.nq, d.q0, lane);
 			if (lane == 0)
 				mbar_arrive(&bar_empty[b]);
 		}
@@ -410,13 +413,19 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 	for (uint32_t tile = blockIdx.x * npairs + pair; tile < n_tiles; tile += gridDim.x * npairs) {
 		const uint32_t rb = tile * kTileRecs;
 		// ---- first 16 bytes of every record (length + 3 base words); is the tile uniform? ----
-		bool uniform = rb + kTileRecs <= n_rec;
+		// The last tile may be partial: slots past the end re-read the batch's last record (so every load is in
+		// bounds and the uniformity test is unaffected) and are masked out of every hand-off (vmask).
+		const uint32_t nvalid = min(kTileRecs, n_rec - rb), last_rec = n_rec - 1u;
+		uint32_t vmask = 0;
+		bool uniform;
 		uint4 v[32];
 		uint32_t len0 = 0;
-		if (uniform) {
+		{
 #pragma unroll
-			for (int s = 0; s < 32; s++)
-				v[s] = ldg_keep_v4(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride), c.keep_policy);
+			for (int s = 0; s < 32; s++) {
+				v[s] = ldg_keep_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride), c.keep_policy);
+				vmask |= (s * 32u + lane < nvalid ? 1u : 0u) << s;
+			}
 			len0 = __shfl_sync(0xFFFFFFFFu, v[0].x, 0);
 			bool same = true;
 #pragma unroll
@@ -477,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 			if (i == 3 && g + 1 < ngroups) {
 #pragma unroll
 				for (int s = 0; s < 32; s++)
-					v[s] = ldg_keep_v4(reinterpret_cast<const uint4*>(words + (uint64_t)(rb + s * 32u + lane) * stride) + (g + 1), c.keep_policy);
+					v[s] = ldg_keep_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride) + (g + 1), c.keep_policy);
 			}
 			if (w == nwords / 2) {
 				// half way through: warm L2 with this warp's next tile (bulk async prefetch); earlier is too early, the
@@ -505,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 				mbar_wait(&bar_empty[b], ((it / NB) - 1) & 1u);
 #pragma unroll 1
 			for (int qb = q0; qb < q0 + nq; qb += kBlock) {
-				DevBlock<KM, S, 0>::run(st, planes + lane, hw + (qb - q0) * 32 + lane, qb, k, rmask);
+				DevBlock<KM, S, 0>::run(st, planes + lane, hw + (qb - q0) * 32 + lane, qb, k, rmask, vmask);
 				rotate_home(st);
 			}
 			if (has_windows) {
@@ -518,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) bitslice_kernel(const uint32_t* _
 			}
 		}
 		if (lane == 0)
-			f1_local += (unsigned long long)kTileRecs * (unsigned long long)(n - k + 1);
+			f1_local += (unsigned long long)nvalid * (unsigned long long)(n - k + 1);
 	}
 	// tell the hit warps to stop: the next kHitWarps units (one per hit warp) carry nq = 0
 #pragma unroll 1

@@ -12,6 +12,7 @@ struct BsLaunch {          // per-k launch constants, passed by value
 	uint32_t ring;                  // positions in a scan warp's shared-memory plane ring (power of two >= k + 16)
 	uint32_t nbuf;                  // mask buffers (hand-off units in flight) per scan warp
 	uint32_t pairs;                 // active scan warps per CTA (each with two hit warps)
+	uint32_t dbg;                   // experiments: bit0 = hit warps skip all work, bit1 = no RED
 	uint32_t F0[31], R0[31];        // initial bit-sliced state (bitslice_core.cuh init_state)
 	uint64_t rot_a, rot_b;          // byte m: (k%32 + 32m) % 31 and % 33 for block m of the hit path (k < 288)
 };

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/ntcard_b200.h"
@@ -365,6 +366,7 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 			L.ki = ki;
 			L.rBits = rBits;
 			L.ring = L.nbuf = L.pairs = 0;
+			L.dbg = getenv("NTC_BS_DEBUG") ? (uint32_t)atoi(getenv("NTC_BS_DEBUG")) : 0u;
 			ntc::bs::init_state(c->k[ki], L.F0, L.R0);
 			L.rot_a = L.rot_b = 0;
 			for (unsigned m = 0; m < 8; m++) {
