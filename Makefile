@@ -11,7 +11,7 @@ BUILD = build
 # k mod 31 variants of the bit-sliced kernel to compile (each is one translation unit)
 BS_KMS ?= 0 1 2 3 4 12
 BS_KM_LIST = $(foreach n,$(BS_KMS),X($(n)))
-CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(SRC)/bitslice_dispatch.cu
+CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(SRC)/hit_kernels.cu $(SRC)/bitslice_dispatch.cu
 BS_OBJS = $(foreach n,$(BS_KMS),$(BUILD)/bitslice_km$(n).o)
 CPP_SRCS = $(SRC)/host_util.cpp
 CU_OBJS = $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS))

@@ -67,15 +67,17 @@ typedef struct ntc_ctx ntc_ctx;
  * sketch of NTC_NSAMP x 2^rBits counters per k, sampling on sBits leading bits
  * (opt::rBits / opt::sBits, ntcard.cpp:57-58; the caller applies the "sBits = 7
  * below 50 GB" rule of ntcard.cpp:430-431).  Replaces ntcard.cpp:437-439.
- * d_counters: optional caller-owned DEVICE buffer of nK*2*2^rBits uint32 (zeroed
- * by this call), e.g. a torch tensor that torch.distributed will all-reduce;
+ * d_counters: optional caller-owned DEVICE buffer of nK*2*2^rBits uint32 (its content
+ * is defined -- zeroed, then incremented -- from the first flush on; read it only after
+ * ntc_counters_device / ntc_sync), e.g. a torch tensor that torch.distributed will all-reduce;
  * NULL lets the context allocate it.  cuda_stream: optional cudaStream_t on
  * which all device work is ordered (NULL = the context creates its own). */
 int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits, unsigned sBits, int device,
     void* d_counters, void* cuda_stream);
 void ntc_destroy(ntc_ctx* ctx);
 
-/* Zero the sketch and the k-mer totals (a fresh `new uint16_t[...]()`). */
+/* Zero the sketch and the k-mer totals (a fresh `new uint16_t[...]()`); the zeros are written
+ * lazily, by the first flush. */
 int ntc_reset(ntc_ctx* ctx);
 int ntc_set_kernel(ntc_ctx* ctx, int kernel);
 
@@ -92,7 +94,13 @@ int ntc_submit(ntc_ctx* ctx, const uint32_t* words, size_t n_words, const uint32
 int ntc_submit_device(ntc_ctx* ctx, const uint32_t* d_words, size_t n_words, const uint32_t* d_off, size_t n_rec,
     uint32_t stride_words);
 int ntc_wait(ntc_ctx* ctx, uint64_t ticket); /* host buffer of that batch is reusable */
-int ntc_sync(ntc_ctx* ctx);                  /* all submitted work has finished */
+int ntc_sync(ntc_ctx* ctx);                  /* all submitted work has finished (implies ntc_flush) */
+/* The device path is a pipeline: batches are scanned and their sketch increments (ntComp's
+ * ++t_Counter[...], ntcard.cpp:141-143) are first appended to a binned log in HBM; a flush applies the log
+ * to the counters slice by slice while each slice is L2 resident.  The library flushes by itself when the
+ * log fills up and inside every call that reads the counters (ntc_sync, ntc_finish, ntc_counters_device,
+ * ntc_hist_range); ntc_flush forces one (asynchronous, ordered on the context's stream). */
+int ntc_flush(ntc_ctx* ctx);
 
 /* Multi-GPU plumbing: the device counters (uint32, [nK][2][2^rBits]; summed
  * across ranks by the caller's collective, then narrowed mod 2^16 by

@@ -19,7 +19,7 @@ KERNEL_AUTO, KERNEL_ROLL64, KERNEL_BITSLICE = 0, 1, 2
 # every symbol include/ntcard_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_submit", "ntc_submit_device", "ntc_wait",
-    "ntc_sync", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_set_totals", "ntc_finish", "ntc_estimate",
+    "ntc_sync", "ntc_flush", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_set_totals", "ntc_finish", "ntc_estimate",
     "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
     "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_device_count",
     "ntc_last_error", "ntc_version",
@@ -48,6 +48,7 @@ def _load():
         "ntc_submit_device": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]),
         "ntc_wait": (C.c_int, [vp, C.c_uint64]),
         "ntc_sync": (C.c_int, [vp]),
+        "ntc_flush": (C.c_int, [vp]),
         "ntc_counters_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "ntc_totals": (C.c_int, [vp, u64p]),
         "ntc_set_totals": (C.c_int, [vp, u64p]),
@@ -242,6 +243,10 @@ class Sketch:
 
     def sync(self):
         _check(lib.ntc_sync(self.h))
+
+    def flush(self):
+        """Apply the pending sketch increments to the counters in HBM (asynchronous, stream ordered)."""
+        _check(lib.ntc_flush(self.h))
 
     def counters_device(self):
         p, n = C.c_void_p(), C.c_size_t()

@@ -2,6 +2,7 @@
 // BS_KM_LIST is the list of compiled variants, e.g. -DBS_KM_LIST="X(0) X(1) X(2)".
 #include "bitslice_launch.h"
 #include "nthash_device.cuh"
+#include "pipeline.h"
 
 #ifndef BS_KM_LIST
 #define BS_KM_LIST
@@ -55,4 +56,24 @@ void build_tables(uint32_t* tab)
 }
 
 } // namespace bs
+
+namespace pl {
+
+#define X(n) cudaError_t launch_scan_km_##n(unsigned sBits, const ScanArgs& a);
+BS_KM_LIST
+#undef X
+
+bool have_scan_kernel(unsigned k, unsigned sBits) { return bs::have_kernel(k, sBits); }
+
+cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a)
+{
+	switch (k % 31) {
+#define X(n) case n: return launch_scan_km_##n(sBits, a);
+		BS_KM_LIST
+#undef X
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+} // namespace pl
 } // namespace ntc

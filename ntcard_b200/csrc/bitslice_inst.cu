@@ -2,6 +2,7 @@
 // unrolled variants build in parallel.  Each instantiates the kernel for sBits = 7 and 11, the two
 // values the reference can reach without its hidden -s flag (ntcard.cpp:58, 430-431).
 #include "bitslice_kernel.cuh"
+#include "scan_kernel.cuh"
 
 #ifndef BS_KM
 #error "compile with -DBS_KM=<k mod 31>"
@@ -23,4 +24,17 @@ cudaError_t BS_CAT(launch_km_, BS_KM)(unsigned sBits, const BsArgs& a)
 }
 
 } // namespace bs
+
+namespace pl {
+
+cudaError_t BS_CAT(launch_scan_km_, BS_KM)(unsigned sBits, const ScanArgs& a)
+{
+	if (sBits == 7)
+		return launch_scan_one<BS_KM, 7>(a);
+	if (sBits == 11)
+		return launch_scan_one<BS_KM, 11>(a);
+	return cudaErrorInvalidValue;
+}
+
+} // namespace pl
 } // namespace ntc

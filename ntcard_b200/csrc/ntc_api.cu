@@ -15,6 +15,7 @@
 #include "bitslice_launch.h"
 #include "internal.h"
 #include "launch.h"
+#include "pipeline.h"
 #include "sketch_common.cuh"
 
 namespace {
@@ -73,6 +74,18 @@ struct ntc_ctx {
 	size_t cap_piece_rec = 0;
 	void* d_scan_tmp = nullptr;
 	size_t cap_scan_tmp = 0;
+	// sketch pipeline (scan -> hit log -> apply), pipeline.h
+	ntc::pl::Pool pool{};
+	uint32_t* d_pool_ctl_region = nullptr; // ctl + slice_nblk + zero_done + apply_done + cand, one allocation (zeroed by reset)
+	size_t pool_ctl_bytes = 0;
+	uint32_t* d_masks = nullptr;
+	size_t cap_masks = 0;
+	uint32_t* d_tile_info = nullptr;
+	size_t cap_tile_info = 0;
+	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
+	bool use_pipeline = true;
+	unsigned apply_grid = 0, hit_grid_max = 0;
+	uint64_t n_flush_launches = 0;
 	// finish buffers
 	uint16_t* d_narrow = nullptr;
 	uint32_t* d_phist = nullptr;
@@ -186,6 +199,158 @@ BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 	return cfg;
 }
 
+
+// ---- sketch pipeline -------------------------------------------------------------------------------------
+int pool_create(ntc_ctx* c)
+{
+	ntc::pl::Pool& P = c->pool;
+	const char* env = getenv("NTC_POOL_BLOCKS");
+	P.n_blocks = env ? (uint32_t)strtoul(env, nullptr, 10) : (256u << 10); // x 256 entries x 4 B = 256 MiB
+	P.n_blocks = std::min(std::max(P.n_blocks, 64u), (1u << 23) - 1u); // a block id has 23 bits in the slice lists
+	P.rBits = c->rBits;
+	P.nK = c->nK;
+	const uint32_t idx_bits = c->rBits + 1;
+	P.bin_shift = idx_bits <= 22 ? idx_bits : std::max(22u, idx_bits - 6u); // slices of 16 MiB (r <= 27), <= 64 per k
+	P.nbins = 1u << (idx_bits - P.bin_shift);
+	P.n_slices = c->nK * P.nbins;
+	P.slice_cap = std::max(16u, P.n_blocks / 4);
+	CK(cudaMalloc((void**)&P.entries, (size_t)P.n_blocks * ntc::pl::kBlkEntries * sizeof(uint32_t)));
+	CK(cudaMalloc((void**)&P.slice_blocks, (size_t)P.n_slices * P.slice_cap * sizeof(uint32_t)));
+	// control region: [ctl CTL_WORDS][slice_nblk n_slices][zero_done n_slices][apply_done n_slices][pad][cand 2 words]
+	const size_t words = ntc::pl::CTL_WORDS + 3 * (size_t)P.n_slices + 4;
+	c->pool_ctl_bytes = words * sizeof(uint32_t);
+	CK(cudaMalloc((void**)&c->d_pool_ctl_region, c->pool_ctl_bytes));
+	P.ctl = c->d_pool_ctl_region;
+	P.slice_nblk = P.ctl + ntc::pl::CTL_WORDS;
+	P.zero_done = P.slice_nblk + P.n_slices;
+	P.apply_done = P.zero_done + P.n_slices;
+	P.cand = reinterpret_cast<unsigned long long*>(P.apply_done + P.n_slices + ((ntc::pl::CTL_WORDS + 3 * P.n_slices) & 1u));
+	c->apply_grid = (unsigned)ntc::pl::apply_max_grid(c->n_sm);
+	c->hit_grid_max = (unsigned)c->n_sm * 2u;
+	return NTC_OK;
+}
+
+// Apply everything that is pending to the counters in HBM (and materialise them after a reset).
+int flush(ntc_ctx* c)
+{
+	if (!c->pending)
+		return NTC_OK;
+	cudaEvent_t e0, e1;
+	int rc;
+	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
+		return rc;
+	CK(cudaEventRecord(e0, c->stream));
+	CK(ntc::pl::launch_apply(c->pool, c->d_counters, 1, 0, c->apply_grid, c->stream));
+	CK(cudaEventRecord(e1, c->stream));
+	c->timing.emplace_back(e0, e1);
+	c->n_launches++;
+	c->n_flush_launches++;
+	c->pending = false;
+	return NTC_OK;
+}
+
+struct PipeShape {
+	uint32_t ring = 0, nwarps = 0, npos_max = 0, rows_per_unit = 64;
+	size_t smem = 0;
+};
+
+// Which k indices the scan -> hit -> apply pipeline can take for this batch.
+uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, PipeShape* shape)
+{
+	if (!c->use_pipeline || c->kernel == NTC_KERNEL_ROLL64 || b.off || !record_is_piece || b.stride < 4 || (b.stride & 3u) || b.n_rec < 1024 ||
+	    (reinterpret_cast<uintptr_t>(b.words) & 15u))
+		return 0;
+	uint32_t kmask = 0;
+	const uint32_t max_len = (b.stride - 1) * 16;
+	for (unsigned ki = 0; ki < c->nK; ki++) {
+		const unsigned k = c->k[ki];
+		if (k >= 288 || !ntc::pl::have_scan_kernel(k, c->sBits))
+			continue;
+		PipeShape& s = shape[ki];
+		if (max_len < k) { // no k-mer fits any record of this batch: nothing to do for this k
+			s.npos_max = 0;
+			kmask |= 1u << ki;
+			continue;
+		}
+		s.npos_max = max_len - k + 1;
+		if (s.npos_max > 65535)
+			continue;
+		uint32_t r = 64;
+		while (r < k + 16)
+			r <<= 1;
+		const size_t per_warp = (size_t)(r + 1) * 256;
+		const uint32_t nw = (uint32_t)std::min<size_t>(8, ntc::bs::kSmemMax / per_warp);
+		if (nw < 1)
+			continue;
+		s.ring = r;
+		s.nwarps = nw;
+		s.smem = nw * per_warp;
+		// a mask row holds 32 x 32 k-mers, sampled at 2^-(sBits-1): 2^(sBits-1) rows = 1024 candidates on average
+		s.rows_per_unit = std::min(2048u, std::max(2u, 1u << (c->sBits - 1)));
+		kmask |= 1u << ki;
+	}
+	return kmask;
+}
+
+int run_pipeline_k(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh)
+{
+	if (sh.npos_max == 0)
+		return NTC_OK;
+	int rc;
+	const uint32_t n_tiles = (b.n_rec + 1023) / 1024;
+	if ((rc = grow(&c->d_masks, &c->cap_masks, (size_t)n_tiles * sh.npos_max * 32, false)) ||
+	    (rc = grow(&c->d_tile_info, &c->cap_tile_info, (size_t)n_tiles, false)))
+		return rc;
+	ntc::pl::Pool& P = c->pool;
+	CK(cudaMemsetAsync(P.cand, 0, sizeof(unsigned long long), c->stream));
+	CK(cudaMemsetAsync(P.ctl + ntc::pl::CTL_NFLAG, 0, sizeof(uint32_t), c->stream));
+	ntc::pl::ScanArgs sa;
+	sa.words = b.words;
+	sa.stride = b.stride;
+	sa.n_rec = b.n_rec;
+	sa.L.k = c->k[ki];
+	sa.L.ring = sh.ring;
+	sa.L.nwarps = sh.nwarps;
+	sa.L.npos_max = sh.npos_max;
+	memcpy(sa.L.F0, c->bs_launch[ki].F0, sizeof sa.L.F0);
+	memcpy(sa.L.R0, c->bs_launch[ki].R0, sizeof sa.L.R0);
+	sa.masks = c->d_masks;
+	sa.tile_info = c->d_tile_info;
+	sa.f1_k = c->d_f1 + ki;
+	sa.cand = P.cand;
+	sa.ctl = P.ctl;
+	sa.grid = std::min<unsigned>((unsigned)c->n_sm, n_tiles);
+	sa.smem_bytes = sh.smem;
+	sa.stream = c->stream;
+	CK(ntc::pl::launch_scan(c->k[ki], c->sBits, sa));
+	ntc::pl::HitArgs ha;
+	ha.words = b.words;
+	ha.stride = b.stride;
+	ha.n_rec = b.n_rec;
+	ha.n_tiles = n_tiles;
+	ha.k = c->k[ki];
+	ha.ki = ki;
+	ha.sBits = c->sBits;
+	ha.npos_max = sh.npos_max;
+	ha.rows_per_unit = sh.rows_per_unit;
+	ha.masks = c->d_masks;
+	ha.d_tab = c->d_bs_tab;
+	ha.rot_a = c->bs_launch[ki].rot_a;
+	ha.rot_b = c->bs_launch[ki].rot_b;
+	ha.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
+	ha.pool = P;
+	const uint64_t n_units = ((uint64_t)n_tiles * sh.npos_max + sh.rows_per_unit - 1) / sh.rows_per_unit;
+	ha.grid = (unsigned)std::min<uint64_t>(c->hit_grid_max, (n_units + ntc::pl::kHitGroups - 1) / ntc::pl::kHitGroups);
+	ha.stream = c->stream;
+	// conditional flush: only when this batch could exhaust the pool while the sketch is not materialised yet
+	CK(ntc::pl::launch_apply(P, c->d_counters, 0, ha.grid * ntc::pl::kHitGroups * P.nbins + 8, c->apply_grid, c->stream));
+	CK(ntc::pl::launch_hit(ha));
+	CK(ntc::pl::launch_fallback(b.words, b.stride, b.n_rec, n_tiles, c->d_tile_info, c->d_params, ki, ha.ctr_k, P.ctl, c->n_sm, c->stream));
+	c->n_launches += 4;
+	c->pending = true;
+	return NTC_OK;
+}
+
 // Run the sketch kernels over one device-resident batch on the compute stream.
 int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 {
@@ -196,11 +361,19 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
 		return rc;
 	CK(cudaEventRecord(e0, c->stream));
-	const BsConfig bs = bitslice_config(c, b, record_is_piece);
+	PipeShape shape[NTC_MAX_K];
+	const uint32_t pmask = pipeline_config(c, b, record_is_piece, shape);
+	BsConfig bs = c->use_pipeline ? BsConfig() : bitslice_config(c, b, record_is_piece);
 	const uint32_t all = c->nK >= 32 ? 0xFFFFFFFFu : ((1u << c->nK) - 1);
-	const uint32_t roll_mask = all & ~bs.kmask;
+	const uint32_t roll_mask = all & ~(bs.kmask | pmask);
 	if (c->kernel == NTC_KERNEL_BITSLICE && roll_mask)
-		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", bs.kmask);
+		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", bs.kmask | pmask);
+	for (unsigned ki = 0; ki < c->nK; ki++)
+		if ((pmask >> ki) & 1u)
+			if ((rc = run_pipeline_k(c, b, ki, shape[ki])))
+				return rc;
+	if ((bs.kmask || roll_mask) && (rc = flush(c))) // these kernels increment the counters in HBM directly
+		return rc;
 	for (unsigned ki = 0; ki < c->nK; ki++) {
 		if (!((bs.kmask >> ki) & 1u))
 			continue;
@@ -375,6 +548,9 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 			}
 		}
 	}
+	c->use_pipeline = !(getenv("NTC_PIPELINE") && atoi(getenv("NTC_PIPELINE")) == 0);
+	if ((rc = pool_create(c)))
+		return fail(rc);
 	for (int i = 0; i < NBUF; i++) {
 		CKF(cudaEventCreateWithFlags(&c->stage[i].copied, cudaEventDisableTiming));
 		CKF(cudaEventCreateWithFlags(&c->stage[i].consumed, cudaEventDisableTiming));
@@ -418,6 +594,11 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->d_f1) cudaFree(c->d_f1);
 	if (c->d_params) cudaFree(c->d_params);
 	if (c->d_bs_tab) cudaFree(c->d_bs_tab);
+	if (c->pool.entries) cudaFree(c->pool.entries);
+	if (c->pool.slice_blocks) cudaFree(c->pool.slice_blocks);
+	if (c->d_pool_ctl_region) cudaFree(c->d_pool_ctl_region);
+	if (c->d_masks) cudaFree(c->d_masks);
+	if (c->d_tile_info) cudaFree(c->d_tile_info);
 	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -431,9 +612,12 @@ int ntc_reset(ntc_ctx* c)
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
-	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(uint32_t), c->stream));
+	// The counters are NOT cleared here: the first flush after a reset writes zeros slice by slice right before it
+	// applies the slice's increments (apply_kernel, state 0), which saves one full pass over the 1 GiB/k sketch.
+	CK(cudaMemsetAsync(c->d_pool_ctl_region, 0, c->pool_ctl_bytes, c->stream)); // empty log, state = not materialised
 	CK(cudaMemsetAsync(c->d_f1, 0, NTC_MAX_K * sizeof(unsigned long long), c->stream));
 	c->totals_overridden = false;
+	c->pending = true;
 	return NTC_OK;
 }
 
@@ -554,15 +738,30 @@ int ntc_sync(ntc_ctx* c)
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
+	if ((rc = flush(c)))
+		return rc;
 	CK(cudaStreamSynchronize(c->copy_stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return drain_timing(c);
+}
+
+int ntc_flush(ntc_ctx* c)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	return flush(c);
 }
 
 int ntc_counters_device(ntc_ctx* c, void** d_counters, size_t* n_counters)
 {
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
+	int rc;
+	if ((rc = use_device(c)) || (rc = flush(c))) // what the caller reads (or all-reduces) must be complete
+		return rc;
 	if (d_counters) *d_counters = c->d_counters;
 	if (n_counters) *n_counters = c->n_counters;
 	return NTC_OK;
@@ -601,6 +800,8 @@ int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_h
 		return set_err(NTC_EINVAL, "null context");
 	int rc;
 	if ((rc = use_device(c)))
+		return rc;
+	if ((rc = flush(c)))
 		return rc;
 	if (totKmer && (rc = ntc_totals(c, totKmer)))
 		return rc;
@@ -643,6 +844,8 @@ int ntc_hist_range(ntc_ctx* c, const void* d_counters, uint64_t first, uint64_t 
 		return set_err(NTC_EINVAL, "ntc_hist_range: bad argument");
 	int rc;
 	if ((rc = use_device(c)))
+		return rc;
+	if ((rc = flush(c)))
 		return rc;
 	const uint32_t n_tables = c->nK * NTC_NSAMP;
 	const size_t hist_bytes = (size_t)n_tables * 65536 * sizeof(uint32_t);

@@ -1,0 +1,91 @@
+// pipeline.h -- host-side interface of the three-stage sketch pipeline (internal):
+//
+//   S  scan_kernel<KM,S>   bit-sliced upper-ring filter over a uniform-stride batch -> one 32-slot mask word per
+//                          (tile, k-mer position, lane) in HBM, the candidate count, per-tile info
+//   H  hit_kernel          candidates -> full 64-bit canonical hash -> ntComp -> counter index, appended to a
+//                          BINNED hit log (pool of 1 KB blocks, one list of blocks per 32 MiB slice of the sketch)
+//   A  apply_kernel        per slice: bring the slice into L2 (write zeros on the first flush after a reset, read
+//                          it otherwise), then RED.ADD the slice's log entries -- L2-resident atomics run ~8x
+//                          faster than random atomics into the 1 GiB sketch in HBM
+//   F  fallback_kernel     tiles whose records are not all of one length: 64-bit recurrence, direct RED
+//
+// Exactness never depends on capacities: when the pool is exhausted H increments the sketch directly, and the
+// conditional flush in front of H (apply_kernel with force = 0) guarantees the sketch is materialised (zeroed)
+// whenever that can happen.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ntc {
+struct DevParams;
+namespace pl {
+
+constexpr uint32_t kBlkEntries = 256;         // log entries per pool block (1 KB)
+constexpr uint32_t kVoid = 0xFFFFFFFFu;
+constexpr uint32_t kTileFlag = 0xFFFFFFFFu;   // tile_info value: not uniform -> fallback kernel
+constexpr uint32_t kTileRecs = 1024;
+constexpr uint32_t kMaxBins = 64;             // slices per k
+constexpr uint32_t kQueueCap = 2048;          // candidates per round of a hit group
+constexpr uint32_t kGroupThreads = 256, kHitGroups = 2, kHitThreads = kGroupThreads * kHitGroups;
+constexpr uint32_t kApplyThreads = 512;
+
+// control words (device)
+enum { CTL_NEXT = 0, CTL_STATE = 1, CTL_NFLAG = 2, CTL_TICKET = 3, CTL_FLUSHES = 4, CTL_DIRECT = 5, CTL_WORDS = 8 };
+
+struct Pool {                    // device pointers + geometry, passed by value
+	uint32_t* entries;           // [n_blocks][kBlkEntries] counter indices inside one k's [2][2^rBits] sub-sketch
+	uint32_t* slice_blocks;      // [n_slices][slice_cap] block id << 9 | entries in the block
+	uint32_t* slice_nblk;        // [n_slices]
+	uint32_t* zero_done;         // [n_slices] CTAs that zeroed their share of the slice (apply kernel)
+	uint32_t* apply_done;        // [n_slices] CTAs that applied their share of the slice's log
+	uint32_t* ctl;               // [CTL_WORDS]
+	unsigned long long* cand;    // candidate k-mers of the batch being processed (upper bound of its log entries)
+	uint32_t n_blocks, slice_cap, n_slices, nbins, bin_shift, rBits, nK;
+};
+
+struct ScanLaunch {              // per-k constants of the scan kernel, passed by value
+	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (power of two >= k + 16)
+	uint32_t npos_max;           // mask rows per tile
+	uint32_t F0[31], R0[31];     // initial bit-sliced state (bitslice_core.cuh init_state)
+};
+
+struct ScanArgs {
+	const uint32_t* words;
+	uint32_t stride, n_rec;
+	ScanLaunch L;
+	uint32_t* masks;             // [n_tiles][npos_max][32]
+	uint32_t* tile_info;         // [n_tiles]: k-mer positions per record (uniform tile), 0, or kTileFlag
+	unsigned long long* f1_k;
+	unsigned long long* cand;
+	uint32_t* ctl;
+	unsigned grid;
+	size_t smem_bytes;
+	cudaStream_t stream;
+};
+
+struct HitArgs {
+	const uint32_t* words;
+	uint32_t stride, n_rec, n_tiles;
+	uint32_t k, ki, sBits, npos_max, rows_per_unit;
+	const uint32_t* masks;
+	const uint4* d_tab;          // [8][256] byte tables of the full hash
+	uint64_t rot_a, rot_b;
+	uint32_t* ctr_k;             // counters of this k
+	Pool pool;
+	unsigned grid;
+	cudaStream_t stream;
+};
+
+bool have_scan_kernel(unsigned k, unsigned sBits);
+cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a);
+cudaError_t launch_hit(const HitArgs& a);
+size_t hit_smem_bytes();
+cudaError_t launch_fallback(const uint32_t* words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, const uint32_t* tile_info,
+    const DevParams* d_params, uint32_t ki, uint32_t* ctr_k, const uint32_t* ctl, int n_sm, cudaStream_t st);
+// force = 0: flush only if the batch about to be hashed could overflow the pool while the sketch is still
+// unmaterialised (or has flagged tiles); force = 1: flush whatever is pending and materialise the sketch.
+cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32_t reserve_blocks, unsigned grid, cudaStream_t st);
+int apply_max_grid(int n_sm);
+
+} // namespace pl
+} // namespace ntc

@@ -1,0 +1,242 @@
+// scan_kernel.cuh -- stage S of the sketch pipeline: the bit-sliced sampling filter (bitslice_core.cuh) over a
+// uniform-stride batch.  8 warps per CTA (2 per SM sub-partition, so one warp's loads and shared-memory round
+// trips hide behind the other's LOP3 stream), one CTA per SM, up to 255 registers per thread.
+//
+// A warp owns a TILE of 1024 consecutive records (slot s of lane l is record tile*1024 + s*32 + l).  Per column
+// of 16 positions: 128-bit loads of the packed bases (4 columns per load, requested one column ahead), a 32x32
+// bit transpose in registers, bit planes to a shared-memory ring, then the scan: 62 LOP3 for the two 31-bit upper
+// rings + ~30 for the word preparation and the bit-sliced ntComp test per position, for 32 k-mers per lane.
+// Output: one mask word per (tile, k-mer position, lane) -- bit s set = the k-mer of slot s ending here is
+// sampled by ntComp (ntcard.cpp:132-145) -- written straight to HBM with coalesced 128-byte stores; the hit
+// kernel (hit_kernels.cu) turns the set bits into sketch increments.  Also: F1 (ntcard.cpp:155), the candidate
+// count of the batch, and per-tile info (k-mer positions per record; tiles whose records differ in length are
+// flagged for the fallback kernel).
+//
+// No tensor cores: there is no dense contraction; the kernel is bound by the 16-lane integer ALU pipe.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bitslice_core.cuh"
+#include "pipeline.h"
+#include "sketch_common.cuh"
+
+namespace ntc {
+namespace pl {
+
+constexpr int kScanBlock = 4;      // scan positions per unrolled block
+constexpr int kScanThreads = 256;  // 8 warps
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+
+// Branch free on purpose: positions past the end of the read run on whatever the planes hold and store nothing.
+// Planes live in a ring of rmask+1 positions (slot = position mod ring size); slot rmask+1 is all zero and stands
+// for the virtual bases before the read (window not full yet).
+template <int KM, int S, int U> struct ScanBlock {
+	static __device__ __forceinline__ void run(bs::State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ mrow, int qb, int k, int n,
+	    int rmask, uint32_t vmask, uint32_t& cand)
+	{
+		const int q = qb + U;
+		const uint2 in = pl[(q & rmask) * 32];
+		const int oq = q - k;
+		const uint2 out = pl[(oq < 0 ? rmask + 1 : (oq & rmask)) * 32];
+		bs::step<KM, U>(st, in.x, in.y, out.x, out.y);
+		const uint32_t m = bs::sampled_mask<U, S>(st) & vmask;
+		if (q >= k - 1 && q < n) {
+			__stcs(mrow + q * 32, m); // streaming store: read once by the hit kernel
+			cand += __popc(m);
+		}
+		ScanBlock<KM, S, U + 1>::run(st, pl, mrow, qb, k, n, rmask, vmask, cand);
+	}
+};
+template <int KM, int S> struct ScanBlock<KM, S, kScanBlock> {
+	static __device__ __forceinline__ void run(bs::State&, const uint2* __restrict__, uint32_t* __restrict__, int, int, int, int, uint32_t, uint32_t&) {}
+};
+
+// After kScanBlock steps logical ring bit r sits in physical F[r - kScanBlock] / R[r + kScanBlock]: move it home
+// (the compiler absorbs the moves into the destination registers of the block's last position).
+__device__ __forceinline__ void scan_rotate_home(bs::State& st)
+{
+	bs::State t;
+#pragma unroll
+	for (int j = 0; j < 31; j++) {
+		t.F[j] = st.F[bs::mod31(j - kScanBlock)];
+		t.R[j] = st.R[bs::mod31(j + kScanBlock)];
+	}
+	st = t;
+}
+
+// mask rows [r0, npos_max) of a tile hold no k-mer: all-zero words (the hit kernel reads every row of every tile)
+__device__ __forceinline__ void zero_rows(uint32_t* __restrict__ masks, uint32_t tile, uint32_t r0, uint32_t npos_max, uint32_t lane)
+{
+	uint32_t* p = masks + ((size_t)tile * npos_max) * 32 + lane;
+	for (uint32_t r = r0; r < npos_max; r++)
+		__stcs(p + (size_t)r * 32, 0u);
+}
+
+template <int KM, int S>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec, ScanLaunch L,
+    uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_info, unsigned long long* __restrict__ f1_k,
+    unsigned long long* __restrict__ cand_out, uint32_t* __restrict__ ctl)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	if (warp >= L.nwarps)
+		return;
+	const int rmask = (int)L.ring - 1;
+	uint2* planes = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * (L.ring + 1u) * 256u); // [position mod ring][lane]; slot `ring` = zeros
+	planes[L.ring * 32 + lane] = make_uint2(0u, 0u);
+	__syncwarp();
+
+	const int k = (int)L.k;
+	unsigned long long f1_local = 0, cand_local = 0;
+	uint32_t n_flag = 0;
+	const uint32_t n_tiles = (n_rec + kTileRecs - 1) / kTileRecs;
+	// tile = round * (grid * nwarps) + warp * grid + cta: the tiles of the last, partial round go to warp 0 (then 1, ...)
+	// of EVERY SM instead of to all warps of a few SMs
+	for (uint32_t tile = warp * gridDim.x + blockIdx.x; tile < n_tiles; tile += gridDim.x * L.nwarps) {
+		const uint32_t rb = tile * kTileRecs;
+		// The last tile may be partial: slots past the end re-read the batch's last record (every load stays in
+		// bounds, the uniformity test is unaffected) and are masked out of every mask word (vmask).
+		const uint32_t nvalid = min(kTileRecs, n_rec - rb), last_rec = n_rec - 1u;
+		uint32_t vmask = 0;
+		uint4 v[32];
+#pragma unroll
+		for (int s = 0; s < 32; s++) {
+			v[s] = ldg_nc_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride));
+			vmask |= (s * 32u + lane < nvalid ? 1u : 0u) << s;
+		}
+		const uint32_t len0 = __shfl_sync(0xFFFFFFFFu, v[0].x, 0);
+		bool same = true;
+#pragma unroll
+		for (int s = 0; s < 32; s++)
+			same = same && (v[s].x == len0);
+		if (!__all_sync(0xFFFFFFFFu, same)) {
+			// records of different lengths: the fallback kernel hashes this tile with the 64-bit recurrence; its k-mers
+			// are counted here (F1, and as an upper bound of the tile's sketch increments)
+			unsigned long long cnt = 0;
+#pragma unroll
+			for (int s = 0; s < 32; s++)
+				if ((vmask >> s) & 1u)
+					cnt += v[s].x >= (uint32_t)k ? v[s].x - (uint32_t)k + 1u : 0u;
+			f1_local += cnt;
+			cand_local += cnt;
+			if (lane == 0) {
+				tile_info[tile] = kTileFlag;
+				n_flag++;
+			}
+			zero_rows(masks, tile, 0, L.npos_max, lane);
+			continue;
+		}
+		const int n = (int)len0;
+		if (n < k) {
+			if (lane == 0)
+				tile_info[tile] = 0;
+			zero_rows(masks, tile, 0, L.npos_max, lane);
+			continue;
+		}
+		zero_rows(masks, tile, (uint32_t)(n - k + 1), L.npos_max, lane);
+		if (lane == 0)
+			tile_info[tile] = (uint32_t)(n - k + 1);
+		const uint32_t nwords = (uint32_t)(n + 15) >> 4;
+		const uint32_t ngroups = (nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
+		uint32_t* mrow = masks + ((long long)tile * L.npos_max - (k - 1)) * 32 + lane; // row of position q: mrow + 32 q
+		bs::State st;
+#pragma unroll
+		for (int j = 0; j < 31; j++) {
+			st.F[j] = L.F0[j];
+			st.R[j] = L.R0[j];
+		}
+		uint32_t cand = 0;
+		// One column = one packed word of every record = 16 positions: transpose it into the plane ring, scan it.
+		// The next 16 bytes of every record are requested right after the last word of the current 16 bytes has
+		// been taken out of v[], so the loads fly during a whole column's scan.
+#pragma unroll 1
+		for (uint32_t w = 0; w < nwords; w++) {
+			const uint32_t g = (w + 1) >> 2, i = (w + 1) & 3u;
+			uint32_t A[32];
+			switch (i) {
+			case 0:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].x;
+				break;
+			case 1:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].y;
+				break;
+			case 2:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].z;
+				break;
+			default:
+#pragma unroll
+				for (int s = 0; s < 32; s++) A[s] = v[s].w;
+				break;
+			}
+			if (i == 3 && g + 1 < ngroups) {
+#pragma unroll
+				for (int s = 0; s < 32; s++)
+					v[s] = ldg_nc_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride) + (g + 1));
+			}
+			if (w == 0) {
+				// warm L2 with this warp's next tile (bulk async prefetch)
+				const uint64_t nrb = (uint64_t)(tile + gridDim.x * L.nwarps) * kTileRecs;
+				if (lane == 0 && nrb + kTileRecs <= n_rec) {
+					const uint32_t bytes = kTileRecs * stride * 4u;
+					asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(words + nrb * stride), "r"(bytes) : "memory");
+				}
+			}
+			bs::transpose32(A);
+			const int q0 = (int)(16u * w);
+			{
+				uint2* dst = planes + (q0 & rmask) * 32 + lane; // a column never wraps: the ring size is a multiple of 16
+#pragma unroll
+				for (int j = 0; j < 16; j++)
+					dst[j * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
+			}
+			__syncwarp();
+			const int nq = min(16, n - q0);
+#pragma unroll 1
+			for (int qb = q0; qb < q0 + nq; qb += kScanBlock) {
+				ScanBlock<KM, S, 0>::run(st, planes + lane, mrow, qb, k, n, rmask, vmask, cand);
+				scan_rotate_home(st);
+			}
+			__syncwarp();
+		}
+		cand_local += cand;
+		if (lane == 0)
+			f1_local += (unsigned long long)nvalid * (unsigned long long)(n - k + 1);
+	}
+	// totKmer (ntcard.cpp:155), candidate count, flagged tiles: warp-reduce, then one atomic per warp
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		f1_local += __shfl_xor_sync(0xFFFFFFFFu, f1_local, d);
+		cand_local += __shfl_xor_sync(0xFFFFFFFFu, cand_local, d);
+	}
+	if (lane == 0) {
+		if (f1_local)
+			atomicAdd(f1_k, f1_local);
+		if (cand_local)
+			atomicAdd(cand_out, cand_local);
+		if (n_flag)
+			atomicAdd(ctl + CTL_NFLAG, n_flag);
+	}
+}
+
+template <int KM, int S>
+cudaError_t launch_scan_one(const ScanArgs& a)
+{
+	auto kern = scan_kernel<KM, S>;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes);
+	if (e != cudaSuccess)
+		return e;
+	kern<<<a.grid, kScanThreads, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.masks, a.tile_info, a.f1_k, a.cand, a.ctl);
+	return cudaGetLastError();
+}
+
+} // namespace pl
+} // namespace ntc
