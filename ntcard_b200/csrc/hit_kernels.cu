@@ -40,22 +40,19 @@ struct HashCtx {
 	uint64_t rot_a, rot_b;
 };
 
-struct HitLoad { // a candidate with the packed words of its first 32-base block in flight
-	uint32_t p, nwords;
-	const uint32_t* __restrict__ b;
+struct HitLoad { // the packed words of a candidate's first 32-base block, in flight
 	uint32_t x0, x1, x2;
 };
 
-__device__ __forceinline__ HitLoad hit_issue(const HashCtx& c, uint32_t rec, uint32_t p, uint32_t nwords)
+// rec_words: the base words of the record (word 0 = length skipped); p: k-mer start; last: index of the last base word
+// that may be read (the record's slot in the uniform-stride batch)
+__device__ __forceinline__ HitLoad hit_issue(const HashCtx& c, const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
 {
 	HitLoad h;
-	h.p = p;
-	h.nwords = nwords;
-	h.b = c.words + (uint64_t)rec * c.stride + 1;
 	const uint32_t wi = (p + (c.k & 31u)) >> 4;
-	h.x0 = __ldg(h.b + min(wi, nwords - 1));
-	h.x1 = __ldg(h.b + min(wi + 1, nwords - 1));
-	h.x2 = __ldg(h.b + min(wi + 2, nwords - 1));
+	h.x0 = __ldg(rec_words + min(wi, last));
+	h.x1 = __ldg(rec_words + min(wi + 1, last));
+	h.x2 = __ldg(rec_words + min(wi + 2, last));
 	return h;
 }
 
@@ -81,12 +78,12 @@ __device__ __forceinline__ void block_tables(const uint4* __restrict__ tab, uint
 // (NTF64/NTR64 base forms, nthash.hpp:220-239), then M blocks of 32 bases:
 //   fh = srol^32(fh) ^ FB_m        rh ^= srol^(t+32m) RB_m
 // Returns the counter index inside the k's [2][2^rBits] sub-sketch, or kVoid when ntComp does not sample it.
-__device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& h)
+__device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& h, const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
 {
 	const uint32_t t = c.k & 31u, M = c.k >> 5;
 	uint32_t hh, hl; // canonical hash, high / low word
 	if (t == 0 && M == 1) { // k = 32: pure 32-bit path
-		const uint32_t sh = (h.p & 15u) * 2u;
+		const uint32_t sh = (p & 15u) * 2u;
 		uint32_t f0, f1, r0, r1;
 		block_tables(c.tab, __funnelshift_r(h.x0, h.x1, sh), __funnelshift_r(h.x1, h.x2, sh), f0, f1, r0, r1);
 		const bool rlt = r1 < f1 || (r1 == f1 && r0 < f0);
@@ -95,18 +92,18 @@ __device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& 
 	} else {
 		uint64_t fh = 0, rh = 0;
 		for (uint32_t i = 0; i < t; i++) {
-			const uint32_t code = base_at(h.b, h.p + i);
+			const uint32_t code = base_at(rec_words, p + i);
 			fh = srol(fh) ^ seed_of(code);
 			rh ^= srol_n(seed_of(3u - code), i);
 		}
 		uint32_t x0 = h.x0, x1 = h.x1, x2 = h.x2;
 		for (uint32_t m = 0; m < M; m++) {
-			const uint32_t o = h.p + t + 32u * m, sh = (o & 15u) * 2u;
+			const uint32_t o = p + t + 32u * m, sh = (o & 15u) * 2u;
 			if (m) {
 				const uint32_t wi = o >> 4;
-				x0 = __ldg(h.b + wi);
-				x1 = __ldg(h.b + wi + 1);
-				x2 = __ldg(h.b + min(wi + 2, h.nwords - 1));
+				x0 = __ldg(rec_words + wi);
+				x1 = __ldg(rec_words + wi + 1);
+				x2 = __ldg(rec_words + min(wi + 2, last));
 			}
 			uint32_t f0, f1, r0, r1;
 			block_tables(c.tab, __funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), f0, f1, r0, r1);
@@ -132,128 +129,161 @@ __device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& 
 // hit kernel
 // ------------------------------------------------------------------------------------------------
 // A CTA is kHitGroups independent groups of 256 threads that share only the byte tables; each group works on its
-// own unit (kHitRows... `rows_per_unit` consecutive mask rows = 1024 candidates on average) and synchronises with
-// a named barrier, so the groups of an SM are in different phases and hide each other's latencies.
+// own unit (a run of mask rows holding ~2048 candidates on average) and synchronises with a named barrier, so the
+// groups of an SM are in different phases and hide each other's latencies.
+//
+// Log appends are optimistic: every bin of a group has an open pool block with at least kBlkSlack free entries at
+// the start of a round, a hit takes its slot with one shared-memory atomic and is stored straight to the block.
+// The rare hit that finds its block full waits in an overflow list for the end of the round, when thread b tops
+// bin b up: a block with less than kBlkSlack free entries is closed and the spare block -- requested one round
+// earlier, so its allocation latency is never waited for -- takes its place.
 struct GroupSmem {
 	uint32_t queue[kQueueCap];
-	uint16_t rank[kQueueCap];
-	uint32_t cnt[kMaxBins];
-	uint32_t cur[kMaxBins], fill[kMaxBins], curpos[kMaxBins];                      // open block of every bin (persists over rounds)
-	uint32_t cur0[kMaxBins], fill0[kMaxBins], first[kMaxBins], nvalid[kMaxBins];   // this round's placement
-	uint32_t qn, ovf;
+	uint32_t ovf_list[kQueueCap];
+	uint32_t cur[kMaxBins], fill[kMaxBins], curpos[kMaxBins]; // open block of every bin (persists over rounds)
+	uint32_t qn, ovf, n_ovf;
 };
 struct HitSmem {
 	uint4 tab[8 * 256];
 	GroupSmem g[kHitGroups];
 };
 
-constexpr int kHitBatch = 2; // candidates per thread whose loads are in flight together
+constexpr int kHitBatch = 4; // candidates per thread whose loads are in flight together
 
 __device__ __forceinline__ void group_sync(uint32_t g)
 {
 	asm volatile("bar.sync %0, %1;" ::"r"(g + 1u), "n"(kGroupThreads) : "memory");
 }
 
+struct Unit {            // the mask rows a group works on
+	uint32_t tile0;      // first tile
+	uint32_t r0;         // first row inside tile0 (one-tile units), 0 otherwise
+	uint32_t nrows;
+	bool multi;          // rows run over several whole tiles (row r -> tile0 + r / npos_max)
+};
+
+struct Spare {           // thread b's spare block for bin b, in registers
+	uint32_t blk, at;
+	bool have;
+};
+
 // queue entry: slot (5 bits) | lane (5) << 5 | mask row inside the unit << 10
-__device__ __forceinline__ void process_queue(GroupSmem& sm, const HitArgs& a, const HashCtx& c, uint32_t n, uint32_t row0, uint32_t g, uint32_t gtid)
+__device__ __forceinline__ void decode(const HitArgs& a, const Unit& U, uint32_t e, uint32_t& rec, uint32_t& p)
+{
+	const uint32_t s = e & 31u, ln = (e >> 5) & 31u, r = e >> 10;
+	uint32_t tile = U.tile0;
+	p = U.r0 + r;
+	if (U.multi) {
+		const uint32_t t = r / a.npos_max;
+		tile += t;
+		p = r - t * a.npos_max;
+	}
+	rec = tile * kTileRecs + s * 32u + ln;
+}
+
+// one log entry: slot in the bin's open block, or the overflow list when the block is full / absent
+__device__ __forceinline__ void append(GroupSmem& sm, const HitArgs& a, uint32_t idx, bool retry)
 {
 	const Pool& P = a.pool;
-	if (gtid < kMaxBins)
-		sm.cnt[gtid] = 0;
-	group_sync(g);
-	// ---- pass 1: candidates -> counter indices, rank inside the bin --------------------------------------------
+	const uint32_t b = idx >> P.bin_shift;
+	const uint32_t cu = sm.cur[b];
+	if (cu == kVoid) { // the pool ran out: the sketch is materialised whenever that can happen (pipeline.h) -> RED
+		atomicAdd(a.ctr_k + idx, 1u);
+		P.ctl[CTL_DIRECT] = 1u; // statistics only
+		return;
+	}
+	const uint32_t slot = atomicAdd(&sm.fill[b], 1u);
+	if (slot < kBlkEntries) {
+		if (!(P.dbg & 16u))
+			P.entries[(size_t)cu * kBlkEntries + slot] = idx;
+	} else {
+		sm.ovf_list[atomicAdd(&sm.n_ovf, 1u)] = idx;
+	}
+	(void)retry;
+}
+
+// end of a round: thread b closes bin b's block if it is (nearly) full and opens the spare
+__device__ __forceinline__ void top_up(GroupSmem& sm, const HitArgs& a, uint32_t b, Spare& sp)
+{
+	const Pool& P = a.pool;
+	const uint32_t slice = a.ki * P.nbins + b;
+	uint32_t* list = P.slice_blocks + (size_t)slice * P.slice_cap;
+	const uint32_t cu = sm.cur[b];
+	const uint32_t f = min(sm.fill[b], kBlkEntries);
+	if (cu != kVoid) {
+		list[sm.curpos[b]] = (cu << 9) | f;
+		if (f + kBlkSlack <= kBlkEntries) {
+			sm.fill[b] = f;
+			return;
+		}
+	}
+	// open the spare (a void spare = pool exhausted: the bin goes to direct increments)
+	if (!sp.have) { // only at the very first round of the kernel
+		sp.blk = atomicAdd(P.ctl + CTL_NEXT, 1u);
+		sp.at = atomicAdd(P.slice_nblk + slice, 1u);
+	}
+	const bool ok = sp.blk < P.n_blocks && sp.at < P.slice_cap;
+	if (sp.at < P.slice_cap)
+		list[sp.at] = ok ? (sp.blk << 9) : kVoid;
+	sm.cur[b] = ok ? sp.blk : kVoid;
+	sm.curpos[b] = sp.at;
+	sm.fill[b] = 0;
+	// request the next spare now; nobody waits for the answer before the next top-up
+	sp.blk = atomicAdd(P.ctl + CTL_NEXT, 1u);
+	sp.at = atomicAdd(P.slice_nblk + slice, 1u);
+	sp.have = true;
+}
+
+__device__ __forceinline__ void process_queue(GroupSmem& sm, const HitArgs& a, const HashCtx& c, uint32_t n, const Unit& U, uint32_t g,
+    uint32_t gtid, Spare& sp)
+{
+	const Pool& P = a.pool;
+	const uint32_t last = a.stride - 2u;
+	// ---- candidates -> counter indices -> log ------------------------------------------------------------------
 	for (uint32_t base = 0; base < n; base += kGroupThreads * kHitBatch) {
 		HitLoad h[kHitBatch];
 #pragma unroll
 		for (int u = 0; u < kHitBatch; u++) {
 			const uint32_t i = base + u * kGroupThreads + gtid;
 			if (i < n) {
-				const uint32_t e = sm.queue[i];
-				const uint32_t s = e & 31u, ln = (e >> 5) & 31u, grow = row0 + (e >> 10);
-				const uint32_t tile = grow / a.npos_max, p = grow - tile * a.npos_max;
-				h[u] = hit_issue(c, tile * kTileRecs + s * 32u + ln, p, a.stride - 1u);
+				uint32_t rec, p;
+				decode(a, U, sm.queue[i], rec, p);
+				if (!(P.dbg & 32u))
+					h[u] = hit_issue(c, c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1, p, last);
 			}
 		}
 #pragma unroll
 		for (int u = 0; u < kHitBatch; u++) {
 			const uint32_t i = base + u * kGroupThreads + gtid;
 			if (i < n) {
-				const uint32_t idx = hit_finish(c, h[u]);
-				sm.queue[i] = idx;
+				uint32_t rec, p;
+				decode(a, U, sm.queue[i], rec, p);
+				uint32_t idx = rec < a.n_rec ? hit_finish(c, h[u], c.words + (uint64_t)rec * c.stride + 1, p, last) : kVoid;
+				if (P.dbg & 32u)
+					idx = (rec * 2654435761u + p * 40503u) & ((2u << P.rBits) - 1u);
 				if (idx != kVoid)
-					sm.rank[i] = (uint16_t)atomicAdd(&sm.cnt[idx >> P.bin_shift], 1u);
+					append(sm, a, idx, false);
 			}
 		}
 	}
 	group_sync(g);
-	// ---- placement: pool blocks for what does not fit the open blocks; block lists of the slices ----------------
-	if (gtid < P.nbins) {
-		const uint32_t b = gtid;
-		const uint32_t cb = sm.cnt[b];
-		const uint32_t f0 = sm.fill[b], cu = sm.cur[b];
-		const uint32_t space = kBlkEntries - f0; // an absent block has fill = kBlkEntries
-		sm.fill0[b] = f0;
-		sm.cur0[b] = cu;
-		sm.first[b] = 0;
-		sm.nvalid[b] = 0;
-		const uint32_t slice = a.ki * P.nbins + b;
-		uint32_t* list = P.slice_blocks + (size_t)slice * P.slice_cap;
-		if (cb > space) {
-			const uint32_t rem = cb - space, need = (rem + kBlkEntries - 1) / kBlkEntries;
-			const uint32_t fst = atomicAdd(P.ctl + CTL_NEXT, need);
-			const uint32_t at = atomicAdd(P.slice_nblk + slice, need);
-			const uint32_t last_fill = rem - (need - 1) * kBlkEntries;
-			if (cu != kVoid)
-				list[sm.curpos[b]] = (cu << 9) | kBlkEntries; // the open block gets filled up
-			uint32_t nv = 0;
-			for (uint32_t j = 0; j < need; j++) {
-				const uint64_t blk = (uint64_t)fst + j;
-				const bool ok = blk < P.n_blocks && (uint64_t)at + j < P.slice_cap;
-				if ((uint64_t)at + j < P.slice_cap)
-					list[at + j] = ok ? (((uint32_t)blk << 9) | (j == need - 1 ? last_fill : kBlkEntries)) : kVoid;
-				if (ok)
-					nv = j + 1;
-			}
-			sm.first[b] = fst;
-			sm.nvalid[b] = nv;
-			if (nv == need) {
-				sm.cur[b] = fst + need - 1;
-				sm.fill[b] = last_fill;
-				sm.curpos[b] = at + need - 1;
-			} else { // pool exhausted: what did not get a block is added to the sketch directly (see pipeline.h)
-				sm.cur[b] = kVoid;
-				sm.fill[b] = kBlkEntries;
-			}
-		} else if (cb) {
-			sm.fill[b] = f0 + cb;
-			list[sm.curpos[b]] = (cu << 9) | (f0 + cb);
-		}
+	// ---- top up the bins; place what overflowed (rare) ------------------------------------------------------------
+	for (;;) {
+		const uint32_t n_ovf = sm.n_ovf;
+		if (gtid < P.nbins)
+			top_up(sm, a, gtid, sp);
+		if (n_ovf == 0)
+			break;
+		group_sync(g);
+		for (uint32_t i = gtid; i < n_ovf; i += kGroupThreads)
+			sm.queue[i] = sm.ovf_list[i];
+		if (gtid == 0)
+			sm.n_ovf = 0;
+		group_sync(g);
+		for (uint32_t i = gtid; i < n_ovf; i += kGroupThreads)
+			append(sm, a, sm.queue[i], true);
+		group_sync(g);
 	}
-	group_sync(g);
-	// ---- pass 2: entries into the pool blocks -----------------------------------------------------------------------
-	for (uint32_t i = gtid; i < n; i += kGroupThreads) {
-		const uint32_t idx = sm.queue[i];
-		if (idx == kVoid)
-			continue;
-		const uint32_t b = idx >> P.bin_shift;
-		const uint32_t v = sm.fill0[b] + sm.rank[i];
-		uint32_t blk, o;
-		if (v < kBlkEntries) {
-			blk = sm.cur0[b];
-			o = v;
-		} else {
-			const uint32_t q = (v - kBlkEntries) / kBlkEntries;
-			o = (v - kBlkEntries) % kBlkEntries;
-			blk = q < sm.nvalid[b] ? sm.first[b] + q : kVoid;
-		}
-		if (blk != kVoid) {
-			P.entries[(size_t)blk * kBlkEntries + o] = idx;
-		} else {
-			atomicAdd(a.ctr_k + idx, 1u); // RED: legal, the sketch is materialised whenever the pool can run out
-			P.ctl[CTL_DIRECT] = 1u;       // statistics only
-		}
-	}
-	group_sync(g);
 }
 
 __device__ __forceinline__ void emit_bits(GroupSmem& sm, uint32_t x, uint32_t w, uint32_t& at)
@@ -273,11 +303,33 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 	GroupSmem& sm = S.g[g];
 	for (uint32_t i = tid; i < 8 * 256; i += kHitThreads)
 		S.tab[i] = a.d_tab[i];
+	// open / spare blocks of this group: carried over from the previous launch unless a flush or a reset came between
+	const uint32_t group_id = blockIdx.x * kHitGroups + g;
+	const uint32_t nb = a.pool.nbins;
+	uint32_t* gs = a.pool.gstate + ((size_t)a.ki * a.pool.max_groups + group_id) * (1 + 5 * (size_t)nb);
+	const uint32_t gen = (a.pool.epoch << 16) | (a.pool.ctl[CTL_FLUSHES] & 0xFFFFu);
+	const bool active = group_id < a.n_units && group_id < a.pool.max_groups;
+	const bool resume = active && gs[0] == gen;
+	Spare sp;
+	sp.have = false;
+	sp.blk = sp.at = 0;
 	if (gtid < kMaxBins) {
 		sm.cur[gtid] = kVoid;
 		sm.fill[gtid] = kBlkEntries;
+		if (resume && gtid < nb) {
+			sm.cur[gtid] = gs[1 + gtid];
+			sm.fill[gtid] = gs[1 + nb + gtid];
+			sm.curpos[gtid] = gs[1 + 2 * nb + gtid];
+			sp.blk = gs[1 + 3 * nb + gtid];
+			sp.at = gs[1 + 4 * nb + gtid];
+			sp.have = true;
+		}
 	}
+	if (gtid == 0)
+		sm.n_ovf = 0;
 	__syncthreads();
+	if (gtid < nb && active && !resume)
+		top_up(sm, a, gtid, sp); // open a first block for every bin
 	HashCtx c;
 	c.words = a.words;
 	c.stride = a.stride;
@@ -287,14 +339,21 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 	c.tab = S.tab;
 	c.rot_a = a.rot_a;
 	c.rot_b = a.rot_b;
-	const uint64_t total_rows = (uint64_t)a.n_tiles * a.npos_max;
-	const uint32_t RU = a.rows_per_unit;
-	const uint32_t n_units = (uint32_t)((total_rows + RU - 1) / RU);
 	constexpr int kW = 8; // mask words per thread in flight
-	for (uint32_t unit = blockIdx.x * kHitGroups + g; unit < n_units; unit += gridDim.x * kHitGroups) {
-		const uint32_t row0 = unit * RU;
-		const uint32_t nw = (uint32_t)min((uint64_t)RU, total_rows - row0) * 32u;
-		const uint32_t* m = a.masks + (size_t)row0 * 32u;
+	for (uint32_t unit = blockIdx.x * kHitGroups + g; unit < a.n_units; unit += gridDim.x * kHitGroups) {
+		Unit U;
+		U.multi = a.tiles_per_unit > 1;
+		if (!U.multi) {
+			U.tile0 = unit / a.units_per_tile;
+			U.r0 = (unit - U.tile0 * a.units_per_tile) * a.rows_per_unit;
+			U.nrows = min(a.rows_per_unit, a.npos_max - U.r0);
+		} else {
+			U.tile0 = unit * a.tiles_per_unit;
+			U.r0 = 0;
+			U.nrows = min(a.tiles_per_unit, a.n_tiles - U.tile0) * a.npos_max;
+		}
+		const uint32_t nw = U.nrows * 32u;
+		const uint32_t* m = a.masks + ((size_t)U.tile0 * a.npos_max + U.r0) * 32u;
 		if (gtid == 0) {
 			sm.qn = 0;
 			sm.ovf = 0;
@@ -325,17 +384,17 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 		group_sync(g);
 		if (!sm.ovf) {
 			const uint32_t n = sm.qn;
-			if (n)
-				process_queue(sm, a, c, n, row0, g, gtid);
+			if (n && !(a.pool.dbg & 64u))
+				process_queue(sm, a, c, n, U, g, gtid, sp);
 		} else {
-			// skewed data: more candidates than the queue holds -> two mask rows (<= 2048 candidates) per round
-			for (uint32_t w0 = 0; w0 < nw; w0 += 64) {
+			// skewed data: more candidates than the queue holds -> four mask rows (<= 4096 candidates) per round
+			for (uint32_t w0 = 0; w0 < nw; w0 += 128) {
 				group_sync(g);
 				if (gtid == 0)
 					sm.qn = 0;
 				group_sync(g);
 				const uint32_t w = w0 + gtid;
-				const uint32_t x = (gtid < 64 && w < nw) ? __ldg(m + w) : 0u;
+				const uint32_t x = (gtid < 128 && w < nw) ? __ldg(m + w) : 0u;
 				if (x) {
 					uint32_t at = atomicAdd(&sm.qn, (uint32_t)__popc(x));
 					emit_bits(sm, x, w, at);
@@ -343,9 +402,27 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 				group_sync(g);
 				const uint32_t n = sm.qn;
 				if (n)
-					process_queue(sm, a, c, n, row0, g, gtid);
+					process_queue(sm, a, c, n, U, g, gtid, sp);
 			}
 		}
+	}
+	// keep the open and spare blocks for the next launch; the spare is registered as an empty block
+	if (active) {
+		group_sync(g);
+		if (gtid < nb) {
+			if (sp.have) {
+				uint32_t* list = a.pool.slice_blocks + (size_t)(a.ki * nb + gtid) * a.pool.slice_cap;
+				if (sp.at < a.pool.slice_cap)
+					list[sp.at] = (sp.blk < a.pool.n_blocks) ? (sp.blk << 9) : kVoid;
+			}
+			gs[1 + gtid] = sm.cur[gtid];
+			gs[1 + nb + gtid] = sm.fill[gtid];
+			gs[1 + 2 * nb + gtid] = sm.curpos[gtid];
+			gs[1 + 3 * nb + gtid] = sp.blk;
+			gs[1 + 4 * nb + gtid] = sp.at;
+		}
+		if (gtid == 0)
+			gs[0] = sp.have ? gen : 0u;
 	}
 }
 
@@ -399,16 +476,17 @@ __device__ __forceinline__ void role_sync(uint32_t role)
 //                               prefetches -- at most kApplyAhead slices ahead of the slowest applier;
 //   appliers (threads 256..511) RED.ADD the log entries of slice s once every CTA has staged it.
 // In steady state the stagers stream the sketch at HBM write speed while the appliers' atomics hit L2.
-constexpr uint32_t kApplyAhead = 2;
+
 
 __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint32_t* __restrict__ counters, int force, uint32_t reserve_blocks)
 {
+	const uint32_t kApplyAhead = P.ahead;
 	// ---- decide (every CTA reads the same values: they were written by earlier kernels) ----
 	const uint32_t next = P.ctl[CTL_NEXT];
 	const uint32_t used = min(next, P.n_blocks);
 	const uint32_t state = P.ctl[CTL_STATE];
 	if (!force) {
-		const unsigned long long need = *P.cand / kBlkEntries + reserve_blocks;
+		const unsigned long long need = *P.cand / (kBlkEntries - kBlkSlack) + reserve_blocks; // closed blocks hold > 256 - slack entries
 		const bool tight = used + need > P.n_blocks;
 		const bool flush = state == 0 ? (tight || P.ctl[CTL_NFLAG] != 0) : (tight && used > 0);
 		if (!flush)
@@ -427,16 +505,17 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 		const size_t n16 = slice_len / 4; // 16-byte units per slice
 		const size_t a0 = n16 * blockIdx.x / gridDim.x, a1 = n16 * (blockIdx.x + 1) / gridDim.x;
 		for (uint32_t s = 0; s < P.n_slices; s++) {
-			if (s >= kApplyAhead) { // L2 footprint: do not run more than kApplyAhead slices ahead of the appliers
+			if (s >= kApplyAhead && !(P.dbg & 4u)) { // L2 footprint: do not run more than kApplyAhead slices ahead of the appliers
 				if (rtid == 0)
 					while (ld_acquire(P.apply_done + s - kApplyAhead) < gridDim.x)
-						__nanosleep(32);
+						__nanosleep(20);
 				role_sync(role);
 			}
 			uint4* p = reinterpret_cast<uint4*>(counters + (size_t)(s / P.nbins) * per_k + (size_t)(s % P.nbins) * slice_len);
 			if (zero_mode) {
-				for (size_t i = a0 + rtid; i < a1; i += nrt)
-					p[i] = make_uint4(0u, 0u, 0u, 0u);
+				if (!(P.dbg & 8u))
+					for (size_t i = a0 + rtid; i < a1; i += nrt)
+						p[i] = make_uint4(0u, 0u, 0u, 0u);
 				role_sync(role);
 				if (rtid == 0) {
 					__threadfence();
@@ -451,37 +530,55 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 		}
 	} else {
 		// ================= appliers =================
+		// One warp per log block.  The first block of the NEXT slice is loaded (list entry -> 256 entries) before
+		// the warp waits for the current slice to be staged, so the loads' latency is off the per-slice chain.
 		const uint32_t lane = rtid & 31u, warp = rtid >> 5, nwarp = nrt / 32;
+		constexpr int kV = kBlkEntries / 32;
+		const uint32_t j0 = blockIdx.x * nwarp + warp, jstep = gridDim.x * nwarp;
+		auto load_block = [&](uint32_t s, uint32_t j, uint32_t nb, uint32_t (&v)[kV]) {
+			uint32_t le = kVoid;
+			if (j < nb)
+				le = __ldcs(P.slice_blocks + (size_t)s * P.slice_cap + j);
+			const uint32_t f = le == kVoid ? 0u : min(le & 511u, kBlkEntries);
+			const uint32_t* e = P.entries + (size_t)(le >> 9) * kBlkEntries;
+#pragma unroll
+			for (int u = 0; u < kV; u++)
+				v[u] = lane + 32u * u < f ? __ldcs(e + lane + 32u * u) : kVoid;
+		};
+		uint32_t v[kV], vn[kV];
+		uint32_t nb = min(P.slice_nblk[0], P.slice_cap);
+		load_block(0, j0, nb, v);
 		for (uint32_t s = 0; s < P.n_slices; s++) {
-			const uint32_t nb = min(P.slice_nblk[s], P.slice_cap);
+			const uint32_t nbn = s + 1 < P.n_slices ? min(P.slice_nblk[s + 1], P.slice_cap) : 0u;
+			if (s + 1 < P.n_slices)
+				load_block(s + 1, j0, nbn, vn);
 			if (nb) {
-				if (zero_mode) {
+				if (zero_mode && !(P.dbg & 2u)) {
 					if (rtid == 0)
 						while (ld_acquire(P.zero_done + s) < gridDim.x)
-							__nanosleep(32);
+							__nanosleep(20);
 					role_sync(role);
 				}
 				uint32_t* ctr = counters + (size_t)(s / P.nbins) * per_k;
-				const uint32_t* list = P.slice_blocks + (size_t)s * P.slice_cap;
-				for (uint32_t j = blockIdx.x * nwarp + warp; j < nb; j += gridDim.x * nwarp) {
-					const uint32_t le = __ldcs(list + j);
-					if (le == kVoid)
-						continue;
-					const uint32_t f = min(le & 511u, kBlkEntries);
-					const uint32_t* e = P.entries + (size_t)(le >> 9) * kBlkEntries;
-					uint32_t v[kBlkEntries / 32];
 #pragma unroll
-					for (int u = 0; u < (int)(kBlkEntries / 32); u++)
-						v[u] = lane + 32u * u < f ? __ldcs(e + lane + 32u * u) : kVoid;
+				for (int u = 0; u < kV; u++)
+					if (v[u] != kVoid && !(P.dbg & 1u))
+						atomicAdd(ctr + v[u], 1u); // RED.ADD, L2 resident
+				for (uint32_t j = j0 + jstep; j < nb; j += jstep) { // more blocks than warps: the rest, unpipelined
+					load_block(s, j, nb, v);
 #pragma unroll
-					for (int u = 0; u < (int)(kBlkEntries / 32); u++)
+					for (int u = 0; u < kV; u++)
 						if (v[u] != kVoid)
-							atomicAdd(ctr + v[u], 1u); // RED.ADD, L2 resident
+							atomicAdd(ctr + v[u], 1u);
 				}
 			}
 			role_sync(role);
 			if (rtid == 0)
 				atomicAdd(P.apply_done + s, 1u);
+#pragma unroll
+			for (int u = 0; u < kV; u++)
+				v[u] = vn[u];
+			nb = nbn;
 		}
 	}
 	// ---- the last CTA to finish resets the pool ----

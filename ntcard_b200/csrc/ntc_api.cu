@@ -85,6 +85,7 @@ struct ntc_ctx {
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
 	unsigned apply_grid = 0, hit_grid_max = 0;
+	unsigned chunk_waves = 1; // scan waves per pipeline chunk (0 = whole batch)
 	uint64_t n_flush_launches = 0;
 	// finish buffers
 	uint16_t* d_narrow = nullptr;
@@ -205,12 +206,17 @@ int pool_create(ntc_ctx* c)
 {
 	ntc::pl::Pool& P = c->pool;
 	const char* env = getenv("NTC_POOL_BLOCKS");
-	P.n_blocks = env ? (uint32_t)strtoul(env, nullptr, 10) : (256u << 10); // x 256 entries x 4 B = 256 MiB
+	P.n_blocks = env ? (uint32_t)strtoul(env, nullptr, 10) : (512u << 10); // x 256 entries x 4 B = 512 MiB
 	P.n_blocks = std::min(std::max(P.n_blocks, 64u), (1u << 23) - 1u); // a block id has 23 bits in the slice lists
 	P.rBits = c->rBits;
 	P.nK = c->nK;
+	P.ahead = getenv("NTC_APPLY_AHEAD") ? (uint32_t)atoi(getenv("NTC_APPLY_AHEAD")) : 2u;
+	P.dbg = getenv("NTC_PL_DEBUG") ? (uint32_t)strtoul(getenv("NTC_PL_DEBUG"), nullptr, 0) : 0u;
 	const uint32_t idx_bits = c->rBits + 1;
-	P.bin_shift = idx_bits <= 22 ? idx_bits : std::max(22u, idx_bits - 6u); // slices of 16 MiB (r <= 27), <= 64 per k
+	{
+		const uint32_t ss = getenv("NTC_SLICE_SHIFT") ? (uint32_t)atoi(getenv("NTC_SLICE_SHIFT")) : 23u; // 2^23 counters = 32 MiB
+		P.bin_shift = idx_bits <= ss ? idx_bits : std::max(ss, idx_bits - 6u); // <= 64 slices per k
+	}
 	P.nbins = 1u << (idx_bits - P.bin_shift);
 	P.n_slices = c->nK * P.nbins;
 	P.slice_cap = std::max(16u, P.n_blocks / 4);
@@ -227,6 +233,13 @@ int pool_create(ntc_ctx* c)
 	P.cand = reinterpret_cast<unsigned long long*>(P.apply_done + P.n_slices + ((ntc::pl::CTL_WORDS + 3 * P.n_slices) & 1u));
 	c->apply_grid = (unsigned)ntc::pl::apply_max_grid(c->n_sm);
 	c->hit_grid_max = (unsigned)c->n_sm * 2u;
+	P.max_groups = c->hit_grid_max * ntc::pl::kHitGroups;
+	P.epoch = 1;
+	{
+		const size_t gwords = (size_t)c->nK * P.max_groups * (1 + 5 * (size_t)P.nbins);
+		CK(cudaMalloc((void**)&P.gstate, gwords * sizeof(uint32_t)));
+		CK(cudaMemset(P.gstate, 0, gwords * sizeof(uint32_t)));
+	}
 	return NTC_OK;
 }
 
@@ -250,7 +263,7 @@ int flush(ntc_ctx* c)
 }
 
 struct PipeShape {
-	uint32_t ring = 0, nwarps = 0, npos_max = 0, rows_per_unit = 64;
+	uint32_t ring = 0, nwarps = 0, npos_max = 0, rows_per_unit = 64, units_per_tile = 1, tiles_per_unit = 1;
 	size_t smem = 0;
 };
 
@@ -285,17 +298,53 @@ uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 		s.ring = r;
 		s.nwarps = nw;
 		s.smem = nw * per_warp;
-		// a mask row holds 32 x 32 k-mers, sampled at 2^-(sBits-1): 2^(sBits-1) rows = 1024 candidates on average
-		s.rows_per_unit = std::min(2048u, std::max(2u, 1u << (c->sBits - 1)));
+		// a mask row holds 32 x 32 k-mers, sampled at 2^-(sBits-1): 2^(sBits-1) rows = 1024 candidates on average.
+		// A unit of the hit kernel is either a run of rows of one tile or several whole tiles.
+		const uint32_t target = std::min(4096u, std::max(4u, 2u << (c->sBits - 1))); // 2048 candidates per unit
+		if (s.npos_max >= target) {
+			s.units_per_tile = std::max(1u, (s.npos_max + target / 2) / target);
+			s.rows_per_unit = (s.npos_max + s.units_per_tile - 1) / s.units_per_tile;
+			s.tiles_per_unit = 1;
+		} else {
+			s.units_per_tile = 1;
+			s.tiles_per_unit = std::max(1u, target / s.npos_max);
+			s.rows_per_unit = s.npos_max;
+		}
 		kmask |= 1u << ki;
 	}
 	return kmask;
 }
 
+int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh);
+
+// One k over one batch.  The batch is cut into chunks of about one wave of scan tiles (8 per SM): the hit kernel then
+// finds the packed reads and the mask words its scan kernel just touched still in L2, not in HBM.
 int run_pipeline_k(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh)
 {
 	if (sh.npos_max == 0)
 		return NTC_OK;
+	const uint32_t n_tiles = (b.n_rec + 1023) / 1024;
+	uint32_t chunk_tiles = (uint32_t)c->n_sm * std::max(1u, sh.nwarps) * c->chunk_waves;
+	if (c->chunk_waves == 0 || chunk_tiles >= n_tiles)
+		return run_pipeline_chunk(c, b, ki, sh);
+	// equal chunks, each a whole number of tiles
+	const uint32_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+	chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
+	for (uint32_t t0 = 0; t0 < n_tiles; t0 += chunk_tiles) {
+		ntc::BatchView sub = b;
+		const uint64_t r0 = (uint64_t)t0 * 1024;
+		sub.words = b.words + r0 * b.stride;
+		sub.n_rec = (uint32_t)std::min<uint64_t>((uint64_t)chunk_tiles * 1024, b.n_rec - r0);
+		sub.n_words = (uint64_t)sub.n_rec * b.stride;
+		int rc = run_pipeline_chunk(c, sub, ki, sh);
+		if (rc)
+			return rc;
+	}
+	return NTC_OK;
+}
+
+int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh)
+{
 	int rc;
 	const uint32_t n_tiles = (b.n_rec + 1023) / 1024;
 	if ((rc = grow(&c->d_masks, &c->cap_masks, (size_t)n_tiles * sh.npos_max * 32, false)) ||
@@ -333,17 +382,19 @@ int run_pipeline_k(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeS
 	ha.sBits = c->sBits;
 	ha.npos_max = sh.npos_max;
 	ha.rows_per_unit = sh.rows_per_unit;
+	ha.units_per_tile = sh.units_per_tile;
+	ha.tiles_per_unit = sh.tiles_per_unit;
+	ha.n_units = sh.tiles_per_unit > 1 ? (n_tiles + sh.tiles_per_unit - 1) / sh.tiles_per_unit : n_tiles * sh.units_per_tile;
 	ha.masks = c->d_masks;
 	ha.d_tab = c->d_bs_tab;
 	ha.rot_a = c->bs_launch[ki].rot_a;
 	ha.rot_b = c->bs_launch[ki].rot_b;
 	ha.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 	ha.pool = P;
-	const uint64_t n_units = ((uint64_t)n_tiles * sh.npos_max + sh.rows_per_unit - 1) / sh.rows_per_unit;
-	ha.grid = (unsigned)std::min<uint64_t>(c->hit_grid_max, (n_units + ntc::pl::kHitGroups - 1) / ntc::pl::kHitGroups);
+	ha.grid = std::min<unsigned>(c->hit_grid_max, (ha.n_units + ntc::pl::kHitGroups - 1) / ntc::pl::kHitGroups);
 	ha.stream = c->stream;
 	// conditional flush: only when this batch could exhaust the pool while the sketch is not materialised yet
-	CK(ntc::pl::launch_apply(P, c->d_counters, 0, ha.grid * ntc::pl::kHitGroups * P.nbins + 8, c->apply_grid, c->stream));
+	CK(ntc::pl::launch_apply(P, c->d_counters, 0, 3 * P.max_groups * P.nbins + 8, c->apply_grid, c->stream));
 	CK(ntc::pl::launch_hit(ha));
 	CK(ntc::pl::launch_fallback(b.words, b.stride, b.n_rec, n_tiles, c->d_tile_info, c->d_params, ki, ha.ctr_k, P.ctl, c->n_sm, c->stream));
 	c->n_launches += 4;
@@ -549,6 +600,8 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 		}
 	}
 	c->use_pipeline = !(getenv("NTC_PIPELINE") && atoi(getenv("NTC_PIPELINE")) == 0);
+	if (getenv("NTC_CHUNK_WAVES"))
+		c->chunk_waves = (unsigned)atoi(getenv("NTC_CHUNK_WAVES"));
 	if ((rc = pool_create(c)))
 		return fail(rc);
 	for (int i = 0; i < NBUF; i++) {
@@ -596,6 +649,7 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->d_bs_tab) cudaFree(c->d_bs_tab);
 	if (c->pool.entries) cudaFree(c->pool.entries);
 	if (c->pool.slice_blocks) cudaFree(c->pool.slice_blocks);
+	if (c->pool.gstate) cudaFree(c->pool.gstate);
 	if (c->d_pool_ctl_region) cudaFree(c->d_pool_ctl_region);
 	if (c->d_masks) cudaFree(c->d_masks);
 	if (c->d_tile_info) cudaFree(c->d_tile_info);
@@ -616,6 +670,9 @@ int ntc_reset(ntc_ctx* c)
 	// applies the slice's increments (apply_kernel, state 0), which saves one full pass over the 1 GiB/k sketch.
 	CK(cudaMemsetAsync(c->d_pool_ctl_region, 0, c->pool_ctl_bytes, c->stream)); // empty log, state = not materialised
 	CK(cudaMemsetAsync(c->d_f1, 0, NTC_MAX_K * sizeof(unsigned long long), c->stream));
+	c->pool.epoch = (c->pool.epoch + 1) & 0xFFFFu; // outdates the hit groups' saved blocks
+	if (c->pool.epoch == 0)
+		c->pool.epoch = 1;
 	c->totals_overridden = false;
 	c->pending = true;
 	return NTC_OK;

@@ -21,11 +21,12 @@ struct DevParams;
 namespace pl {
 
 constexpr uint32_t kBlkEntries = 256;         // log entries per pool block (1 KB)
+constexpr uint32_t kBlkSlack = 96;            // a block with fewer free entries than this is closed at the end of a round
 constexpr uint32_t kVoid = 0xFFFFFFFFu;
 constexpr uint32_t kTileFlag = 0xFFFFFFFFu;   // tile_info value: not uniform -> fallback kernel
 constexpr uint32_t kTileRecs = 1024;
 constexpr uint32_t kMaxBins = 64;             // slices per k
-constexpr uint32_t kQueueCap = 2048;          // candidates per round of a hit group
+constexpr uint32_t kQueueCap = 4096;          // candidates per round of a hit group
 constexpr uint32_t kGroupThreads = 256, kHitGroups = 2, kHitThreads = kGroupThreads * kHitGroups;
 constexpr uint32_t kApplyThreads = 512;
 
@@ -41,6 +42,10 @@ struct Pool {                    // device pointers + geometry, passed by value
 	uint32_t* ctl;               // [CTL_WORDS]
 	unsigned long long* cand;    // candidate k-mers of the batch being processed (upper bound of its log entries)
 	uint32_t n_blocks, slice_cap, n_slices, nbins, bin_shift, rBits, nK;
+	uint32_t* gstate;            // [nK][max_groups][1 + 5 * nbins]: open / spare blocks of every hit group, kept over launches
+	uint32_t max_groups, epoch;  // epoch: bumped by ntc_reset (host); with CTL_FLUSHES it dates gstate
+	uint32_t ahead;              // apply kernel: slices the stagers may run ahead of the appliers (L2 footprint)
+	uint32_t dbg;                // timing experiments (NTC_PL_DEBUG): wrong results when non-zero
 };
 
 struct ScanLaunch {              // per-k constants of the scan kernel, passed by value
@@ -66,7 +71,8 @@ struct ScanArgs {
 struct HitArgs {
 	const uint32_t* words;
 	uint32_t stride, n_rec, n_tiles;
-	uint32_t k, ki, sBits, npos_max, rows_per_unit;
+	uint32_t k, ki, sBits, npos_max;
+	uint32_t rows_per_unit, units_per_tile, tiles_per_unit, n_units; // units_per_tile > 1 xor tiles_per_unit > 1 (or both 1)
 	const uint32_t* masks;
 	const uint4* d_tab;          // [8][256] byte tables of the full hash
 	uint64_t rot_a, rot_b;
