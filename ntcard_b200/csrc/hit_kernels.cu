@@ -20,6 +20,8 @@ namespace pl {
 
 namespace {
 
+constexpr size_t kTabBytes = 8 * 256 * 16;
+
 // ------------------------------------------------------------------------------------------------
 // full 64-bit canonical hash of one k-mer from the packed bases
 // ------------------------------------------------------------------------------------------------
@@ -46,13 +48,19 @@ struct HitLoad { // the packed words of a candidate's first 32-base block, in fl
 
 // rec_words: the base words of the record (word 0 = length skipped); p: k-mer start; last: index of the last base word
 // that may be read (the record's slot in the uniform-stride batch)
+template <bool kStaged> __device__ __forceinline__ uint32_t ld_word(const uint32_t* p)
+{
+	return kStaged ? *p : __ldg(p); // staged: the tile's packed reads sit in shared memory
+}
+
+template <bool kStaged>
 __device__ __forceinline__ HitLoad hit_issue(const HashCtx& c, const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
 {
 	HitLoad h;
 	const uint32_t wi = (p + (c.k & 31u)) >> 4;
-	h.x0 = __ldg(rec_words + min(wi, last));
-	h.x1 = __ldg(rec_words + min(wi + 1, last));
-	h.x2 = __ldg(rec_words + min(wi + 2, last));
+	h.x0 = ld_word<kStaged>(rec_words + min(wi, last));
+	h.x1 = ld_word<kStaged>(rec_words + min(wi + 1, last));
+	h.x2 = ld_word<kStaged>(rec_words + min(wi + 2, last));
 	return h;
 }
 
@@ -78,6 +86,7 @@ __device__ __forceinline__ void block_tables(const uint4* __restrict__ tab, uint
 // (NTF64/NTR64 base forms, nthash.hpp:220-239), then M blocks of 32 bases:
 //   fh = srol^32(fh) ^ FB_m        rh ^= srol^(t+32m) RB_m
 // Returns the counter index inside the k's [2][2^rBits] sub-sketch, or kVoid when ntComp does not sample it.
+template <bool kStaged>
 __device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& h, const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
 {
 	const uint32_t t = c.k & 31u, M = c.k >> 5;
@@ -92,7 +101,7 @@ __device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& 
 	} else {
 		uint64_t fh = 0, rh = 0;
 		for (uint32_t i = 0; i < t; i++) {
-			const uint32_t code = base_at(rec_words, p + i);
+			const uint32_t code = (ld_word<kStaged>(rec_words + ((p + i) >> 4)) >> (((p + i) & 15u) * 2u)) & 3u;
 			fh = srol(fh) ^ seed_of(code);
 			rh ^= srol_n(seed_of(3u - code), i);
 		}
@@ -101,9 +110,9 @@ __device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& 
 			const uint32_t o = p + t + 32u * m, sh = (o & 15u) * 2u;
 			if (m) {
 				const uint32_t wi = o >> 4;
-				x0 = __ldg(rec_words + wi);
-				x1 = __ldg(rec_words + wi + 1);
-				x2 = __ldg(rec_words + min(wi + 2, last));
+				x0 = ld_word<kStaged>(rec_words + wi);
+				x1 = ld_word<kStaged>(rec_words + wi + 1);
+				x2 = ld_word<kStaged>(rec_words + min(wi + 2, last));
 			}
 			uint32_t f0, f1, r0, r1;
 			block_tables(c.tab, __funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), f0, f1, r0, r1);
@@ -137,16 +146,32 @@ __device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& 
 // The rare hit that finds its block full waits in an overflow list for the end of the round, when thread b tops
 // bin b up: a block with less than kBlkSlack free entries is closed and the spare block -- requested one round
 // earlier, so its allocation latency is never waited for -- takes its place.
+// shared memory of a group: [queue qcap][cur, fill, curpos: kMaxBins each][qn, ovf, n_ovf, pad][mbarrier 16 B]
+// [staged tile: 1024 records x stride words (staged kernel only)]
 struct GroupSmem {
-	uint32_t queue[kQueueCap];
-	uint32_t ovf_list[kQueueCap];
-	uint32_t cur[kMaxBins], fill[kMaxBins], curpos[kMaxBins]; // open block of every bin (persists over rounds)
-	uint32_t qn, ovf, n_ovf;
+	uint32_t* queue;
+	uint32_t *cur, *fill, *curpos; // open block of every bin (persists over rounds)
+	uint32_t* scal;                // [0] qn, [1] ovf, [2] n_ovf
+	uint64_t* mbar;
+	uint32_t* tile;
 };
-struct HitSmem {
-	uint4 tab[8 * 256];
-	GroupSmem g[kHitGroups];
-};
+constexpr uint32_t kStagedQueueCap = 3072; // one tile: 1024 x ~119..145 positions / 64 = 1900..2320 candidates at s = 7
+__host__ __device__ constexpr size_t group_smem_fixed(uint32_t qcap) { return ((size_t)qcap + 3 * kMaxBins + 4) * 4 + 16; }
+
+__device__ __forceinline__ GroupSmem group_smem(unsigned char* base, uint32_t qcap)
+{
+	GroupSmem g;
+	g.queue = reinterpret_cast<uint32_t*>(base);
+	g.cur = g.queue + qcap;
+	g.fill = g.cur + kMaxBins;
+	g.curpos = g.fill + kMaxBins;
+	g.scal = g.curpos + kMaxBins;
+	g.mbar = reinterpret_cast<uint64_t*>(g.scal + 4);
+	g.tile = reinterpret_cast<uint32_t*>(g.mbar + 2);
+	return g;
+}
+
+constexpr uint32_t kPendingBit = 0x80000000u; // queue entry after its round: idx | kPendingBit = still to be appended
 
 constexpr int kHitBatch = 4; // candidates per thread whose loads are in flight together
 
@@ -168,7 +193,8 @@ struct Spare {           // thread b's spare block for bin b, in registers
 };
 
 // queue entry: slot (5 bits) | lane (5) << 5 | mask row inside the unit << 10
-__device__ __forceinline__ void decode(const HitArgs& a, const Unit& U, uint32_t e, uint32_t& rec, uint32_t& p)
+// rl: the record's index inside its tile
+__device__ __forceinline__ void decode(const HitArgs& a, const Unit& U, uint32_t e, uint32_t& rec, uint32_t& rl, uint32_t& p)
 {
 	const uint32_t s = e & 31u, ln = (e >> 5) & 31u, r = e >> 10;
 	uint32_t tile = U.tile0;
@@ -178,11 +204,12 @@ __device__ __forceinline__ void decode(const HitArgs& a, const Unit& U, uint32_t
 		tile += t;
 		p = r - t * a.npos_max;
 	}
-	rec = tile * kTileRecs + s * 32u + ln;
+	rl = s * 32u + ln;
+	rec = tile * kTileRecs + rl;
 }
 
-// one log entry: slot in the bin's open block, or the overflow list when the block is full / absent
-__device__ __forceinline__ void append(GroupSmem& sm, const HitArgs& a, uint32_t idx, bool retry)
+// one log entry: a slot in the bin's open block; false when the block is full (the entry is retried after the top-up)
+__device__ __forceinline__ bool append(const GroupSmem& sm, const HitArgs& a, uint32_t idx)
 {
 	const Pool& P = a.pool;
 	const uint32_t b = idx >> P.bin_shift;
@@ -190,20 +217,19 @@ __device__ __forceinline__ void append(GroupSmem& sm, const HitArgs& a, uint32_t
 	if (cu == kVoid) { // the pool ran out: the sketch is materialised whenever that can happen (pipeline.h) -> RED
 		atomicAdd(a.ctr_k + idx, 1u);
 		P.ctl[CTL_DIRECT] = 1u; // statistics only
-		return;
+		return true;
 	}
 	const uint32_t slot = atomicAdd(&sm.fill[b], 1u);
 	if (slot < kBlkEntries) {
 		if (!(P.dbg & 16u))
 			P.entries[(size_t)cu * kBlkEntries + slot] = idx;
-	} else {
-		sm.ovf_list[atomicAdd(&sm.n_ovf, 1u)] = idx;
+		return true;
 	}
-	(void)retry;
+	return false;
 }
 
 // end of a round: thread b closes bin b's block if it is (nearly) full and opens the spare
-__device__ __forceinline__ void top_up(GroupSmem& sm, const HitArgs& a, uint32_t b, Spare& sp)
+__device__ __forceinline__ void top_up(const GroupSmem& sm, const HitArgs& a, uint32_t b, Spare& sp)
 {
 	const Pool& P = a.pool;
 	const uint32_t slice = a.ki * P.nbins + b;
@@ -234,7 +260,8 @@ __device__ __forceinline__ void top_up(GroupSmem& sm, const HitArgs& a, uint32_t
 	sp.have = true;
 }
 
-__device__ __forceinline__ void process_queue(GroupSmem& sm, const HitArgs& a, const HashCtx& c, uint32_t n, const Unit& U, uint32_t g,
+template <bool kStaged>
+__device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs& a, const HashCtx& c, uint32_t n, const Unit& U, uint32_t g,
     uint32_t gtid, Spare& sp)
 {
 	const Pool& P = a.pool;
@@ -246,47 +273,58 @@ __device__ __forceinline__ void process_queue(GroupSmem& sm, const HitArgs& a, c
 		for (int u = 0; u < kHitBatch; u++) {
 			const uint32_t i = base + u * kGroupThreads + gtid;
 			if (i < n) {
-				uint32_t rec, p;
-				decode(a, U, sm.queue[i], rec, p);
+				uint32_t rec, rl, p;
+				decode(a, U, sm.queue[i], rec, rl, p);
+				const uint32_t* rw = kStaged ? sm.tile + rl * c.stride + 1 : c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1;
 				if (!(P.dbg & 32u))
-					h[u] = hit_issue(c, c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1, p, last);
+					h[u] = hit_issue<kStaged>(c, rw, p, last);
 			}
 		}
 #pragma unroll
 		for (int u = 0; u < kHitBatch; u++) {
 			const uint32_t i = base + u * kGroupThreads + gtid;
 			if (i < n) {
-				uint32_t rec, p;
-				decode(a, U, sm.queue[i], rec, p);
-				uint32_t idx = rec < a.n_rec ? hit_finish(c, h[u], c.words + (uint64_t)rec * c.stride + 1, p, last) : kVoid;
+				uint32_t rec, rl, p;
+				decode(a, U, sm.queue[i], rec, rl, p);
+				const uint32_t* rw = kStaged ? sm.tile + rl * c.stride + 1 : c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1;
+				uint32_t idx = rec < a.n_rec ? hit_finish<kStaged>(c, h[u], rw, p, last) : kVoid;
 				if (P.dbg & 32u)
 					idx = (rec * 2654435761u + p * 40503u) & ((2u << P.rBits) - 1u);
-				if (idx != kVoid)
-					append(sm, a, idx, false);
+				uint32_t after = 0;
+				if (idx != kVoid && !append(sm, a, idx)) {
+					after = idx | kPendingBit;
+					atomicAdd(&sm.scal[2], 1u);
+				}
+				sm.queue[i] = after;
 			}
 		}
 	}
 	group_sync(g);
 	// ---- top up the bins; place what overflowed (rare) ------------------------------------------------------------
 	for (;;) {
-		const uint32_t n_ovf = sm.n_ovf;
+		const uint32_t n_ovf = sm.scal[2];
 		if (gtid < P.nbins)
 			top_up(sm, a, gtid, sp);
 		if (n_ovf == 0)
 			break;
 		group_sync(g);
-		for (uint32_t i = gtid; i < n_ovf; i += kGroupThreads)
-			sm.queue[i] = sm.ovf_list[i];
 		if (gtid == 0)
-			sm.n_ovf = 0;
+			sm.scal[2] = 0;
 		group_sync(g);
-		for (uint32_t i = gtid; i < n_ovf; i += kGroupThreads)
-			append(sm, a, sm.queue[i], true);
+		for (uint32_t i = gtid; i < n; i += kGroupThreads) {
+			const uint32_t e = sm.queue[i];
+			if (e & kPendingBit) {
+				if (append(sm, a, e & ~kPendingBit))
+					sm.queue[i] = 0;
+				else
+					atomicAdd(&sm.scal[2], 1u);
+			}
+		}
 		group_sync(g);
 	}
 }
 
-__device__ __forceinline__ void emit_bits(GroupSmem& sm, uint32_t x, uint32_t w, uint32_t& at)
+__device__ __forceinline__ void emit_bits(const GroupSmem& sm, uint32_t x, uint32_t w, uint32_t& at)
 {
 	while (x) {
 		const uint32_t s = __ffs(x) - 1;
@@ -295,16 +333,25 @@ __device__ __forceinline__ void emit_bits(GroupSmem& sm, uint32_t x, uint32_t w,
 	}
 }
 
-__global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// kStaged: a unit is one whole tile whose packed reads (1024 x stride words, <= 48 KB) are copied to shared memory by
+// one bulk-async (TMA) request while the group enumerates the tile's mask words; the candidates' bases are then
+// gathered from shared memory instead of with three uncoalesced global loads each (the L1 tag stage is the limit
+// there: 32 different lines per warp instruction).
+template <bool kStaged, int kGroups>
+__global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_kernel(const HitArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	HitSmem& S = *reinterpret_cast<HitSmem*>(smem_raw);
+	uint4* tab = reinterpret_cast<uint4*>(smem_raw);
 	const uint32_t tid = threadIdx.x, g = tid / kGroupThreads, gtid = tid % kGroupThreads;
-	GroupSmem& sm = S.g[g];
-	for (uint32_t i = tid; i < 8 * 256; i += kHitThreads)
-		S.tab[i] = a.d_tab[i];
+	constexpr uint32_t kQCap = kStaged ? kStagedQueueCap : kQueueCap;
+	const size_t group_bytes = group_smem_fixed(kQCap) + (kStaged ? (size_t)kTileRecs * a.stride * 4 : 0);
+	const GroupSmem sm = group_smem(smem_raw + kTabBytes + g * group_bytes, kQCap);
+	for (uint32_t i = tid; i < 8 * 256; i += kGroups * kGroupThreads)
+		tab[i] = a.d_tab[i];
 	// open / spare blocks of this group: carried over from the previous launch unless a flush or a reset came between
-	const uint32_t group_id = blockIdx.x * kHitGroups + g;
+	const uint32_t group_id = blockIdx.x * kGroups + g;
 	const uint32_t nb = a.pool.nbins;
 	uint32_t* gs = a.pool.gstate + ((size_t)a.ki * a.pool.max_groups + group_id) * (1 + 5 * (size_t)nb);
 	const uint32_t gen = (a.pool.epoch << 16) | (a.pool.ctl[CTL_FLUSHES] & 0xFFFFu);
@@ -325,8 +372,13 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 			sp.have = true;
 		}
 	}
-	if (gtid == 0)
-		sm.n_ovf = 0;
+	if (gtid == 0) {
+		sm.scal[2] = 0;
+		if (kStaged) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(sm.mbar)), "r"(1u) : "memory");
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+	}
 	__syncthreads();
 	if (gtid < nb && active && !resume)
 		top_up(sm, a, gtid, sp); // open a first block for every bin
@@ -336,17 +388,20 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 	c.k = a.k;
 	c.rBits = a.pool.rBits;
 	c.sBits = a.sBits;
-	c.tab = S.tab;
+	c.tab = tab;
 	c.rot_a = a.rot_a;
 	c.rot_b = a.rot_b;
 	constexpr int kW = 8; // mask words per thread in flight
-	for (uint32_t unit = blockIdx.x * kHitGroups + g; unit < a.n_units; unit += gridDim.x * kHitGroups) {
+	uint32_t phase = 0;
+	for (uint32_t unit = blockIdx.x * kGroups + g; unit < a.n_units; unit += gridDim.x * kGroups) {
 		Unit U;
 		U.multi = a.tiles_per_unit > 1;
 		if (!U.multi) {
 			U.tile0 = unit / a.units_per_tile;
 			U.r0 = (unit - U.tile0 * a.units_per_tile) * a.rows_per_unit;
-			U.nrows = min(a.rows_per_unit, a.npos_max - U.r0);
+			const uint32_t info = __ldg(a.tile_info + U.tile0);          // rows past the tile's k-mer positions are all zero
+			const uint32_t npos = info == kTileFlag ? 0u : min(info, a.npos_max);
+			U.nrows = npos > U.r0 ? min(a.rows_per_unit, npos - U.r0) : 0u;
 		} else {
 			U.tile0 = unit * a.tiles_per_unit;
 			U.r0 = 0;
@@ -355,8 +410,18 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 		const uint32_t nw = U.nrows * 32u;
 		const uint32_t* m = a.masks + ((size_t)U.tile0 * a.npos_max + U.r0) * 32u;
 		if (gtid == 0) {
-			sm.qn = 0;
-			sm.ovf = 0;
+			sm.scal[0] = 0;
+			sm.scal[1] = 0;
+			if (kStaged) {
+				// everybody finished reading the previous tile (group_sync at the end of the last round): fetch this one
+				const uint32_t nrec = min(kTileRecs, a.n_rec - U.tile0 * kTileRecs);
+				const uint32_t bytes = nrec * a.stride * 4u;
+				const uint32_t* src = a.words + (size_t)U.tile0 * kTileRecs * a.stride;
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(sm.mbar)), "r"(bytes) : "memory");
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(sm.tile)),
+				             "l"(src), "r"(bytes), "r"(smem_addr(sm.mbar))
+				             : "memory");
+			}
 		}
 		group_sync(g);
 		for (uint32_t w0 = 0; w0 < nw; w0 += kGroupThreads * kW) {
@@ -371,40 +436,50 @@ __global__ void __launch_bounds__(kHitThreads, 2) hit_kernel(const HitArgs a)
 			for (int u = 0; u < kW; u++)
 				cnt += __popc(x[u]);
 			if (cnt) {
-				uint32_t at = atomicAdd(&sm.qn, cnt);
-				if (at + cnt <= kQueueCap) {
+				uint32_t at = atomicAdd(&sm.scal[0], cnt);
+				if (at + cnt <= kQCap) {
 #pragma unroll
 					for (int u = 0; u < kW; u++)
 						emit_bits(sm, x[u], w0 + u * kGroupThreads + gtid, at);
 				} else {
-					sm.ovf = 1;
+					sm.scal[1] = 1;
 				}
 			}
 		}
 		group_sync(g);
-		if (!sm.ovf) {
-			const uint32_t n = sm.qn;
+		if (kStaged) { // the tile has landed?
+			uint32_t done = 0;
+			while (!done)
+				asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+				             : "=r"(done)
+				             : "r"(smem_addr(sm.mbar)), "r"(phase)
+				             : "memory");
+			phase ^= 1u;
+		}
+		if (!sm.scal[1]) {
+			const uint32_t n = sm.scal[0];
 			if (n && !(a.pool.dbg & 64u))
-				process_queue(sm, a, c, n, U, g, gtid, sp);
+				process_queue<kStaged>(sm, a, c, n, U, g, gtid, sp);
 		} else {
-			// skewed data: more candidates than the queue holds -> four mask rows (<= 4096 candidates) per round
-			for (uint32_t w0 = 0; w0 < nw; w0 += 128) {
+			// skewed data: more candidates than the queue holds -> two mask rows (<= 2048 candidates) per round
+			for (uint32_t w0 = 0; w0 < nw; w0 += 64) {
 				group_sync(g);
 				if (gtid == 0)
-					sm.qn = 0;
+					sm.scal[0] = 0;
 				group_sync(g);
 				const uint32_t w = w0 + gtid;
-				const uint32_t x = (gtid < 128 && w < nw) ? __ldg(m + w) : 0u;
+				const uint32_t x = (gtid < 64 && w < nw) ? __ldg(m + w) : 0u;
 				if (x) {
-					uint32_t at = atomicAdd(&sm.qn, (uint32_t)__popc(x));
+					uint32_t at = atomicAdd(&sm.scal[0], (uint32_t)__popc(x));
 					emit_bits(sm, x, w, at);
 				}
 				group_sync(g);
-				const uint32_t n = sm.qn;
+				const uint32_t n = sm.scal[0];
 				if (n)
-					process_queue(sm, a, c, n, U, g, gtid, sp);
+					process_queue<kStaged>(sm, a, c, n, U, g, gtid, sp);
 			}
 		}
+		group_sync(g); // the staged tile and the queue are free again
 	}
 	// keep the open and spare blocks for the next launch; the spare is registered as an empty block
 	if (active) {
@@ -603,18 +678,37 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 
 } // namespace
 
-size_t hit_smem_bytes() { return sizeof(HitSmem); }
+constexpr int kStagedGroups = 3, kPlainGroups = 2;
 
-cudaError_t launch_hit(const HitArgs& a)
+static size_t hit_smem(bool staged, uint32_t stride)
 {
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(hit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HitSmem));
-		if (e != cudaSuccess)
+	const size_t per_group = group_smem_fixed(staged ? kStagedQueueCap : kQueueCap) + (staged ? (size_t)kTileRecs * stride * 4 : 0);
+	return kTabBytes + (staged ? kStagedGroups : kPlainGroups) * per_group;
+}
+
+// staged: one unit = one whole tile and three groups with their tiles fit the 227 KB of an SM
+bool hit_can_stage(uint32_t stride, uint32_t units_per_tile, uint32_t tiles_per_unit)
+{
+	return units_per_tile == 1 && tiles_per_unit == 1 && hit_smem(true, stride) <= 232448;
+}
+
+unsigned hit_groups_per_sm(bool staged) { return staged ? kStagedGroups : 2 * kPlainGroups; }
+
+cudaError_t launch_hit(const HitArgs& a, bool staged, unsigned ctas)
+{
+	const size_t smem = hit_smem(staged, a.stride);
+	cudaError_t e;
+	if (staged) {
+		auto kern = hit_kernel<true, kStagedGroups>;
+		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
 			return e;
-		attr_set = true;
+		kern<<<ctas, kStagedGroups * kGroupThreads, smem, a.stream>>>(a);
+	} else {
+		auto kern = hit_kernel<false, kPlainGroups>;
+		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+			return e;
+		kern<<<ctas, kPlainGroups * kGroupThreads, smem, a.stream>>>(a);
 	}
-	hit_kernel<<<a.grid, kHitThreads, sizeof(HitSmem), a.stream>>>(a);
 	return cudaGetLastError();
 }
 

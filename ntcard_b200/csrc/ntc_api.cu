@@ -85,7 +85,7 @@ struct ntc_ctx {
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
 	unsigned apply_grid = 0, hit_grid_max = 0;
-	unsigned chunk_waves = 1; // scan waves per pipeline chunk (0 = whole batch)
+	unsigned chunk_waves = 0; // scan waves per pipeline chunk (0 = whole batch; chunking measured slower, kept for experiments)
 	uint64_t n_flush_launches = 0;
 	// finish buffers
 	uint16_t* d_narrow = nullptr;
@@ -233,7 +233,7 @@ int pool_create(ntc_ctx* c)
 	P.cand = reinterpret_cast<unsigned long long*>(P.apply_done + P.n_slices + ((ntc::pl::CTL_WORDS + 3 * P.n_slices) & 1u));
 	c->apply_grid = (unsigned)ntc::pl::apply_max_grid(c->n_sm);
 	c->hit_grid_max = (unsigned)c->n_sm * 2u;
-	P.max_groups = c->hit_grid_max * ntc::pl::kHitGroups;
+	P.max_groups = (unsigned)c->n_sm * 4u;
 	P.epoch = 1;
 	{
 		const size_t gwords = (size_t)c->nK * P.max_groups * (1 + 5 * (size_t)P.nbins);
@@ -386,16 +386,19 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	ha.tiles_per_unit = sh.tiles_per_unit;
 	ha.n_units = sh.tiles_per_unit > 1 ? (n_tiles + sh.tiles_per_unit - 1) / sh.tiles_per_unit : n_tiles * sh.units_per_tile;
 	ha.masks = c->d_masks;
+	ha.tile_info = c->d_tile_info;
 	ha.d_tab = c->d_bs_tab;
 	ha.rot_a = c->bs_launch[ki].rot_a;
 	ha.rot_b = c->bs_launch[ki].rot_b;
 	ha.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 	ha.pool = P;
-	ha.grid = std::min<unsigned>(c->hit_grid_max, (ha.n_units + ntc::pl::kHitGroups - 1) / ntc::pl::kHitGroups);
 	ha.stream = c->stream;
+	const bool staged = ntc::pl::hit_can_stage(b.stride, sh.units_per_tile, sh.tiles_per_unit) && !(getenv("NTC_NO_STAGE"));
+	const unsigned gpc = staged ? 3u : 2u; // groups per CTA
+	const unsigned hit_ctas = std::min<unsigned>((unsigned)c->n_sm * (staged ? 1u : 2u), (ha.n_units + gpc - 1) / gpc);
 	// conditional flush: only when this batch could exhaust the pool while the sketch is not materialised yet
 	CK(ntc::pl::launch_apply(P, c->d_counters, 0, 3 * P.max_groups * P.nbins + 8, c->apply_grid, c->stream));
-	CK(ntc::pl::launch_hit(ha));
+	CK(ntc::pl::launch_hit(ha, staged, hit_ctas));
 	CK(ntc::pl::launch_fallback(b.words, b.stride, b.n_rec, n_tiles, c->d_tile_info, c->d_params, ki, ha.ctr_k, P.ctl, c->n_sm, c->stream));
 	c->n_launches += 4;
 	c->pending = true;

@@ -27,7 +27,7 @@ constexpr uint32_t kTileFlag = 0xFFFFFFFFu;   // tile_info value: not uniform ->
 constexpr uint32_t kTileRecs = 1024;
 constexpr uint32_t kMaxBins = 64;             // slices per k
 constexpr uint32_t kQueueCap = 4096;          // candidates per round of a hit group
-constexpr uint32_t kGroupThreads = 256, kHitGroups = 2, kHitThreads = kGroupThreads * kHitGroups;
+constexpr uint32_t kGroupThreads = 256;
 constexpr uint32_t kApplyThreads = 512;
 
 // control words (device)
@@ -74,18 +74,19 @@ struct HitArgs {
 	uint32_t k, ki, sBits, npos_max;
 	uint32_t rows_per_unit, units_per_tile, tiles_per_unit, n_units; // units_per_tile > 1 xor tiles_per_unit > 1 (or both 1)
 	const uint32_t* masks;
+	const uint32_t* tile_info;   // k-mer positions per record of every tile (0 / kTileFlag: no rows to read)
 	const uint4* d_tab;          // [8][256] byte tables of the full hash
 	uint64_t rot_a, rot_b;
 	uint32_t* ctr_k;             // counters of this k
 	Pool pool;
-	unsigned grid;
 	cudaStream_t stream;
 };
 
 bool have_scan_kernel(unsigned k, unsigned sBits);
 cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a);
-cudaError_t launch_hit(const HitArgs& a);
-size_t hit_smem_bytes();
+bool hit_can_stage(uint32_t stride, uint32_t units_per_tile, uint32_t tiles_per_unit);
+unsigned hit_groups_per_sm(bool staged);
+cudaError_t launch_hit(const HitArgs& a, bool staged, unsigned ctas);
 cudaError_t launch_fallback(const uint32_t* words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, const uint32_t* tile_info,
     const DevParams* d_params, uint32_t ki, uint32_t* ctr_k, const uint32_t* ctl, int n_sm, cudaStream_t st);
 // force = 0: flush only if the batch about to be hashed could overflow the pool while the sketch is still

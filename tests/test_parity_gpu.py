@@ -288,3 +288,90 @@ def test_hist_range_matches_bincount(oracle):
                 assert np.array_equal(p_full[ki, tb], np.bincount(t[ki, tb], minlength=65536))
         with pytest.raises(nt.NtcError):
             sk.hist_range(ptr, 100, 1000)   # not chunk aligned
+
+
+# ---- the scan -> hit log -> apply pipeline: flush modes, pool exhaustion, mixed kernels ------------
+def _uniform_case(oracle, seed, n, L, kList, rBits, sBits, mode=1, U=None):
+    U = U or max(1, n // 4)
+    a = oracle.gen_reads(seed, 0, n, L, mode, U)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+    stride = nt.stride_words(L)
+    words = nt.gen_packed(seed, 0, n, L, mode, U, stride)
+    return words, stride, want, wf1
+
+
+@pytest.mark.parametrize("rBits", [20, 24])
+def test_pipeline_many_batches_and_flushes(oracle, rBits):
+    """Batches interleaved with explicit flushes: the first flush writes the zeros (state 0), the later ones
+    accumulate into the materialised sketch (L2-prefetch mode); counters read through ntc_counters_device in
+    between must be complete.  rBits = 24 gives several slices per k."""
+    import torch
+    n, L, kList = 8192, 150, [32, 64]
+    words, stride, want, wf1 = _uniform_case(oracle, 41, n, L, kList, rBits, 7)
+    with nt.Sketch(kList, rBits=rBits, sBits=7) as sk:
+        sk.set_kernel(nt.KERNEL_BITSLICE)
+        per = 2048
+        for b in range(0, n, per):
+            sk.submit(words[b * stride:(b + per) * stride], None, per, stride)
+            if b == 0:
+                sk.flush()
+            if b == 2 * per:
+                sk.sync()
+                sk.counters_device()
+        t, f1, _ = sk.finish(counters=True, hist=False)
+        assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+        # a second pass into the same (materialised) sketch doubles every counter
+        for b in range(0, n, per):
+            sk.submit(words[b * stride:(b + per) * stride], None, per, stride)
+        t2, f2, _ = sk.finish(counters=True, hist=False)
+        assert np.array_equal(f2, 2 * wf1)
+        assert np.array_equal(t2.reshape(-1), (want.astype(np.uint32) * 2).astype(np.uint16))
+
+
+def test_pipeline_pool_exhaustion_is_exact(oracle, monkeypatch):
+    """A hit log far too small for the batch (64 blocks): the conditional flush in front of the hit kernel must
+    materialise the sketch and the hits that find no block must be added directly -- same counters."""
+    monkeypatch.setenv("NTC_POOL_BLOCKS", "64")
+    n, L, kList = 20000, 150, [32]
+    words, stride, want, wf1 = _uniform_case(oracle, 43, n, L, kList, 22, 7)
+    with nt.Sketch(kList, rBits=22, sBits=7) as sk:
+        sk.set_kernel(nt.KERNEL_BITSLICE)
+        sk.submit(words[:8192 * stride], None, 8192, stride)
+        sk.submit(words[8192 * stride:], None, n - 8192, stride)
+        t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+
+
+def test_pipeline_mixed_with_roll64_batches(oracle):
+    """Uniform batches (pipeline) and ragged batches (roll64, direct increments) into one sketch, in both
+    orders, with a reset in between: the lazily zeroed sketch must be materialised before the first direct
+    increment and nothing may be lost or doubled."""
+    n, L, kList = 4096, 150, [31, 32]
+    words, stride, want_u, wf1_u = _uniform_case(oracle, 47, n, L, kList, 21, 7)
+    a = oracle.gen_reads(48, 0, 3000, 120, 2, 0)
+    ragged = [bytes(a[i * 120:(i + 1) * 120]) for i in range(3000)]
+    want_r, wf1_r = oracle.sketch_reads(ragged, kList, 21, 7, nthreads=4)
+    want = (want_u.astype(np.uint32) + want_r.astype(np.uint32)).astype(np.uint16)
+    with nt.Sketch(kList, rBits=21, sBits=7) as sk:
+        for order in (0, 1):
+            sk.reset()
+            if order == 0:
+                sk.submit(words, None, n, stride)
+                sk.submit_reads(ragged)
+            else:
+                sk.submit_reads(ragged)
+                sk.submit(words, None, n, stride)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+            assert np.array_equal(f1, wf1_u + wf1_r) and np.array_equal(t.reshape(-1), want)
+
+
+def test_pipeline_general_hit_kernel_long_reads(oracle):
+    """Reads too long for the staged (shared-memory) hit kernel and multi-tile units at s = 11."""
+    for L, sBits, n in ((400, 7, 3072), (300, 11, 5000)):
+        words, stride, want, wf1 = _uniform_case(oracle, 53, n, L, [32, 96], 20, sBits)
+        with nt.Sketch([32, 96], rBits=20, sBits=sBits) as sk:
+            sk.set_kernel(nt.KERNEL_BITSLICE)
+            sk.submit(words, None, n, stride)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+        assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
