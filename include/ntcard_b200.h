@@ -107,7 +107,35 @@ int ntc_flush(ntc_ctx* ctx);
  * ntc_finish) and the per-k totals (F1). */
 int ntc_counters_device(ntc_ctx* ctx, void** d_counters, size_t* n_counters);
 int ntc_totals(ntc_ctx* ctx, uint64_t* totKmer /* [nK] */); /* syncs */
+int ntc_totals_nosync(ntc_ctx* ctx, uint64_t* totKmer);     /* the same, waiting for the stream but not flushing the hit log */
 int ntc_set_totals(ntc_ctx* ctx, const uint64_t* totKmer);  /* after an all-reduce of F1 */
+
+/* ---- multi-GPU: exchanging the hit log instead of the sketch ------------------------------------------
+ * While nothing has been flushed, everything a rank has sampled sits in its hit log: counter indices in
+ * blocks of 256, one list of blocks per SLICE of the sketch (slice s of n_slices covers counters
+ * [s * counters_per_slice, (s+1) * counters_per_slice) of the flat [nK][2][2^rBits] array).  For inputs whose
+ * hit count is small against the 2^(rBits+1) counters per k (10 M reads: 74 MB of log, 1 GiB of counters)
+ * it is far cheaper to give every rank a subset of the slices, move the log blocks to their owners (one
+ * all-to-all), and let each rank materialise and histogram only its own slices:
+ *   ntc_log_counts   block count of every slice (syncs); *exportable = 0 when part of the log was already
+ *                    flushed or added directly -- use the dense reduction (ntc_counters_device) then
+ *   ntc_log_export   copy the blocks of `slices` (in that order) to d_blocks [sum nblk][260] uint32, a device
+ *                    buffer of the caller: 256 entries, then the number of valid entries, then padding
+ *   ntc_log_import   append blocks received from other ranks: runs[i] = {slice, n_blocks}, consecutive in
+ *                    d_blocks; NTC_ENOMEM when they do not fit (nothing imported)
+ *   ntc_flush_slices zero + apply only the slices with owned[s] != 0; the log of the others is dropped and
+ *                    the context accepts only ntc_hist_slices / ntc_totals / ntc_reset afterwards
+ *   ntc_hist_slices  counter-value histogram (v >= 1) of the owned slices, [nK][2][65536] uint32, to host
+ *                    memory (p_hist, synchronous) and / or to a device buffer of the caller (d_p_hist,
+ *                    asynchronous on the context's stream: ready for an all-reduce on the device)         */
+int ntc_log_info(ntc_ctx* ctx, uint32_t* n_slices, uint64_t* counters_per_slice, uint32_t* entries_per_block);
+/* pool_info (optional) [3]: blocks in use, blocks in the pool, block-list capacity per slice */
+int ntc_log_counts(ntc_ctx* ctx, uint32_t* nblk /* [n_slices] */, int* exportable, uint32_t* pool_info);
+int ntc_log_export(ntc_ctx* ctx, const uint32_t* slices, uint32_t n, void* d_blocks);
+int ntc_log_import(ntc_ctx* ctx, const void* d_blocks, uint32_t n_blocks, const uint32_t* runs, uint32_t n_runs);
+int ntc_flush_slices(ntc_ctx* ctx, const uint8_t* owned /* [n_slices] */);
+int ntc_stream_sync(ntc_ctx* ctx); /* wait for the context's stream WITHOUT flushing (before handing exported buffers to a collective) */
+int ntc_hist_slices(ntc_ctx* ctx, const uint8_t* owned /* [n_slices] */, uint32_t* p_hist, void* d_p_hist);
 
 /* Counter-value histogram (values >= 1 only; entry 0 of every table is left 0) of the range
  * [first, first+n) of the flat counter array, read from the DEVICE pointer d_counters (which points at
@@ -170,6 +198,9 @@ int ntc_stats(ntc_ctx* ctx, uint64_t* n_launches, uint64_t* n_batches);
 /* Milliseconds the sketch kernels of the last ntc_sync()-ed batches took on the
  * device (CUDA events on the context's stream), and how many launches. */
 int ntc_kernel_time(ntc_ctx* ctx, double* ms_total, uint64_t* n_timed);
+/* The same split by pipeline stage, accumulated since the last call (after ntc_sync): ms3[0] scan kernels,
+ * ms3[1] hit (+ fallback) kernels, ms3[2] apply kernels (flushes). */
+int ntc_stage_times(ntc_ctx* ctx, double* ms3);
 int ntc_device_count(void);
 const char* ntc_last_error(void);
 const char* ntc_version(void);

@@ -19,9 +19,10 @@ KERNEL_AUTO, KERNEL_ROLL64, KERNEL_BITSLICE = 0, 1, 2
 # every symbol include/ntcard_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_submit", "ntc_submit_device", "ntc_wait",
-    "ntc_sync", "ntc_flush", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_set_totals", "ntc_finish", "ntc_estimate",
+    "ntc_sync", "ntc_flush", "ntc_log_info", "ntc_log_counts", "ntc_log_export", "ntc_log_import", "ntc_flush_slices",
+    "ntc_hist_slices", "ntc_stream_sync", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_totals_nosync", "ntc_set_totals", "ntc_finish", "ntc_estimate",
     "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
-    "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_device_count",
+    "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_stage_times", "ntc_device_count",
     "ntc_last_error", "ntc_version",
 ]
 
@@ -49,8 +50,16 @@ def _load():
         "ntc_wait": (C.c_int, [vp, C.c_uint64]),
         "ntc_sync": (C.c_int, [vp]),
         "ntc_flush": (C.c_int, [vp]),
+        "ntc_log_info": (C.c_int, [vp, u32p, u64p, u32p]),
+        "ntc_log_counts": (C.c_int, [vp, vp, C.POINTER(C.c_int), vp]),
+        "ntc_stream_sync": (C.c_int, [vp]),
+        "ntc_log_export": (C.c_int, [vp, vp, C.c_uint32, vp]),
+        "ntc_log_import": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32]),
+        "ntc_flush_slices": (C.c_int, [vp, vp]),
+        "ntc_hist_slices": (C.c_int, [vp, vp, vp, vp]),
         "ntc_counters_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "ntc_totals": (C.c_int, [vp, u64p]),
+        "ntc_totals_nosync": (C.c_int, [vp, u64p]),
         "ntc_set_totals": (C.c_int, [vp, u64p]),
         "ntc_finish": (C.c_int, [vp, vp, u64p, vp]),
         "ntc_hist_range": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp]),
@@ -67,6 +76,7 @@ def _load():
         "ntc_stride_words": (C.c_uint32, [C.c_uint32, C.c_int]),
         "ntc_stats": (C.c_int, [vp, u64p, u64p]),
         "ntc_kernel_time": (C.c_int, [vp, dblp, u64p]),
+        "ntc_stage_times": (C.c_int, [vp, dblp]),
         "ntc_device_count": (C.c_int, []),
         "ntc_last_error": (C.c_char_p, []),
         "ntc_version": (C.c_char_p, []),
@@ -248,6 +258,48 @@ class Sketch:
         """Apply the pending sketch increments to the counters in HBM (asynchronous, stream ordered)."""
         _check(lib.ntc_flush(self.h))
 
+    # ---- hit-log exchange (multi-GPU sparse reduction; include/ntcard_b200.h) ----
+    def log_info(self):
+        n, cps, epb = C.c_uint32(), C.c_uint64(), C.c_uint32()
+        _check(lib.ntc_log_info(self.h, C.byref(n), C.byref(cps), C.byref(epb)))
+        return n.value, cps.value, epb.value
+
+    def log_counts(self):
+        """(nblk uint32[n_slices], exportable bool, (blocks used, blocks in pool, list capacity per slice))"""
+        n = self.log_info()[0]
+        nblk = np.zeros(n, dtype=np.uint32)
+        info = np.zeros(3, dtype=np.uint32)
+        ok = C.c_int()
+        _check(lib.ntc_log_counts(self.h, nblk.ctypes.data, C.byref(ok), info.ctypes.data))
+        return nblk, bool(ok.value), tuple(int(x) for x in info)
+
+    def stream_sync(self):
+        _check(lib.ntc_stream_sync(self.h))
+
+    WIRE_BLOCK_WORDS = 260  # a log block on the wire: 256 entries, fill, padding
+
+    def log_export(self, slices, d_blocks):
+        sl = np.ascontiguousarray(slices, dtype=np.uint32)
+        _check(lib.ntc_log_export(self.h, sl.ctypes.data, len(sl), d_blocks))
+
+    def log_import(self, d_blocks, n_blocks, runs):
+        r = np.ascontiguousarray(runs, dtype=np.uint32).reshape(-1, 2)
+        _check(lib.ntc_log_import(self.h, d_blocks, n_blocks, r.ctypes.data, len(r)))
+
+    def flush_slices(self, owned):
+        o = np.ascontiguousarray(owned, dtype=np.uint8)
+        _check(lib.ntc_flush_slices(self.h, o.ctypes.data))
+
+    def hist_slices(self, owned, d_out=None):
+        """Histogram (v >= 1) of the owned slices: to a device buffer (d_out: pointer, asynchronous) or as numpy."""
+        o = np.ascontiguousarray(owned, dtype=np.uint8)
+        if d_out is not None:
+            _check(lib.ntc_hist_slices(self.h, o.ctypes.data, None, d_out))
+            return None
+        p = np.zeros((self.nK, 2, 65536), dtype=np.uint32)
+        _check(lib.ntc_hist_slices(self.h, o.ctypes.data, p.ctypes.data, None))
+        return p
+
     def counters_device(self):
         p, n = C.c_void_p(), C.c_size_t()
         _check(lib.ntc_counters_device(self.h, C.byref(p), C.byref(n)))
@@ -256,6 +308,12 @@ class Sketch:
     def totals(self):
         t = np.zeros(self.nK, dtype=np.uint64)
         _check(lib.ntc_totals(self.h, t.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return t
+
+    def totals_nosync(self):
+        """F1 as counted so far on the device, without flushing (valid after a stream_sync / log_counts)."""
+        t = np.zeros(self.nK, dtype=np.uint64)
+        _check(lib.ntc_totals_nosync(self.h, t.ctypes.data_as(C.POINTER(C.c_uint64))))
         return t
 
     def set_totals(self, tot):
@@ -285,6 +343,12 @@ class Sketch:
         a, b = C.c_uint64(), C.c_uint64()
         _check(lib.ntc_stats(self.h, C.byref(a), C.byref(b)))
         return {"launches": a.value, "batches": b.value}
+
+    def stage_times(self):
+        """(scan_ms, hit_ms, apply_ms) accumulated since the last call; call after sync()."""
+        ms = (C.c_double * 3)()
+        _check(lib.ntc_stage_times(self.h, C.cast(ms, C.POINTER(C.c_double))))
+        return tuple(ms)
 
     def kernel_time(self):
         ms, n = C.c_double(), C.c_uint64()

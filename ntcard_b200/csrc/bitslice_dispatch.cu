@@ -1,6 +1,5 @@
-// bitslice_dispatch.cu -- picks the compiled (k mod 31) variant; builds the hit-path byte tables.
-// BS_KM_LIST is the list of compiled variants, e.g. -DBS_KM_LIST="X(0) X(1) X(2)".
-#include "bitslice_launch.h"
+// bitslice_dispatch.cu -- picks the compiled (k mod 31) variant of the scan kernel; builds the byte tables of the
+// full hash.  BS_KM_LIST is the list of compiled variants, e.g. -DBS_KM_LIST="X(0) X(1) X(2)".
 #include "nthash_device.cuh"
 #include "pipeline.h"
 
@@ -9,13 +8,13 @@
 #endif
 
 namespace ntc {
-namespace bs {
+namespace pl {
 
-#define X(n) cudaError_t launch_km_##n(unsigned sBits, const BsArgs& a);
+#define X(n) cudaError_t launch_scan_km_##n(unsigned sBits, const ScanArgs& a);
 BS_KM_LIST
 #undef X
 
-bool have_kernel(unsigned k, unsigned sBits)
+bool have_scan_kernel(unsigned k, unsigned sBits)
 {
 	if (sBits != 7 && sBits != 11)
 		return false;
@@ -27,16 +26,17 @@ bool have_kernel(unsigned k, unsigned sBits)
 	}
 }
 
-cudaError_t launch(unsigned k, unsigned sBits, const BsArgs& a)
+cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a)
 {
 	switch (k % 31) {
-#define X(n) case n: return launch_km_##n(sBits, a);
+#define X(n) case n: return launch_scan_km_##n(sBits, a);
 		BS_KM_LIST
 #undef X
 	default: return cudaErrorInvalidValue;
 	}
 }
 
+// Per byte position j (4 bases) of a 32-base block: FB = XOR_u srol^(31-i) seed[c_i], RB = XOR_u srol^i seed[3-c_i], i = 4j+u
 void build_tables(uint32_t* tab)
 {
 	for (unsigned j = 0; j < 8; j++)
@@ -53,26 +53,6 @@ void build_tables(uint32_t* tab)
 			e[2] = (uint32_t)rb;
 			e[3] = (uint32_t)(rb >> 32);
 		}
-}
-
-} // namespace bs
-
-namespace pl {
-
-#define X(n) cudaError_t launch_scan_km_##n(unsigned sBits, const ScanArgs& a);
-BS_KM_LIST
-#undef X
-
-bool have_scan_kernel(unsigned k, unsigned sBits) { return bs::have_kernel(k, sBits); }
-
-cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a)
-{
-	switch (k % 31) {
-#define X(n) case n: return launch_scan_km_##n(sBits, a);
-		BS_KM_LIST
-#undef X
-	default: return cudaErrorInvalidValue;
-	}
 }
 
 } // namespace pl

@@ -1,7 +1,6 @@
-// bitslice_inst.cu -- one translation unit per k mod 31 (compiled with -DBS_KM=<0..30>), so the 31
-// unrolled variants build in parallel.  Each instantiates the kernel for sBits = 7 and 11, the two
-// values the reference can reach without its hidden -s flag (ntcard.cpp:58, 430-431).
-#include "bitslice_kernel.cuh"
+// bitslice_inst.cu -- one translation unit per k mod 31 (compiled with -DBS_KM=<0..30>), so the unrolled variants
+// of the scan kernel build in parallel.  Each instantiates the kernel for sBits = 7 and 11, the two values the
+// reference can reach without its hidden -s flag (ntcard.cpp:58, 430-431).
 #include "scan_kernel.cuh"
 
 #ifndef BS_KM
@@ -12,19 +11,6 @@
 #define BS_CAT(a, b) BS_CAT2(a, b)
 
 namespace ntc {
-namespace bs {
-
-cudaError_t BS_CAT(launch_km_, BS_KM)(unsigned sBits, const BsArgs& a)
-{
-	if (sBits == 7)
-		return launch_one<BS_KM, 7>(a);
-	if (sBits == 11)
-		return launch_one<BS_KM, 11>(a);
-	return cudaErrorInvalidValue;
-}
-
-} // namespace bs
-
 namespace pl {
 
 cudaError_t BS_CAT(launch_scan_km_, BS_KM)(unsigned sBits, const ScanArgs& a)

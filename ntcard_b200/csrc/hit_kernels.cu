@@ -553,9 +553,12 @@ __device__ __forceinline__ void role_sync(uint32_t role)
 // In steady state the stagers stream the sketch at HBM write speed while the appliers' atomics hit L2.
 
 
-__global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint32_t* __restrict__ counters, int force, uint32_t reserve_blocks)
+// order / n_order: the slices to flush, in pipeline order (nullptr = all n_slices); the log of every other slice is dropped
+__global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint32_t* __restrict__ counters, int force, uint32_t reserve_blocks,
+    const uint32_t* __restrict__ order, uint32_t n_order)
 {
 	const uint32_t kApplyAhead = P.ahead;
+	const uint32_t NS = order ? n_order : P.n_slices;
 	// ---- decide (every CTA reads the same values: they were written by earlier kernels) ----
 	const uint32_t next = P.ctl[CTL_NEXT];
 	const uint32_t used = min(next, P.n_blocks);
@@ -579,10 +582,11 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 		// ================= stagers =================
 		const size_t n16 = slice_len / 4; // 16-byte units per slice
 		const size_t a0 = n16 * blockIdx.x / gridDim.x, a1 = n16 * (blockIdx.x + 1) / gridDim.x;
-		for (uint32_t s = 0; s < P.n_slices; s++) {
-			if (s >= kApplyAhead && !(P.dbg & 4u)) { // L2 footprint: do not run more than kApplyAhead slices ahead of the appliers
+		for (uint32_t si = 0; si < NS; si++) {
+			const uint32_t s = order ? order[si] : si;
+			if (si >= kApplyAhead && !(P.dbg & 4u)) { // L2 footprint: do not run more than kApplyAhead slices ahead of the appliers
 				if (rtid == 0)
-					while (ld_acquire(P.apply_done + s - kApplyAhead) < gridDim.x)
+					while (ld_acquire(P.apply_done + si - kApplyAhead) < gridDim.x)
 						__nanosleep(20);
 				role_sync(role);
 			}
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 				role_sync(role);
 				if (rtid == 0) {
 					__threadfence();
-					atomicAdd(P.zero_done + s, 1u);
+					atomicAdd(P.zero_done + si, 1u);
 				}
 			} else if (min(P.slice_nblk[s], P.slice_cap) >= sparse_below) {
 				for (size_t i = a0 + (size_t)rtid * 256; i < a1; i += (size_t)nrt * 256) { // 4 KB per request
@@ -621,16 +625,20 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 				v[u] = lane + 32u * u < f ? __ldcs(e + lane + 32u * u) : kVoid;
 		};
 		uint32_t v[kV], vn[kV];
-		uint32_t nb = min(P.slice_nblk[0], P.slice_cap);
-		load_block(0, j0, nb, v);
-		for (uint32_t s = 0; s < P.n_slices; s++) {
-			const uint32_t nbn = s + 1 < P.n_slices ? min(P.slice_nblk[s + 1], P.slice_cap) : 0u;
-			if (s + 1 < P.n_slices)
-				load_block(s + 1, j0, nbn, vn);
+		auto slice_at = [&](uint32_t si) { return order ? order[si] : si; };
+		uint32_t nb = NS ? min(P.slice_nblk[slice_at(0)], P.slice_cap) : 0u;
+		if (NS)
+			load_block(slice_at(0), j0, nb, v);
+		for (uint32_t si = 0; si < NS; si++) {
+			const uint32_t s = slice_at(si);
+			const uint32_t sn = si + 1 < NS ? slice_at(si + 1) : 0u;
+			const uint32_t nbn = si + 1 < NS ? min(P.slice_nblk[sn], P.slice_cap) : 0u;
+			if (si + 1 < NS)
+				load_block(sn, j0, nbn, vn);
 			if (nb) {
 				if (zero_mode && !(P.dbg & 2u)) {
 					if (rtid == 0)
-						while (ld_acquire(P.zero_done + s) < gridDim.x)
+						while (ld_acquire(P.zero_done + si) < gridDim.x)
 							__nanosleep(20);
 					role_sync(role);
 				}
@@ -649,7 +657,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 			}
 			role_sync(role);
 			if (rtid == 0)
-				atomicAdd(P.apply_done + s, 1u);
+				atomicAdd(P.apply_done + si, 1u);
 #pragma unroll
 			for (int u = 0; u < kV; u++)
 				v[u] = vn[u];
@@ -728,9 +736,141 @@ int apply_max_grid(int n_sm)
 	return n_sm * (occ > 2 ? 2 : occ);
 }
 
-cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32_t reserve_blocks, unsigned grid, cudaStream_t st)
+cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32_t reserve_blocks, unsigned grid, cudaStream_t st,
+    const uint32_t* d_order, uint32_t n_order)
 {
-	apply_kernel<<<grid, kApplyThreads, 0, st>>>(pool, counters, force, reserve_blocks);
+	apply_kernel<<<grid, kApplyThreads, 0, st>>>(pool, counters, force, reserve_blocks, d_order, n_order);
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// hit-log exchange (multi-GPU): export the blocks of some slices into contiguous buffers; import blocks
+// received from other ranks into the free part of the pool
+// ------------------------------------------------------------------------------------------------
+// runs: [n_runs][2] = {slice, first output / input block of the run}; run r covers blocks [runs[r][1], runs[r+1][1])
+__device__ __forceinline__ uint32_t find_run(const uint32_t* __restrict__ runs, uint32_t n_runs, uint32_t blk)
+{
+	uint32_t lo = 0, hi = n_runs; // last run whose first block <= blk
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) / 2;
+		if (runs[2 * mid + 1] <= blk)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	return lo;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) export_kernel(const Pool P, const uint32_t* __restrict__ runs, uint32_t n_runs, uint32_t n_out,
+    uint32_t* __restrict__ out)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	for (uint32_t o = blockIdx.x * 8 + (threadIdx.x >> 5); o < n_out; o += gridDim.x * 8) {
+		const uint32_t r = find_run(runs, n_runs, o);
+		const uint32_t s = runs[2 * r], j = o - runs[2 * r + 1];
+		const uint32_t le = j < P.slice_cap ? P.slice_blocks[(size_t)s * P.slice_cap + j] : kVoid;
+		const uint32_t f = le == kVoid ? 0u : min(le & 511u, kBlkEntries);
+		if (lane == 0)
+			out[(size_t)o * kWireBlkWords + kBlkEntries] = f; // trailer: valid entries
+		const uint32_t* e = P.entries + (size_t)(le >> 9) * kBlkEntries;
+		for (uint32_t i = lane; i < f; i += 32)
+			out[(size_t)o * kWireBlkWords + i] = e[i];
+	}
+}
+
+__global__ void __launch_bounds__(256) import_kernel(const Pool P, const uint32_t* __restrict__ runs, uint32_t n_runs, uint32_t n_in,
+    uint32_t base_blk, const uint32_t* __restrict__ in)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0)
+		P.ctl[CTL_NEXT] = base_blk + n_in; // the imported blocks now belong to the pool
+	if (i >= n_in)
+		return;
+	const uint32_t s = runs[2 * find_run(runs, n_runs, i)];
+	const uint32_t f = min(in[(size_t)i * kWireBlkWords + kBlkEntries], kBlkEntries);
+	if (f == 0)
+		return;
+	const uint32_t at = atomicAdd(P.slice_nblk + s, 1u);
+	if (at < P.slice_cap)
+		P.slice_blocks[(size_t)s * P.slice_cap + at] = ((base_blk + i) << 9) | f;
+	else
+		P.ctl[CTL_DIRECT] = 2u; // cannot happen: the host checks the capacities before importing
+}
+} // namespace
+
+cudaError_t launch_export(const Pool& pool, const uint32_t* d_runs, uint32_t n_runs, uint32_t n_out, uint32_t* d_out, cudaStream_t st)
+{
+	if (n_out == 0)
+		return cudaSuccess;
+	const unsigned grid = (n_out + 7) / 8 < 148 * 8 ? (n_out + 7) / 8 : 148 * 8;
+	export_kernel<<<grid, 256, 0, st>>>(pool, d_runs, n_runs, n_out, d_out);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_import(const Pool& pool, const uint32_t* d_runs, uint32_t n_runs, uint32_t n_in, uint32_t base_blk, const uint32_t* d_in,
+    cudaStream_t st)
+{
+	import_kernel<<<(n_in + 255) / 256 + (n_in == 0), 256, 0, st>>>(pool, d_runs, n_runs, n_in, base_blk, d_in);
+	return cudaGetLastError();
+}
+
+// counter-value histogram (v >= 1) of a list of slices in ONE launch: CTA = 16 K consecutive counters
+namespace {
+constexpr uint32_t kHistChunk = 16384, kHistBins = 2048;
+__global__ void __launch_bounds__(256) hist_slices_kernel(const uint32_t* __restrict__ counters, const uint32_t* __restrict__ order, uint32_t bin_shift,
+    uint32_t nbins, uint32_t rBits, uint32_t* __restrict__ p_hist)
+{
+	__shared__ uint32_t sh[kHistBins];
+	for (uint32_t i = threadIdx.x; i < kHistBins; i += blockDim.x)
+		sh[i] = 0;
+	__syncthreads();
+	const uint64_t slice_len = (uint64_t)1 << bin_shift, per_k = (uint64_t)2 << rBits;
+	const uint32_t chunk = (uint32_t)min((uint64_t)kHistChunk, slice_len);
+	const uint32_t chunks_per_slice = (uint32_t)(slice_len / chunk);
+	const uint32_t s = order[blockIdx.x / chunks_per_slice];
+	const uint64_t first = (uint64_t)(s / nbins) * per_k + (uint64_t)(s % nbins) * slice_len + (uint64_t)(blockIdx.x % chunks_per_slice) * chunk;
+	uint32_t* ph = p_hist + (first >> rBits) * 65536; // a chunk lies inside one table (chunk <= 2^rBits: the host checks)
+	auto count = [&](uint32_t v) {
+		v &= 0xFFFFu; // uint16_t wrap of ntcard.cpp:143
+		if (v) {
+			if (v < kHistBins)
+				atomicAdd(&sh[v], 1u);
+			else
+				atomicAdd(&ph[v], 1u);
+		}
+	};
+	if (chunk % 4 == 0) {
+		const uint4* src = reinterpret_cast<const uint4*>(counters + first);
+		for (uint32_t i = threadIdx.x; i < chunk / 4; i += blockDim.x) {
+			const uint4 v = __ldcs(src + i);
+			if (v.x | v.y | v.z | v.w) {
+				count(v.x);
+				count(v.y);
+				count(v.z);
+				count(v.w);
+			}
+		}
+	} else {
+		for (uint32_t i = threadIdx.x; i < chunk; i += blockDim.x)
+			count(counters[first + i]);
+	}
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < kHistBins; i += blockDim.x)
+		if (sh[i])
+			atomicAdd(&ph[i], sh[i]);
+}
+} // namespace
+
+cudaError_t launch_hist_slices(const Pool& pool, const uint32_t* counters, const uint32_t* d_order, uint32_t n_order, uint32_t* d_phist, cudaStream_t st)
+{
+	if (n_order == 0)
+		return cudaSuccess;
+	const uint64_t slice_len = (uint64_t)1 << pool.bin_shift;
+	const uint64_t chunk = slice_len < kHistChunk ? slice_len : kHistChunk;
+	if (chunk > ((uint64_t)1 << pool.rBits))
+		return cudaErrorInvalidValue;
+	hist_slices_kernel<<<(unsigned)(n_order * (slice_len / chunk)), 256, 0, st>>>(counters, d_order, pool.bin_shift, pool.nbins, pool.rBits, d_phist);
 	return cudaGetLastError();
 }
 

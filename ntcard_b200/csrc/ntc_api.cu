@@ -12,7 +12,6 @@
 
 #include "../../include/ntcard_b200.h"
 #include "bitslice_core.cuh"
-#include "bitslice_launch.h"
 #include "internal.h"
 #include "launch.h"
 #include "pipeline.h"
@@ -62,7 +61,10 @@ struct ntc_ctx {
 	unsigned long long* d_f1 = nullptr;
 	ntc::DevParams* d_params = nullptr;
 	uint4* d_bs_tab = nullptr;            // hit-path byte tables of the bit-sliced kernel
-	ntc::bs::BsLaunch bs_launch[NTC_MAX_K]; // per-k constants of the bit-sliced kernel
+	struct KInit {                          // per-k constants of the scan / hit kernels
+		uint32_t F0[31], R0[31];            // initial bit-sliced state (bitslice_core.cuh init_state)
+		uint64_t rot_a, rot_b;              // byte m: (k%32 + 32m) % 31 and % 33 for block m of the full hash (k < 288)
+	} kinit[NTC_MAX_K];
 	bool totals_overridden = false;
 	uint64_t totals[NTC_MAX_K] = {};
 	Stage stage[NBUF];
@@ -84,6 +86,11 @@ struct ntc_ctx {
 	size_t cap_tile_info = 0;
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
+	bool partial = false;     // after ntc_flush_slices: only the owned slices of the sketch are defined (until ntc_reset)
+	std::vector<uint32_t> h_nblk; // block counts per slice as of the last ntc_log_counts
+	uint32_t log_used = 0;
+	uint32_t* d_runs = nullptr;
+	size_t cap_runs = 0;
 	unsigned apply_grid = 0, hit_grid_max = 0;
 	unsigned chunk_waves = 0; // scan waves per pipeline chunk (0 = whole batch; chunking measured slower, kept for experiments)
 	uint64_t n_flush_launches = 0;
@@ -93,6 +100,9 @@ struct ntc_ctx {
 	// stats / timing
 	uint64_t n_launches = 0, n_batches = 0;
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing; // per batch, around the sketch kernels
+	struct StageSpan { cudaEvent_t a, b; int stage; };
+	std::vector<StageSpan> stage_timing;                      // per pipeline stage: 0 scan, 1 hit (+ fallback), 2 apply
+	double stage_ms[3] = { 0, 0, 0 };
 	std::vector<cudaEvent_t> event_pool;
 	double kernel_ms = 0;
 	uint64_t n_timed = 0;
@@ -158,49 +168,6 @@ void build_params(const ntc_ctx* c, ntc::DevParams* P)
 	}
 }
 
-// Which k indices the bit-sliced kernel can take for this batch; plane capacity / warps per CTA in *cfg.
-struct BsConfig {
-	uint32_t kmask = 0;
-	uint32_t pairs[NTC_MAX_K] = {}, ring[NTC_MAX_K] = {}, nbuf[NTC_MAX_K] = {};
-	size_t smem[NTC_MAX_K] = {};
-};
-
-// Shared memory of one CTA of the bit-sliced kernel for a given k: the byte tables plus, per scan warp, a plane ring of
-// `ring` positions (power of two >= k + 16, + 1 zero slot), nbuf mask buffers, two hit queues, descriptors + mbarriers.
-bool bitslice_shape(unsigned k, uint32_t* pairs, uint32_t* ring, uint32_t* nbuf, size_t* smem)
-{
-	uint32_t r = 64;
-	while (r < k + 16)
-		r <<= 1;
-	for (uint32_t p = 4; p >= 1; p--)
-		for (uint32_t nb = 8; nb >= 4; nb -= 4) {
-			const size_t per_pair = (size_t)(r + 1) * 256 + nb * ntc::bs::kMaskBytes + ntc::bs::kHitWarpsPerScan * ntc::bs::kQueueCap * 4 + nb * 32;
-			const size_t total = ntc::bs::kTabBytes + p * per_pair;
-			if (total <= ntc::bs::kSmemMax) {
-				*pairs = p;
-				*ring = r;
-				*nbuf = nb;
-				*smem = total;
-				return true;
-			}
-		}
-	return false;
-}
-
-BsConfig bitslice_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
-{
-	BsConfig cfg;
-	if (c->kernel == NTC_KERNEL_ROLL64 || b.off || !record_is_piece || b.stride < 4 || (b.stride & 3u) ||
-	    b.n_rec < 1024 || (reinterpret_cast<uintptr_t>(b.words) & 15u))
-		return cfg;
-	for (unsigned ki = 0; ki < c->nK; ki++)
-		if (c->k[ki] < 288 && ntc::bs::have_kernel(c->k[ki], c->sBits) &&
-		    bitslice_shape(c->k[ki], &cfg.pairs[ki], &cfg.ring[ki], &cfg.nbuf[ki], &cfg.smem[ki]))
-			cfg.kmask |= 1u << ki;
-	return cfg;
-}
-
-
 // ---- sketch pipeline -------------------------------------------------------------------------------------
 int pool_create(ntc_ctx* c)
 {
@@ -243,6 +210,24 @@ int pool_create(ntc_ctx* c)
 	return NTC_OK;
 }
 
+// CUDA events around one pipeline stage (0 scan, 1 hit + fallback, 2 apply) on the compute stream
+int stage_begin(ntc_ctx* c, int stage)
+{
+	ntc_ctx::StageSpan sp;
+	int rc;
+	if ((rc = get_event(c, &sp.a)) || (rc = get_event(c, &sp.b)))
+		return rc;
+	sp.stage = stage;
+	CK(cudaEventRecord(sp.a, c->stream));
+	c->stage_timing.push_back(sp);
+	return NTC_OK;
+}
+int stage_end(ntc_ctx* c)
+{
+	CK(cudaEventRecord(c->stage_timing.back().b, c->stream));
+	return NTC_OK;
+}
+
 // Apply everything that is pending to the counters in HBM (and materialise them after a reset).
 int flush(ntc_ctx* c)
 {
@@ -253,7 +238,11 @@ int flush(ntc_ctx* c)
 	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
 		return rc;
 	CK(cudaEventRecord(e0, c->stream));
+	if ((rc = stage_begin(c, 2)))
+		return rc;
 	CK(ntc::pl::launch_apply(c->pool, c->d_counters, 1, 0, c->apply_grid, c->stream));
+	if ((rc = stage_end(c)))
+		return rc;
 	CK(cudaEventRecord(e1, c->stream));
 	c->timing.emplace_back(e0, e1);
 	c->n_launches++;
@@ -291,8 +280,8 @@ uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 		uint32_t r = 64;
 		while (r < k + 16)
 			r <<= 1;
-		const size_t per_warp = (size_t)(r + 1) * 256;
-		const uint32_t nw = (uint32_t)std::min<size_t>(8, ntc::bs::kSmemMax / per_warp);
+		const size_t per_warp = (size_t)(r + 3) * 256; // ring + 3 mirror slots (scan_kernel.cuh)
+		const uint32_t nw = (uint32_t)std::min<size_t>(8, ntc::pl::kSmemMax / per_warp);
 		if (nw < 1)
 			continue;
 		s.ring = r;
@@ -361,8 +350,8 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	sa.L.ring = sh.ring;
 	sa.L.nwarps = sh.nwarps;
 	sa.L.npos_max = sh.npos_max;
-	memcpy(sa.L.F0, c->bs_launch[ki].F0, sizeof sa.L.F0);
-	memcpy(sa.L.R0, c->bs_launch[ki].R0, sizeof sa.L.R0);
+	memcpy(sa.L.F0, c->kinit[ki].F0, sizeof sa.L.F0);
+	memcpy(sa.L.R0, c->kinit[ki].R0, sizeof sa.L.R0);
 	sa.masks = c->d_masks;
 	sa.tile_info = c->d_tile_info;
 	sa.f1_k = c->d_f1 + ki;
@@ -371,7 +360,11 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	sa.grid = std::min<unsigned>((unsigned)c->n_sm, n_tiles);
 	sa.smem_bytes = sh.smem;
 	sa.stream = c->stream;
+	if ((rc = stage_begin(c, 0)))
+		return rc;
 	CK(ntc::pl::launch_scan(c->k[ki], c->sBits, sa));
+	if ((rc = stage_end(c)) || (rc = stage_begin(c, 1)))
+		return rc;
 	ntc::pl::HitArgs ha;
 	ha.words = b.words;
 	ha.stride = b.stride;
@@ -388,8 +381,8 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	ha.masks = c->d_masks;
 	ha.tile_info = c->d_tile_info;
 	ha.d_tab = c->d_bs_tab;
-	ha.rot_a = c->bs_launch[ki].rot_a;
-	ha.rot_b = c->bs_launch[ki].rot_b;
+	ha.rot_a = c->kinit[ki].rot_a;
+	ha.rot_b = c->kinit[ki].rot_b;
 	ha.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 	ha.pool = P;
 	ha.stream = c->stream;
@@ -400,6 +393,8 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	CK(ntc::pl::launch_apply(P, c->d_counters, 0, 3 * P.max_groups * P.nbins + 8, c->apply_grid, c->stream));
 	CK(ntc::pl::launch_hit(ha, staged, hit_ctas));
 	CK(ntc::pl::launch_fallback(b.words, b.stride, b.n_rec, n_tiles, c->d_tile_info, c->d_params, ki, ha.ctr_k, P.ctl, c->n_sm, c->stream));
+	if ((rc = stage_end(c)))
+		return rc;
 	c->n_launches += 4;
 	c->pending = true;
 	return NTC_OK;
@@ -417,40 +412,16 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 	CK(cudaEventRecord(e0, c->stream));
 	PipeShape shape[NTC_MAX_K];
 	const uint32_t pmask = pipeline_config(c, b, record_is_piece, shape);
-	BsConfig bs = c->use_pipeline ? BsConfig() : bitslice_config(c, b, record_is_piece);
 	const uint32_t all = c->nK >= 32 ? 0xFFFFFFFFu : ((1u << c->nK) - 1);
-	const uint32_t roll_mask = all & ~(bs.kmask | pmask);
+	const uint32_t roll_mask = all & ~pmask;
 	if (c->kernel == NTC_KERNEL_BITSLICE && roll_mask)
-		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", bs.kmask | pmask);
+		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", pmask);
 	for (unsigned ki = 0; ki < c->nK; ki++)
 		if ((pmask >> ki) & 1u)
 			if ((rc = run_pipeline_k(c, b, ki, shape[ki])))
 				return rc;
-	if ((bs.kmask || roll_mask) && (rc = flush(c))) // these kernels increment the counters in HBM directly
+	if (roll_mask && (rc = flush(c))) // the general kernel increments the counters in HBM directly
 		return rc;
-	for (unsigned ki = 0; ki < c->nK; ki++) {
-		if (!((bs.kmask >> ki) & 1u))
-			continue;
-		ntc::bs::BsArgs a;
-		a.words = b.words;
-		a.stride = b.stride;
-		a.n_rec = b.n_rec;
-		a.L = c->bs_launch[ki];
-		a.L.ring = bs.ring[ki];
-		a.L.nbuf = bs.nbuf[ki];
-		a.L.pairs = bs.pairs[ki];
-		a.d_tab = c->d_bs_tab;
-		a.d_params = c->d_params;
-		a.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
-		a.f1_k = c->d_f1 + ki;
-		a.pairs = bs.pairs[ki];
-		const unsigned n_tiles = (b.n_rec + 1023) / 1024;
-		a.grid = std::min<unsigned>((unsigned)c->n_sm, (n_tiles + bs.pairs[ki] - 1) / bs.pairs[ki]);
-		a.smem_bytes = bs.smem[ki];
-		a.stream = c->stream;
-		CK(ntc::bs::launch(c->k[ki], c->sBits, a));
-		c->n_launches += 1;
-	}
 	if (roll_mask) {
 		uint64_t bound = 0;
 		if (!record_is_piece) {
@@ -490,6 +461,15 @@ int drain_timing(ntc_ctx* c)
 		c->event_pool.push_back(pr.second);
 	}
 	c->timing.clear();
+	for (auto& sp : c->stage_timing) {
+		float ms = 0;
+		CK(cudaEventSynchronize(sp.b));
+		CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+		c->stage_ms[sp.stage] += ms;
+		c->event_pool.push_back(sp.a);
+		c->event_pool.push_back(sp.b);
+	}
+	c->stage_timing.clear();
 	return NTC_OK;
 }
 
@@ -584,16 +564,11 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 	CKF(cudaMemcpy(c->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
 	{
 		std::vector<uint32_t> tab(8 * 256 * 4);
-		ntc::bs::build_tables(tab.data());
+		ntc::pl::build_tables(tab.data());
 		CKF(cudaMalloc((void**)&c->d_bs_tab, tab.size() * sizeof(uint32_t)));
 		CKF(cudaMemcpy(c->d_bs_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		for (unsigned ki = 0; ki < nK; ki++) {
-			ntc::bs::BsLaunch& L = c->bs_launch[ki];
-			L.k = c->k[ki];
-			L.ki = ki;
-			L.rBits = rBits;
-			L.ring = L.nbuf = L.pairs = 0;
-			L.dbg = getenv("NTC_BS_DEBUG") ? (uint32_t)atoi(getenv("NTC_BS_DEBUG")) : 0u;
+			ntc_ctx::KInit& L = c->kinit[ki];
 			ntc::bs::init_state(c->k[ki], L.F0, L.R0);
 			L.rot_a = L.rot_b = 0;
 			for (unsigned m = 0; m < 8; m++) {
@@ -631,6 +606,10 @@ void ntc_destroy(ntc_ctx* c)
 		cudaEventDestroy(pr.first);
 		cudaEventDestroy(pr.second);
 	}
+	for (auto& sp : c->stage_timing) {
+		cudaEventDestroy(sp.a);
+		cudaEventDestroy(sp.b);
+	}
 	for (auto e : c->event_pool)
 		cudaEventDestroy(e);
 	for (int i = 0; i < NBUF; i++) {
@@ -655,6 +634,7 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->pool.gstate) cudaFree(c->pool.gstate);
 	if (c->d_pool_ctl_region) cudaFree(c->d_pool_ctl_region);
 	if (c->d_masks) cudaFree(c->d_masks);
+	if (c->d_runs) cudaFree(c->d_runs);
 	if (c->d_tile_info) cudaFree(c->d_tile_info);
 	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -678,6 +658,7 @@ int ntc_reset(ntc_ctx* c)
 		c->pool.epoch = 1;
 	c->totals_overridden = false;
 	c->pending = true;
+	c->partial = false;
 	return NTC_OK;
 }
 
@@ -700,6 +681,8 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 		*ticket = 0;
 	if (n_rec == 0)
 		return NTC_OK;
+	if (c->partial)
+		return set_err(NTC_ESTATE, "ntc_submit: the sketch was flushed partially (ntc_flush_slices); ntc_reset first");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
@@ -770,6 +753,8 @@ int ntc_submit_device(ntc_ctx* c, const uint32_t* d_words, size_t n_words, const
 		return set_err(NTC_EINVAL, "ntc_submit_device: uniform batch needs stride_words*n_rec <= n_words");
 	if (n_rec == 0)
 		return NTC_OK;
+	if (c->partial)
+		return set_err(NTC_ESTATE, "ntc_submit_device: the sketch was flushed partially (ntc_flush_slices); ntc_reset first");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
@@ -815,11 +800,214 @@ int ntc_flush(ntc_ctx* c)
 	return flush(c);
 }
 
+
+/* ---- hit-log exchange (multi-GPU sparse reduction) ------------------------------------------------------ */
+int ntc_log_info(ntc_ctx* c, uint32_t* n_slices, uint64_t* counters_per_slice, uint32_t* entries_per_block)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	if (n_slices) *n_slices = c->pool.n_slices;
+	if (counters_per_slice) *counters_per_slice = (uint64_t)1 << c->pool.bin_shift;
+	if (entries_per_block) *entries_per_block = ntc::pl::kBlkEntries;
+	return NTC_OK;
+}
+
+int ntc_log_counts(ntc_ctx* c, uint32_t* nblk, int* exportable, uint32_t* pool_info)
+{
+	if (!c || !nblk || !exportable)
+		return set_err(NTC_EINVAL, "ntc_log_counts: bad argument");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	const ntc::pl::Pool& P = c->pool;
+	std::vector<uint32_t> h(ntc::pl::CTL_WORDS + P.n_slices);
+	CK(cudaMemcpyAsync(h.data(), P.ctl, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream)); // ctl and slice_nblk are adjacent
+	CK(cudaStreamSynchronize(c->stream));
+	if ((rc = drain_timing(c)))
+		return rc;
+	c->h_nblk.assign(P.n_slices, 0);
+	for (uint32_t s = 0; s < P.n_slices; s++)
+		nblk[s] = c->h_nblk[s] = std::min(h[ntc::pl::CTL_WORDS + s], P.slice_cap);
+	c->log_used = std::min(h[ntc::pl::CTL_NEXT], P.n_blocks);
+	if (pool_info) {
+		pool_info[0] = c->log_used;
+		pool_info[1] = P.n_blocks;
+		pool_info[2] = P.slice_cap;
+	}
+	// exportable: everything submitted since the reset is still in the log (nothing flushed, nothing added directly)
+	*exportable = (h[ntc::pl::CTL_STATE] == 0 && h[ntc::pl::CTL_DIRECT] == 0 && h[ntc::pl::CTL_NEXT] <= P.n_blocks && c->pending && !c->partial) ? 1 : 0;
+	return NTC_OK;
+}
+
+static int upload_runs(ntc_ctx* c, const std::vector<uint32_t>& runs)
+{
+	int rc;
+	if ((rc = grow(&c->d_runs, &c->cap_runs, runs.size() + 2, false)))
+		return rc;
+	CK(cudaMemcpyAsync(c->d_runs, runs.data(), runs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream)); // `runs` is a host temporary
+	return NTC_OK;
+}
+
+int ntc_log_export(ntc_ctx* c, const uint32_t* slices, uint32_t n, void* d_blocks)
+{
+	if (!c || (n && !slices) || c->h_nblk.size() != c->pool.n_slices)
+		return set_err(NTC_EINVAL, "ntc_log_export: bad argument (call ntc_log_counts first)");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	std::vector<uint32_t> runs;
+	uint32_t total = 0;
+	for (uint32_t i = 0; i < n; i++) {
+		if (slices[i] >= c->pool.n_slices)
+			return set_err(NTC_EINVAL, "ntc_log_export: slice %u of %u", slices[i], c->pool.n_slices);
+		if (c->h_nblk[slices[i]] == 0)
+			continue;
+		runs.push_back(slices[i]);
+		runs.push_back(total);
+		total += c->h_nblk[slices[i]];
+	}
+	if (total == 0)
+		return NTC_OK;
+	if (!d_blocks)
+		return set_err(NTC_EINVAL, "ntc_log_export: null output buffer");
+	if ((rc = upload_runs(c, runs)))
+		return rc;
+	CK(ntc::pl::launch_export(c->pool, c->d_runs, (uint32_t)runs.size() / 2, total, (uint32_t*)d_blocks, c->stream));
+	c->n_launches++;
+	return NTC_OK;
+}
+
+int ntc_log_import(ntc_ctx* c, const void* d_blocks, uint32_t n_blocks, const uint32_t* runs_in, uint32_t n_runs)
+{
+	if (!c || (n_blocks && (!d_blocks || !runs_in)) || c->h_nblk.size() != c->pool.n_slices)
+		return set_err(NTC_EINVAL, "ntc_log_import: bad argument (call ntc_log_counts first)");
+	if (n_blocks == 0)
+		return NTC_OK;
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	const ntc::pl::Pool& P = c->pool;
+	if ((uint64_t)c->log_used + n_blocks > P.n_blocks)
+		return set_err(NTC_ENOMEM, "ntc_log_import: %u blocks do not fit the hit log (%u of %u used)", n_blocks, c->log_used, P.n_blocks);
+	std::vector<uint32_t> runs;
+	uint32_t total = 0;
+	for (uint32_t i = 0; i < n_runs; i++) {
+		const uint32_t s = runs_in[2 * i], nb = runs_in[2 * i + 1];
+		if (s >= P.n_slices)
+			return set_err(NTC_EINVAL, "ntc_log_import: slice %u of %u", s, P.n_slices);
+		if (nb == 0)
+			continue;
+		if ((uint64_t)c->h_nblk[s] + nb > P.slice_cap)
+			return set_err(NTC_ENOMEM, "ntc_log_import: block list of slice %u is full", s);
+		c->h_nblk[s] += nb;
+		runs.push_back(s);
+		runs.push_back(total);
+		total += nb;
+	}
+	if (total != n_blocks)
+		return set_err(NTC_EINVAL, "ntc_log_import: runs cover %u blocks, n_blocks = %u", total, n_blocks);
+	if ((rc = upload_runs(c, runs)))
+		return rc;
+	// wire blocks (260 words) -> pool blocks (256 words)
+	CK(cudaMemcpy2DAsync(P.entries + (size_t)c->log_used * ntc::pl::kBlkEntries, ntc::pl::kBlkEntries * sizeof(uint32_t), d_blocks,
+	    ntc::pl::kWireBlkWords * sizeof(uint32_t), ntc::pl::kBlkEntries * sizeof(uint32_t), n_blocks, cudaMemcpyDeviceToDevice, c->stream));
+	CK(ntc::pl::launch_import(P, c->d_runs, (uint32_t)runs.size() / 2, n_blocks, c->log_used, (const uint32_t*)d_blocks, c->stream));
+	c->log_used += n_blocks;
+	c->n_launches++;
+	c->pending = true;
+	return NTC_OK;
+}
+
+int ntc_stream_sync(ntc_ctx* c)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	return NTC_OK;
+}
+
+int ntc_flush_slices(ntc_ctx* c, const uint8_t* owned)
+{
+	if (!c || !owned)
+		return set_err(NTC_EINVAL, "ntc_flush_slices: bad argument");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	std::vector<uint32_t> order;
+	for (uint32_t s = 0; s < c->pool.n_slices; s++)
+		if (owned[s])
+			order.push_back(s);
+	const uint32_t n = (uint32_t)order.size();
+	order.push_back(0); // never an empty upload
+	if ((rc = upload_runs(c, order)))
+		return rc;
+	cudaEvent_t e0, e1;
+	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
+		return rc;
+	CK(cudaEventRecord(e0, c->stream));
+	if ((rc = stage_begin(c, 2)))
+		return rc;
+	CK(ntc::pl::launch_apply(c->pool, c->d_counters, 1, 0, c->apply_grid, c->stream, c->d_runs, n));
+	if ((rc = stage_end(c)))
+		return rc;
+	CK(cudaEventRecord(e1, c->stream));
+	c->timing.emplace_back(e0, e1);
+	c->n_launches++;
+	c->pending = false;
+	c->partial = true;
+	return NTC_OK;
+}
+
+int ntc_hist_slices(ntc_ctx* c, const uint8_t* owned, uint32_t* p_hist, void* d_p_hist)
+{
+	if (!c || !owned || (!p_hist && !d_p_hist))
+		return set_err(NTC_EINVAL, "ntc_hist_slices: bad argument");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	if (c->pending)
+		return set_err(NTC_ESTATE, "ntc_hist_slices: flush first (ntc_flush_slices / ntc_flush)");
+	const ntc::pl::Pool& P = c->pool;
+	const uint32_t n_tables = c->nK * NTC_NSAMP;
+	const size_t hist_bytes = (size_t)n_tables * 65536 * sizeof(uint32_t);
+	uint32_t* dst = (uint32_t*)d_p_hist;
+	if (!dst) {
+		if (!c->d_phist)
+			CK(cudaMalloc((void**)&c->d_phist, hist_bytes));
+		dst = c->d_phist;
+	}
+	CK(cudaMemsetAsync(dst, 0, hist_bytes, c->stream));
+	std::vector<uint32_t> order;
+	for (uint32_t s = 0; s < P.n_slices; s++)
+		if (owned[s])
+			order.push_back(s);
+	const uint32_t n = (uint32_t)order.size();
+	order.push_back(0);
+	if ((rc = upload_runs(c, order)))
+		return rc;
+	cudaError_t e = ntc::pl::launch_hist_slices(P, c->d_counters, c->d_runs, n, dst, c->stream);
+	if (e == cudaErrorInvalidValue)
+		return set_err(NTC_EINVAL, "ntc_hist_slices: rBits too small for the histogram chunk");
+	CK(e);
+	c->n_launches++;
+	if (p_hist) {
+		CK(cudaMemcpyAsync(p_hist, dst, hist_bytes, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return NTC_OK;
+}
+
 int ntc_counters_device(ntc_ctx* c, void** d_counters, size_t* n_counters)
 {
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	int rc;
+	if (c->partial)
+		return set_err(NTC_ESTATE, "ntc_counters_device: after ntc_flush_slices only ntc_hist_slices / ntc_totals / ntc_reset are valid");
 	if ((rc = use_device(c)) || (rc = flush(c))) // what the caller reads (or all-reduces) must be complete
 		return rc;
 	if (d_counters) *d_counters = c->d_counters;
@@ -845,6 +1033,21 @@ int ntc_totals(ntc_ctx* c, uint64_t* totKmer)
 	return NTC_OK;
 }
 
+int ntc_totals_nosync(ntc_ctx* c, uint64_t* totKmer)
+{
+	if (!c || !totKmer)
+		return set_err(NTC_EINVAL, "ntc_totals_nosync: bad argument");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	unsigned long long h[NTC_MAX_K];
+	CK(cudaMemcpyAsync(h, c->d_f1, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	for (unsigned i = 0; i < c->nK; i++)
+		totKmer[i] = h[i];
+	return NTC_OK;
+}
+
 int ntc_set_totals(ntc_ctx* c, const uint64_t* totKmer)
 {
 	if (!c || !totKmer)
@@ -861,6 +1064,8 @@ int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_h
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
+	if (c->partial)
+		return set_err(NTC_ESTATE, "ntc_finish: after ntc_flush_slices only ntc_hist_slices / ntc_totals / ntc_reset are valid");
 	if ((rc = flush(c)))
 		return rc;
 	if (totKmer && (rc = ntc_totals(c, totKmer)))
@@ -957,6 +1162,17 @@ int ntc_stats(ntc_ctx* c, uint64_t* n_launches, uint64_t* n_batches)
 		return set_err(NTC_EINVAL, "null context");
 	if (n_launches) *n_launches = c->n_launches;
 	if (n_batches) *n_batches = c->n_batches;
+	return NTC_OK;
+}
+
+int ntc_stage_times(ntc_ctx* c, double* ms3)
+{
+	if (!c || !ms3)
+		return set_err(NTC_EINVAL, "ntc_stage_times: bad argument");
+	for (int i = 0; i < 3; i++) {
+		ms3[i] = c->stage_ms[i];
+		c->stage_ms[i] = 0;
+	}
 	return NTC_OK;
 }
 

@@ -21,6 +21,7 @@ struct DevParams;
 namespace pl {
 
 constexpr uint32_t kBlkEntries = 256;         // log entries per pool block (1 KB)
+constexpr uint32_t kWireBlkWords = 260;        // a log block on the wire (multi-GPU exchange): 256 entries, fill, 3 words of padding
 constexpr uint32_t kBlkSlack = 96;            // a block with fewer free entries than this is closed at the end of a round
 constexpr uint32_t kVoid = 0xFFFFFFFFu;
 constexpr uint32_t kTileFlag = 0xFFFFFFFFu;   // tile_info value: not uniform -> fallback kernel
@@ -29,6 +30,7 @@ constexpr uint32_t kMaxBins = 64;             // slices per k
 constexpr uint32_t kQueueCap = 4096;          // candidates per round of a hit group
 constexpr uint32_t kGroupThreads = 256;
 constexpr uint32_t kApplyThreads = 512;
+constexpr size_t kSmemMax = 232448;           // 227 KB opt-in limit per CTA on sm_100
 
 // control words (device)
 enum { CTL_NEXT = 0, CTL_STATE = 1, CTL_NFLAG = 2, CTL_TICKET = 3, CTL_FLUSHES = 4, CTL_DIRECT = 5, CTL_WORDS = 8 };
@@ -82,7 +84,10 @@ struct HitArgs {
 	cudaStream_t stream;
 };
 
+// True when a scan kernel for (k mod 31, sBits) was compiled in (Makefile BS_KMS; sBits 7 and 11).
 bool have_scan_kernel(unsigned k, unsigned sBits);
+// Fill the byte tables of the full hash (host): tab[j*256+b] = {FB lo, FB hi, RB lo, RB hi}.
+void build_tables(uint32_t* tab /* 8*256*4 words */);
 cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a);
 bool hit_can_stage(uint32_t stride, uint32_t units_per_tile, uint32_t tiles_per_unit);
 unsigned hit_groups_per_sm(bool staged);
@@ -91,7 +96,14 @@ cudaError_t launch_fallback(const uint32_t* words, uint32_t stride, uint32_t n_r
     const DevParams* d_params, uint32_t ki, uint32_t* ctr_k, const uint32_t* ctl, int n_sm, cudaStream_t st);
 // force = 0: flush only if the batch about to be hashed could overflow the pool while the sketch is still
 // unmaterialised (or has flagged tiles); force = 1: flush whatever is pending and materialise the sketch.
-cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32_t reserve_blocks, unsigned grid, cudaStream_t st);
+cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32_t reserve_blocks, unsigned grid, cudaStream_t st,
+    const uint32_t* d_order = nullptr, uint32_t n_order = 0);
+// Hit-log exchange between ranks: copy the blocks of runs of slices to contiguous buffers / register received blocks
+// (already copied to pool blocks base_blk..) in the block lists of their slices.  runs: [n_runs][2] = {slice, first block}.
+cudaError_t launch_export(const Pool& pool, const uint32_t* d_runs, uint32_t n_runs, uint32_t n_out, uint32_t* d_out, cudaStream_t st);
+cudaError_t launch_import(const Pool& pool, const uint32_t* d_runs, uint32_t n_runs, uint32_t n_in, uint32_t base_blk, const uint32_t* d_in,
+    cudaStream_t st);
+cudaError_t launch_hist_slices(const Pool& pool, const uint32_t* counters, const uint32_t* d_order, uint32_t n_order, uint32_t* d_phist, cudaStream_t st);
 int apply_max_grid(int n_sm);
 
 } // namespace pl

@@ -26,35 +26,44 @@ namespace pl {
 constexpr int kScanBlock = 4;      // scan positions per unrolled block
 constexpr int kScanThreads = 256;  // 8 warps
 
-__device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p)
+// 128-bit loads of the packed reads with an L2 evict_last hint: a record's three 16-byte groups are read tens of
+// microseconds apart, and without the hint the 32-byte sectors they share leave L2 in between (2.4x the input
+// bytes came from DRAM).
+__device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p, uint64_t policy)
 {
 	uint4 r;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+	             : "l"(p), "l"(policy));
 	return r;
 }
 
 // Branch free on purpose: positions past the end of the read run on whatever the planes hold and store nothing.
-// Planes live in a ring of rmask+1 positions (slot = position mod ring size); slot rmask+1 is all zero and stands
-// for the virtual bases before the read (window not full yet).
+// Planes live in a ring of rmask+1 positions (slot = position mod ring size) followed by 3 slots that mirror slots
+// 0..2, so the kScanBlock slots of a block can be addressed from one base without wrapping.  The k "virtual"
+// positions before the read (window not full yet) are the k slots before slot 0, zeroed at the start of a tile.
+// pin / pout / mb: plane slot of the block's first entering / leaving position, mask row of its first position.
 template <int KM, int S, int U> struct ScanBlock {
-	static __device__ __forceinline__ void run(bs::State& st, const uint2* __restrict__ pl, uint32_t* __restrict__ mrow, int qb, int k, int n,
-	    int rmask, uint32_t vmask, uint32_t& cand)
+	static __device__ __forceinline__ void run(bs::State& st, const uint2* __restrict__ pin, const uint2* __restrict__ pout,
+	    uint32_t* __restrict__ mb, int qb, int k, int n, uint32_t& cand)
 	{
-		const int q = qb + U;
-		const uint2 in = pl[(q & rmask) * 32];
-		const int oq = q - k;
-		const uint2 out = pl[(oq < 0 ? rmask + 1 : (oq & rmask)) * 32];
+		const uint2 in = pin[U * 32];
+		const uint2 out = pout[U * 32];
 		bs::step<KM, U>(st, in.x, in.y, out.x, out.y);
-		const uint32_t m = bs::sampled_mask<U, S>(st) & vmask;
+		const uint32_t m = bs::sampled_mask<U, S>(st); // slots past the end of the batch are dropped by the hit kernel
+		const int q = qb + U;
 		if (q >= k - 1 && q < n) {
-			__stcs(mrow + q * 32, m); // streaming store: read once by the hit kernel
+			__stcs(mb + U * 32, m); // streaming store: read once by the hit kernel
 			cand += __popc(m);
 		}
-		ScanBlock<KM, S, U + 1>::run(st, pl, mrow, qb, k, n, rmask, vmask, cand);
+		ScanBlock<KM, S, U + 1>::run(st, pin, pout, mb, qb, k, n, cand);
 	}
 };
 template <int KM, int S> struct ScanBlock<KM, S, kScanBlock> {
-	static __device__ __forceinline__ void run(bs::State&, const uint2* __restrict__, uint32_t* __restrict__, int, int, int, int, uint32_t, uint32_t&) {}
+	static __device__ __forceinline__ void run(bs::State&, const uint2* __restrict__, const uint2* __restrict__, uint32_t* __restrict__, int, int, int,
+	    uint32_t&)
+	{
+	}
 };
 
 // After kScanBlock steps logical ring bit r sits in physical F[r - kScanBlock] / R[r + kScanBlock]: move it home
@@ -88,10 +97,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 	if (warp >= L.nwarps)
 		return;
 	const int rmask = (int)L.ring - 1;
-	uint2* planes = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * (L.ring + 1u) * 256u); // [position mod ring][lane]; slot `ring` = zeros
-	planes[L.ring * 32 + lane] = make_uint2(0u, 0u);
-	__syncwarp();
+	uint2* planes = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * (L.ring + 3u) * 256u); // [position mod ring (+3 mirror slots)][lane]
 
+	uint64_t keep;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
 	const int k = (int)L.k;
 	unsigned long long f1_local = 0, cand_local = 0;
 	uint32_t n_flag = 0;
@@ -101,13 +110,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 	for (uint32_t tile = warp * gridDim.x + blockIdx.x; tile < n_tiles; tile += gridDim.x * L.nwarps) {
 		const uint32_t rb = tile * kTileRecs;
 		// The last tile may be partial: slots past the end re-read the batch's last record (every load stays in
-		// bounds, the uniformity test is unaffected) and are masked out of every mask word (vmask).
+		// bounds, the uniformity test is unaffected); the hit kernel drops their candidates (record index >= n_rec).
 		const uint32_t nvalid = min(kTileRecs, n_rec - rb), last_rec = n_rec - 1u;
 		uint32_t vmask = 0;
 		uint4 v[32];
 #pragma unroll
 		for (int s = 0; s < 32; s++) {
-			v[s] = ldg_nc_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride));
+			v[s] = ldg_nc_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride), keep);
 			vmask |= (s * 32u + lane < nvalid ? 1u : 0u) << s;
 		}
 		const uint32_t len0 = __shfl_sync(0xFFFFFFFFu, v[0].x, 0);
@@ -152,6 +161,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			st.R[j] = L.R0[j];
 		}
 		uint32_t cand = 0;
+		for (int j = 1; j <= k; j++) // the virtual positions -k..-1: no bases
+			planes[((-j) & rmask) * 32 + lane] = make_uint2(0u, 0u);
 		// One column = one packed word of every record = 16 positions: transpose it into the plane ring, scan it.
 		// The next 16 bytes of every record are requested right after the last word of the current 16 bytes has
 		// been taken out of v[], so the loads fly during a whole column's scan.
@@ -180,10 +191,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			if (i == 3 && g + 1 < ngroups) {
 #pragma unroll
 				for (int s = 0; s < 32; s++)
-					v[s] = ldg_nc_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride) + (g + 1));
+					v[s] = ldg_nc_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride) + (g + 1), keep);
 			}
-			if (w == 0) {
-				// warm L2 with this warp's next tile (bulk async prefetch)
+			if (w == nwords / 2) {
+				// half way through: warm L2 with this warp's next tile (bulk async prefetch)
 				const uint64_t nrb = (uint64_t)(tile + gridDim.x * L.nwarps) * kTileRecs;
 				if (lane == 0 && nrb + kTileRecs <= n_rec) {
 					const uint32_t bytes = kTileRecs * stride * 4u;
@@ -193,16 +204,23 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			bs::transpose32(A);
 			const int q0 = (int)(16u * w);
 			{
-				uint2* dst = planes + (q0 & rmask) * 32 + lane; // a column never wraps: the ring size is a multiple of 16
+				const int c0 = q0 & rmask;
+				uint2* dst = planes + c0 * 32 + lane; // a column never wraps: the ring size is a multiple of 16
 #pragma unroll
 				for (int j = 0; j < 16; j++)
 					dst[j * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
+				if (c0 == 0) { // mirror of slots 0..2 behind the ring
+#pragma unroll
+					for (int j = 0; j < 3; j++)
+						dst[(rmask + 1 + j) * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
+				}
 			}
 			__syncwarp();
 			const int nq = min(16, n - q0);
 #pragma unroll 1
 			for (int qb = q0; qb < q0 + nq; qb += kScanBlock) {
-				ScanBlock<KM, S, 0>::run(st, planes + lane, mrow, qb, k, n, rmask, vmask, cand);
+				ScanBlock<KM, S, 0>::run(st, planes + lane + (qb & rmask) * 32, planes + lane + ((qb - k) & rmask) * 32, mrow + qb * 32, qb, k, n,
+				    cand);
 				scan_rotate_home(st);
 			}
 			__syncwarp();

@@ -52,9 +52,123 @@ def reduce_scatter_hist(sketch, counters: torch.Tensor, rBits: int):
         assert n % world == 0
         mine = torch.empty(n // world, dtype=counters.dtype, device=counters.device)
         dist.reduce_scatter_tensor(mine, counters, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream(counters.device).synchronize()   # the histogram kernel runs on the sketch's own stream
         p = sketch.hist_range(mine.data_ptr(), rank * (n // world), n // world)
         pt = torch.from_numpy(p.astype(np.int64)).to(counters.device)
         dist.all_reduce(pt, op=dist.ReduceOp.SUM)
         p = pt.cpu().numpy().astype(np.uint32)
     p[:, :, 0] = (1 << rBits) - p[:, :, 1:].sum(axis=2, dtype=np.uint64).astype(np.uint32)
     return p
+
+
+# ---- sparse reduction: exchange the hit log, not the sketch ------------------------------------------------
+def plan_exchange(counts: np.ndarray, rank: int):
+    """counts[q, s] = log blocks rank q holds for slice s.  Slice s is owned by rank s % world.  Returns
+    (owned uint8[n_slices], send_slices, send_splits[world], recv_splits[world], runs[(slice, n_blocks)]):
+    this rank sends, to every other rank d, the blocks of d's slices in increasing slice order, and receives
+    from every other rank q the blocks of its own slices in the same order (runs, in arrival order)."""
+    world, n_slices = counts.shape
+    owned = np.fromiter((s % world == rank for s in range(n_slices)), dtype=np.uint8, count=n_slices)
+    send_slices, send_splits, recv_splits, runs = [], [], [], []
+    for d in range(world):
+        sl = [s for s in range(n_slices) if d != rank and s % world == d and counts[rank, s] > 0]
+        send_slices += sl
+        send_splits.append(int(sum(int(counts[rank, s]) for s in sl)))
+    for q in range(world):
+        tot = 0
+        if q != rank:
+            for s in range(n_slices):
+                if s % world == rank and counts[q, s] > 0:
+                    runs.append((s, int(counts[q, s])))
+                    tot += int(counts[q, s])
+        recv_splits.append(tot)
+    return owned, send_slices, send_splits, recv_splits, runs
+
+
+def exchange_feasible(counts: np.ndarray, info: np.ndarray) -> bool:
+    """Every rank evaluates the same predicate on the same gathered data: do the blocks every rank is about to
+    receive fit its pool and its per-slice block lists?  info[q] = (blocks used, blocks in pool, list capacity)."""
+    world, n_slices = counts.shape
+    if n_slices < world:
+        return False
+    for r in range(world):
+        incoming = sum(int(counts[q, s]) for q in range(world) if q != r for s in range(r, n_slices, world))
+        if int(info[r, 0]) + incoming > int(info[r, 1]):
+            return False
+        for s in range(r, n_slices, world):
+            if int(counts[:, s].sum()) > int(info[r, 2]):
+                return False
+    return True
+
+
+def exchange_hist(sketch, rBits: int, device, totals_out=None):
+    """The cheap reduction for inputs whose hit log is small against the sketch (10 M reads: 74 MB vs 1 GiB per
+    k): ranks swap log blocks so that rank r holds everything sampled into the slices it owns (one all-to-all),
+    each rank zeroes + applies + histograms ONLY its slices, and the 512 KiB/k histograms are all-reduced.
+    Returns p_hist uint32 [nK, 2, 65536] (identical on all ranks), or None when some rank's log is no longer
+    complete (it was flushed or overflowed) or the blocks would not fit -- then use reduce_scatter_hist.
+    totals_out: optional list; receives the per-k F1 summed over ranks (it rides on the same all-gather)."""
+    import os
+    import time
+    prof = os.environ.get("NTC_DIST_PROFILE") and dist.get_rank() == 0
+    t = [time.perf_counter()]
+
+    def lap(name):
+        if prof:
+            torch.cuda.synchronize(device)
+            t.append(time.perf_counter())
+            print(f"  exchange_hist {name}: {1e3 * (t[-1] - t[-2]):.3f} ms", flush=True)
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nblk, ok, info = sketch.log_counts()
+    f1 = sketch.totals_nosync()                            # final: log_counts waited for the scan kernels
+    lap("log_counts (sync)")
+    n_slices = len(nblk)
+    mine = torch.from_numpy(np.concatenate([nblk.astype(np.int64), np.asarray(info, dtype=np.int64), [1 if ok else 0],
+                                            f1.astype(np.int64)])).to(device)
+    allv = torch.empty(world * mine.numel(), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allv, mine)
+    allv = allv.cpu().numpy().reshape(world, -1)
+    lap("all_gather counts")
+    counts, infos, oks = allv[:, :n_slices], allv[:, n_slices:n_slices + 3], allv[:, n_slices + 3]
+    if totals_out is not None:
+        totals_out.append(allv[:, n_slices + 4:].sum(axis=0).astype(np.uint64))
+    if not oks.all() or not exchange_feasible(counts, infos):
+        return None
+    owned, send_slices, send_splits, recv_splits, runs = plan_exchange(counts, rank)
+    W = 260                                                # words per block on the wire (256 entries + fill + pad)
+    n_send, n_recv = sum(send_splits), sum(recv_splits)
+    send = _buffer(device, "send", n_send * W)
+    recv = _buffer(device, "recv", n_recv * W)
+    hist = _buffer(device, "hist", sketch.nK * 2 * 65536)
+    lap("plan + buffers")
+    sketch.log_export(send_slices, send.data_ptr())
+    sketch.stream_sync()                                   # the export ran on the sketch's stream
+    lap("export")
+    dist.all_to_all_single(recv[:n_recv * W], send[:n_send * W], [x * W for x in recv_splits], [x * W for x in send_splits])
+    torch.cuda.current_stream(device).synchronize()        # the import runs on the sketch's stream
+    lap(f"all_to_all ({n_send * W * 4 / 1e6:.1f} MB out)")
+    sketch.log_import(recv.data_ptr(), n_recv, runs)
+    sketch.flush_slices(owned)
+    sketch.hist_slices(owned, d_out=hist.data_ptr())
+    sketch.stream_sync()
+    lap("import + flush_slices + hist_slices")
+    h = hist[:sketch.nK * 2 * 65536]
+    dist.all_reduce(h, op=dist.ReduceOp.SUM)               # int32 on the device: a bin counts at most 2^rBits buckets
+    p = h.cpu().numpy().view(np.uint32).reshape(sketch.nK, 2, 65536).copy()
+    p[:, :, 0] = (1 << rBits) - p[:, :, 1:].sum(axis=2, dtype=np.uint64).astype(np.uint32)
+    lap("all_reduce hist")
+    return p
+
+
+_BUFFERS = {}
+
+
+def _buffer(device, name, n_words):
+    """Reusable int32 device buffers of the exchange (grown with slack, never shrunk)."""
+    key = (str(device), name)
+    buf = _BUFFERS.get(key)
+    if buf is None or buf.numel() < max(n_words, 1):
+        buf = torch.empty(max(int(n_words * 1.25), 1024), dtype=torch.int32, device=device)
+        _BUFFERS[key] = buf
+    return buf
