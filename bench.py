@@ -33,6 +33,8 @@ WORKLOADS = {
     "config3": (100_000_000, 150, [32, 64, 96, 128], 7, "config 3: 100M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27"),
     "config4": (125_000_000, 150, [64], 11, "config 4: 125M synthetic 150 bp reads per GPU, k=64, s=11, r=27"),
     "small": (1_000_000, 150, [32], 7, "dev: 1M synthetic 150 bp reads, k=32, s=7, r=27"),
+    "multik": (10_000_000, 150, [32, 64, 96, 128], 7, "dev: 10M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27"),
+    "k64s11": (10_000_000, 150, [64], 11, "dev: 10M synthetic 150 bp reads, k=64, s=11, r=27"),
 }
 RBITS = 27
 METRIC = "k-mers hashed/sec at k=32 on 150bp reads"

@@ -277,9 +277,7 @@ uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 		s.npos_max = max_len - k + 1;
 		if (s.npos_max > 65535)
 			continue;
-		uint32_t r = 64;
-		while (r < k + 16)
-			r <<= 1;
+		const uint32_t r = (k + 16 + 15) & ~15u; // plane ring: k + 16 positions, rounded up to whole columns
 		const size_t per_warp = (size_t)(r + 3) * 256; // ring + 3 mirror slots (scan_kernel.cuh)
 		const uint32_t nw = (uint32_t)std::min<size_t>(8, ntc::pl::kSmemMax / per_warp);
 		if (nw < 1)

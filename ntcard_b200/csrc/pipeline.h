@@ -51,7 +51,7 @@ struct Pool {                    // device pointers + geometry, passed by value
 };
 
 struct ScanLaunch {              // per-k constants of the scan kernel, passed by value
-	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (power of two >= k + 16)
+	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (k + 16 rounded up to a multiple of 16)
 	uint32_t npos_max;           // mask rows per tile
 	uint32_t F0[31], R0[31];     // initial bit-sliced state (bitslice_core.cuh init_state)
 };

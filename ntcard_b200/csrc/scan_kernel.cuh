@@ -39,7 +39,7 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p, uint64_t policy)
 }
 
 // Branch free on purpose: positions past the end of the read run on whatever the planes hold and store nothing.
-// Planes live in a ring of rmask+1 positions (slot = position mod ring size) followed by 3 slots that mirror slots
+// Planes live in a ring of R positions (R = k + 16 rounded up to 16; slot = position mod R) followed by 3 slots that mirror slots
 // 0..2, so the kScanBlock slots of a block can be addressed from one base without wrapping.  The k "virtual"
 // positions before the read (window not full yet) are the k slots before slot 0, zeroed at the start of a tile.
 // pin / pout / mb: plane slot of the block's first entering / leaving position, mask row of its first position.
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	if (warp >= L.nwarps)
 		return;
-	const int rmask = (int)L.ring - 1;
+	const int R = (int)L.ring; // multiple of 16, >= k + 16
 	uint2* planes = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * (L.ring + 3u) * 256u); // [position mod ring (+3 mirror slots)][lane]
 
 	uint64_t keep;
@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 		}
 		uint32_t cand = 0;
 		for (int j = 1; j <= k; j++) // the virtual positions -k..-1: no bases
-			planes[((-j) & rmask) * 32 + lane] = make_uint2(0u, 0u);
+			planes[(R - j) * 32 + lane] = make_uint2(0u, 0u);
+		int cin = 0, cout = R - k; // ring slots of the column's first entering position and of its first leaving position
 		// One column = one packed word of every record = 16 positions: transpose it into the plane ring, scan it.
 		// The next 16 bytes of every record are requested right after the last word of the current 16 bytes has
 		// been taken out of v[], so the loads fly during a whole column's scan.
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			bs::transpose32(A);
 			const int q0 = (int)(16u * w);
 			{
-				const int c0 = q0 & rmask;
+				const int c0 = cin;
 				uint2* dst = planes + c0 * 32 + lane; // a column never wraps: the ring size is a multiple of 16
 #pragma unroll
 				for (int j = 0; j < 16; j++)
@@ -212,17 +213,20 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 				if (c0 == 0) { // mirror of slots 0..2 behind the ring
 #pragma unroll
 					for (int j = 0; j < 3; j++)
-						dst[(rmask + 1 + j) * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
+						dst[(R + j) * 32] = make_uint2(A[2 * j], A[2 * j + 1]);
 				}
 			}
 			__syncwarp();
 			const int nq = min(16, n - q0);
 #pragma unroll 1
 			for (int qb = q0; qb < q0 + nq; qb += kScanBlock) {
-				ScanBlock<KM, S, 0>::run(st, planes + lane + (qb & rmask) * 32, planes + lane + ((qb - k) & rmask) * 32, mrow + qb * 32, qb, k, n,
-				    cand);
+				int ob = cout + (qb - q0);
+				ob = ob >= R ? ob - R : ob; // a block may start up to 3 slots before the end of the ring: mirror slots
+				ScanBlock<KM, S, 0>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, mrow + qb * 32, qb, k, n, cand);
 				scan_rotate_home(st);
 			}
+			cin = cin + 16 == R ? 0 : cin + 16;
+			cout = cout + 16 >= R ? cout + 16 - R : cout + 16;
 			__syncwarp();
 		}
 		cand_local += cand;
