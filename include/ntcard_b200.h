@@ -80,6 +80,11 @@ void ntc_destroy(ntc_ctx* ctx);
  * lazily, by the first flush. */
 int ntc_reset(ntc_ctx* ctx);
 int ntc_set_kernel(ntc_ctx* ctx, int kernel);
+/* Gap seeds, the reference's -g N (stRead / stHashIterator / NTMSM64, ntcard.cpp:160-171, 407-413; nthash.hpp:620-678):
+ * the middle `gap` bases of every k-mer are don't-cares, h = min(fh ^ Mf, rh ^ Mr).  One k only, gap and k of equal
+ * parity, gap <= k - 2 (the reference's own checks, ntcard.cpp:382, 397).  gap = 0 switches back.  Batches submitted
+ * afterwards use the general kernel. */
+int ntc_set_gap(ntc_ctx* ctx, unsigned gap);
 
 /* Submit one batch held in HOST memory (replaces n_rec calls of ntRead,
  * ntcard.cpp:182/203/230).  Pageable memory is copied to internal pinned

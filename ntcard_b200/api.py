@@ -18,7 +18,7 @@ KERNEL_AUTO, KERNEL_ROLL64, KERNEL_BITSLICE = 0, 1, 2
 
 # every symbol include/ntcard_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_submit", "ntc_submit_device", "ntc_wait",
+    "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_set_gap", "ntc_submit", "ntc_submit_device", "ntc_wait",
     "ntc_sync", "ntc_flush", "ntc_log_info", "ntc_log_counts", "ntc_log_export", "ntc_log_import", "ntc_flush_slices",
     "ntc_hist_slices", "ntc_stream_sync", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_totals_nosync", "ntc_set_totals", "ntc_finish", "ntc_estimate",
     "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
@@ -45,6 +45,7 @@ def _load():
         "ntc_destroy": (None, [vp]),
         "ntc_reset": (C.c_int, [vp]),
         "ntc_set_kernel": (C.c_int, [vp, C.c_int]),
+        "ntc_set_gap": (C.c_int, [vp, C.c_uint]),
         "ntc_submit": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, u64p]),
         "ntc_submit_device": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]),
         "ntc_wait": (C.c_int, [vp, C.c_uint64]),
@@ -225,6 +226,10 @@ class Sketch:
 
     def set_kernel(self, kernel):
         _check(lib.ntc_set_kernel(self.h, kernel))
+
+    def set_gap(self, gap):
+        """The reference's -g: spaced seed with `gap` don't-care bases in the middle (one k)."""
+        _check(lib.ntc_set_gap(self.h, gap))
 
     def submit(self, words, off=None, n_rec=None, stride=0):
         """Host batch.  words: uint32 array (numpy or PinnedBuffer.array slice); off: uint32[n_rec+1] or

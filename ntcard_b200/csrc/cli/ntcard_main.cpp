@@ -40,7 +40,8 @@ static const char USAGE_MESSAGE[] =
     "\n"
     "  -t, --threads=N	use N parallel reader threads [1] (N>=2 should be used when input files are >=2)\n"
     "  -k, --kmer=N	the length of kmer (comma separated list for several k in one pass)\n"
-    "  -g, --gap=N	gap seeds are not supported by the GPU path yet [0]\n"
+    "  -g, --gap=N	the length of gap in the gap seed [0]. g mod 2 must equal k mod 2 unless g == 0\n"
+    "           	-g does not support multiple k currently.\n"
     "  -c, --cov=N	the maximum coverage of kmer in output [1000]\n"
     "  -p, --pref=STRING    the prefix for output file name(s)\n"
     "  -o, --output=STRING	the name for output file name (used when output should be a single file)\n"
@@ -177,8 +178,16 @@ int main(int argc, char** argv)
 		std::cerr << PROGRAM ": missing argument -p/-o ... \n";
 		die = true;
 	}
-	if (opt::gap != 0) {
-		std::cerr << PROGRAM ": -g (gap seeds) is not supported by the GPU sketch path yet.\n";
+	if (opt::gap != 0 && !kList.empty() && (opt::gap % 2 != kList[0] % 2)) { // ntcard.cpp:382-385
+		std::cerr << PROGRAM "Gap size and kmer must have the same modulus\n";
+		die = true;
+	}
+	if (opt::gap != 0 && kList.size() != 1) { // ntcard.cpp:397-400
+		std::cerr << PROGRAM ": -g does not support multiple k currently.\n";
+		die = true;
+	}
+	if (opt::gap != 0 && !kList.empty() && opt::gap + 2 > kList[0]) {
+		std::cerr << PROGRAM ": -g must be smaller than k.\n";
 		die = true;
 	}
 	if (kList.size() > NTC_MAX_K) {
@@ -212,6 +221,8 @@ int main(int argc, char** argv)
 		die_ntc("cannot create the device sketch");
 	if (opt::kernel != NTC_KERNEL_AUTO && ntc_set_kernel(ctx, opt::kernel))
 		die_ntc("kernel");
+	if (opt::gap != 0 && ntc_set_gap(ctx, opt::gap)) // stRead instead of ntRead, ntcard.cpp:184-185, 204-205, 231-232
+		die_ntc("gap seed");
 	unsigned kmin = kList[0];
 	for (unsigned k : kList)
 		kmin = k < kmin ? k : kmin;

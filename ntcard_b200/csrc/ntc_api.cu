@@ -55,6 +55,7 @@ struct ntc_ctx {
 	unsigned nK = 0, rBits = 0, sBits = 0, kmin = 0, kmax = 0;
 	unsigned k[NTC_MAX_K] = {};
 	int kernel = NTC_KERNEL_AUTO;
+	unsigned gap = 0;  // -g: spaced seed with `gap` don't-care bases in the middle (general kernel only)
 	uint32_t* d_counters = nullptr;
 	bool own_counters = false;
 	size_t n_counters = 0;
@@ -166,6 +167,17 @@ void build_params(const ntc_ctx* c, ntc::DevParams* P)
 				P->tab[ki].xr[in | out << 2] = ntc::srol_n(ntc::seed_of(3 - in), k) ^ ntc::seed_of(3 - out);
 			}
 	}
+	P->gap = c->gap;
+	if (c->gap) { // gap seeds: rolling constants of the inner window, rotation a = (k - gap) / 2 (sketch_common.cuh)
+		const unsigned a = (c->k[0] - c->gap) / 2, g = c->gap;
+		P->gap_a31 = a % 31;
+		P->gap_a33 = a % 33;
+		for (unsigned in = 0; in < 4; in++)
+			for (unsigned out = 0; out < 4; out++) {
+				P->gtab.xf[in | out << 2] = ntc::seed_of(in) ^ ntc::srol_n(ntc::seed_of(out), g);
+				P->gtab.xr[in | out << 2] = ntc::srol_n(ntc::seed_of(3 - in), g) ^ ntc::seed_of(3 - out);
+			}
+	}
 }
 
 // ---- sketch pipeline -------------------------------------------------------------------------------------
@@ -259,7 +271,7 @@ struct PipeShape {
 // Which k indices the scan -> hit -> apply pipeline can take for this batch.
 uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, PipeShape* shape)
 {
-	if (!c->use_pipeline || c->kernel == NTC_KERNEL_ROLL64 || b.off || !record_is_piece || b.stride < 4 || (b.stride & 3u) || b.n_rec < 1024 ||
+	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || b.off || !record_is_piece || b.stride < 4 || (b.stride & 3u) || b.n_rec < 1024 ||
 	    (reinterpret_cast<uintptr_t>(b.words) & 15u))
 		return 0;
 	uint32_t kmask = 0;
@@ -657,6 +669,28 @@ int ntc_reset(ntc_ctx* c)
 	c->totals_overridden = false;
 	c->pending = true;
 	c->partial = false;
+	return NTC_OK;
+}
+
+int ntc_set_gap(ntc_ctx* c, unsigned gap)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	if (gap != 0) {
+		if (c->nK != 1)
+			return set_err(NTC_EINVAL, "ntc_set_gap: gap seeds support one k only (ntcard.cpp:397)");
+		if (gap % 2 != c->k[0] % 2)
+			return set_err(NTC_EINVAL, "ntc_set_gap: gap size and k must have the same modulus (ntcard.cpp:382)");
+		if (gap + 2 > c->k[0])
+			return set_err(NTC_EINVAL, "ntc_set_gap: gap %u does not fit k = %u", gap, c->k[0]);
+	}
+	int rc;
+	if ((rc = ntc_sync(c))) // batches already submitted keep the old seed
+		return rc;
+	c->gap = gap;
+	ntc::DevParams hp;
+	build_params(c, &hp);
+	CK(cudaMemcpy(c->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
 	return NTC_OK;
 }
 

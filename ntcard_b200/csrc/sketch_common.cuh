@@ -20,6 +20,9 @@ struct DevParams {
 	uint32_t nK, rBits, sBits, kmin;
 	uint32_t k[NTC_MAX_K];
 	KTab tab[NTC_MAX_K];
+	// gap seeds (-g, stRead ntcard.cpp:160-171): gap > 0 only with nK == 1
+	uint32_t gap, gap_a31, gap_a33, pad_;   // a = (k - gap) / 2 ones on either side of the gap; a % 31, a % 33
+	KTab gtab;                               // rolling constants of the gap-long inner window
 };
 
 // k-mer starts handled by one thread of the general kernel ("piece").  Long records are cut into
@@ -99,6 +102,65 @@ __device__ __forceinline__ uint32_t process_piece_k(const uint32_t* __restrict__
 		sample_and_count(rh < fh ? rh : fh, ctr_k, rBits, sBits);
 	}
 	return e - a;
+}
+
+// ---- gap seeds -------------------------------------------------------------------------------------------------
+// NTMSM64 (nthash.hpp:620-678, one seed, one hash) XORs the contribution of every '0' position i of the seed out of
+// the plain hashes: fs = fh ^ srol^(k-1-i) seed[c_i], rs = rh ^ srol^i seed[comp c_i], h = min(fs, rs).  The seed of
+// ntcard.cpp:407-413 is a ones, gap zeros, a ones (k = 2a + gap), so the zero positions are the inner window
+// [a, a + gap) and their contributions are the ntHash of that window rotated by a:
+//   XOR_j srol^(k-1-a-j) seed[c_(a+j)] = srol^a( XOR_j srol^(gap-1-j) seed[c_(a+j)] ) = srol^a( NTF64 of the inner window )
+//   XOR_j srol^(a+j) seed[comp c_(a+j)]                                              = srol^a( NTR64 of the inner window )
+// i.e. a second rolling hash of length gap instead of 2*gap table lookups per k-mer.
+__device__ __forceinline__ uint64_t srol_by(uint64_t v, uint32_t a31, uint32_t a33)
+{
+	uint64_t hi = v >> 33, lo = v & 0x1FFFFFFFFull;
+	hi = ((hi << a31) | (hi >> (31u - a31))) & 0x7FFFFFFFull;
+	lo = ((lo << a33) | (lo >> (33u - a33))) & 0x1FFFFFFFFull;
+	return (hi << 33) | lo;
+}
+
+__device__ __forceinline__ uint32_t process_piece_gap(const uint32_t* __restrict__ b, uint32_t len, uint32_t a0, uint32_t k, uint32_t gap,
+    uint32_t a31, uint32_t a33, const KTab& T, const KTab& G, uint32_t* __restrict__ ctr_k, uint32_t rBits, uint32_t sBits)
+{
+	if (len < k)
+		return 0;
+	const uint32_t ns = len - k + 1;
+	if (a0 >= ns)
+		return 0;
+	const uint32_t e = min(a0 + PIECE_STARTS, ns);
+	const uint32_t a = (k - gap) / 2;
+	uint64_t fh = 0, rh = 0, fg = 0, rg = 0;
+	for (uint32_t i = 0; i < k; i++)
+		fh = srol(fh) ^ seed_of(base_at(b, a0 + i));
+	for (uint32_t i = k; i-- > 0;)
+		rh = srol(rh) ^ seed_of(3u - base_at(b, a0 + i));
+	for (uint32_t i = 0; i < gap; i++)
+		fg = srol(fg) ^ seed_of(base_at(b, a0 + a + i));
+	for (uint32_t i = gap; i-- > 0;)
+		rg = srol(rg) ^ seed_of(3u - base_at(b, a0 + a + i));
+	{
+		const uint64_t fs = fh ^ srol_by(fg, a31, a33), rs = rh ^ srol_by(rg, a31, a33);
+		sample_and_count(rs < fs ? rs : fs, ctr_k, rBits, sBits);
+	}
+	BaseStream so, si, go, gi;
+	so.open(b, a0);
+	go.open(b, a0 + a);
+	if (a0 + 1 < e) {
+		si.open(b, a0 + k);
+		gi.open(b, a0 + a + gap);
+	}
+	for (uint32_t j = a0 + 1; j < e; j++) {
+		const uint32_t idx = si.next() | (so.next() << 2);
+		fh = srol(fh) ^ T.xf[idx];
+		rh = sror(rh ^ T.xr[idx]);
+		const uint32_t gidx = gi.next() | (go.next() << 2);
+		fg = srol(fg) ^ G.xf[gidx];
+		rg = sror(rg ^ G.xr[gidx]);
+		const uint64_t fs = fh ^ srol_by(fg, a31, a33), rs = rh ^ srol_by(rg, a31, a33);
+		sample_and_count(rs < fs ? rs : fs, ctr_k, rBits, sBits);
+	}
+	return e - a0;
 }
 
 #endif

@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(256) roll64_kernel(const uint32_t* __restrict_
 		for (uint32_t ki = 0; ki < sp.nK; ki++) {
 			if (!((kmask >> ki) & 1u))
 				continue;
-			uint32_t n = process_piece_k(r + 1, len, a, sp.k[ki], sp.tab[ki], counters + ki * tab_stride, sp.rBits, sp.sBits);
+			uint32_t n = sp.gap ? process_piece_gap(r + 1, len, a, sp.k[ki], sp.gap, sp.gap_a31, sp.gap_a33, sp.tab[ki], sp.gtab,
+			                          counters + ki * tab_stride, sp.rBits, sp.sBits)
+			                    : process_piece_k(r + 1, len, a, sp.k[ki], sp.tab[ki], counters + ki * tab_stride, sp.rBits, sp.sBits);
 			if (n)
 				atomicAdd(&s_f1[ki], (unsigned long long)n);
 		}

@@ -35,7 +35,59 @@ def rand_seq(rng, L, alphabet=b"ACGT", junk=0.0, junk_chars=b"NnXRY-.*"):
     return bytes(out)
 
 
+def gap_golden():
+    """tests/golden/gap_cases.json: the reference's gap-seed mode (-g; stRead / stHashIterator / NTMSM64,
+    ntcard.cpp:160-171, 407-413; nthash.hpp:620-678) -- hash vectors, sketch digests, CLI output."""
+    build(ref=True)
+    orc, ref = Oracle(), Reference()
+
+    def gen(S, n, L, mode=0, U=0):
+        a = orc.gen_reads(S, 0, n, L, mode, U)
+        return [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+
+    out = {"source": "stRead / stHashIterator / NTMSM64 of the unmodified reference via oracle/_ref (ref_set_gap builds the seed the way "
+                     "ntcard.cpp:407-413 does); reads from the SURVEY 8d generator", "hashes": [], "sketches": [], "cli": {}}
+    seq = b"GAGTGTCAAACATTCAGACAACAGCAGGGGTGCTCTGGAATCCTATGTGAGGAACAAACATTCAGGCCACAGTAGNACGTTGCATGCCAGTNNACGATCGATCGGATCGATTACGAT"
+    for k, g in ((12, 2), (20, 18), (31, 5), (32, 8), (33, 1), (64, 32)):
+        h = ref.st_hash_seq(seq, k, g)
+        out["hashes"].append({"seq": seq.decode(), "k": k, "gap": g, "h": [f"{int(x):#018x}" for x in h]})
+    for name, reads, k, g, rBits, sBits in (("rep_k12_g2", gen(11, 4000, 150, 1, 500), 12, 2, 16, 3),
+                                            ("rep_k32_g8", gen(12, 4000, 150, 1, 500), 32, 8, 18, 7),
+                                            ("nmode_k31_g5", gen(4, 2000, 400, 2, 0), 31, 5, 18, 7),
+                                            ("uni_k64_g32", gen(13, 3000, 150, 0, 0), 64, 32, 18, 7)):
+        sk, tot = ref.sketch_reads_gap(reads, k, g, rBits, sBits, nthreads=4)
+        rB = 1 << rBits
+        tabs = []
+        for t in range(2):
+            d = orc.table_digest(np.ascontiguousarray(sk[t * rB:(t + 1) * rB]))
+            d["digest"] = f"{d['digest']:#018x}"
+            tabs.append(d)
+        F0, fm = ref.compest(np.ascontiguousarray(sk), rBits, sBits)
+        out["sketches"].append({"name": name, "k": k, "gap": g, "rBits": rBits, "sBits": sBits, "F1": int(tot[0]), "tables": tabs,
+                                "est": {"F0": float(F0), "f": [float(x) for x in fm[1:65]]}})
+    out["gens"] = {"rep_k12_g2": [11, 4000, 150, 1, 500], "rep_k32_g8": [12, 4000, 150, 1, 500], "nmode_k31_g5": [4, 2000, 400, 2, 0],
+                   "uni_k64_g32": [13, 3000, 150, 0, 0]}
+    with tempfile.TemporaryDirectory() as td:
+        reads = gen(1, 20000, 150, 1, 2500)
+        fq = os.path.join(td, "a.fq")
+        with open(fq, "w") as f:
+            for i, r in enumerate(reads):
+                f.write(f"@r{i}\n{r.decode()}\n+\n{'I' * len(r)}\n")
+        for tag, args in (("fq_k12_g2_c50", ["-k12", "-g2", "-c50"]), ("fq_k32_g8_c20", ["-k32", "-g8", "-c20"])):
+            pref = os.path.join(td, "out")
+            subprocess.run([REF_CLI] + args + ["-p", pref, fq], capture_output=True, text=True, check=True)
+            k = args[0][2:]
+            with open(os.path.join(td, f"out_k{k}.hist")) as f:
+                out["cli"][tag] = f.read()
+        out["cli"]["gen_a"] = {"S": 1, "n": 20000, "L": 150, "mode": 1, "U": 2500}
+    with open(os.path.join(GOLD, "gap_cases.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("gap_cases.json", os.path.getsize(os.path.join(GOLD, "gap_cases.json")))
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "gap":
+        return gap_golden()
     build(ref=True)
     os.makedirs(GOLD, exist_ok=True)
     ref = Reference()

@@ -281,6 +281,63 @@ void orc_ntread_batch(const char* seqs, const uint64_t* off, size_t n, const uns
 	}
 }
 
+/* ---- gap seeds (-g N): stRead, ntcard.cpp:160-171, with the spaced seed 1..10..01..1 of ntcard.cpp:407-413 ----
+ * stHashIterator (stHashIterator.hpp:60-94) walks the sequence like ntHashIterator; per window NTMSM64
+ * (nthash.hpp:620-678, m = m2 = 1) takes the plain fh/rh and XORs the contribution of every '0' position i
+ * of the seed back out:  fs = fh ^ srol^(k-1-i)(seed[c_i]),  rs = rh ^ srol^i(seed[comp c_i]);  h = min(fs, rs).
+ * The seed string has (k-gap)/2 ones, gap zeros, (k-gap)/2 ones (k and gap of equal parity, ntcard.cpp:382). */
+static inline uint64_t orc_st_hash(const char* w, unsigned k, unsigned gap, uint64_t fh, uint64_t rh)
+{
+	const unsigned a = (k - gap) / 2;
+	uint64_t fs = fh, rs = rh;
+	for (unsigned i = a; i < a + gap; i++) {
+		fs ^= orc_srol_n(orc_seed((unsigned char)w[i]), k - 1 - i);
+		rs ^= orc_srol_n(orc_seed((unsigned char)w[i] & 7), i);
+	}
+	return rs < fs ? rs : fs;
+}
+
+static void orc_stread_impl(const char* seq, size_t len, unsigned k, unsigned gap, unsigned rBits, unsigned sBits, uint16_t* t,
+    uint64_t* totKmer, int atomic)
+{
+	orc_iter it = { seq, len, k, 0, 0, 0 }; /* the position logic of stHashIterator::init/next equals ntHashIterator's */
+	orc_iter_init(&it);
+	while (it.pos != SIZE_MAX) {
+		orc_ntcomp(orc_st_hash(seq + it.pos, k, gap, it.fh, it.rh), t, rBits, sBits, atomic);
+		orc_iter_next(&it);
+		++totKmer[0];
+	}
+}
+
+/* All gap-seed hashes of a sequence in iterator order (unit tests). */
+size_t orc_st_hash_seq(const char* seq, size_t len, unsigned k, unsigned gap, uint64_t* out_h, size_t cap)
+{
+	orc_iter it = { seq, len, k, 0, 0, 0 };
+	size_t n = 0;
+	orc_iter_init(&it);
+	while (it.pos != SIZE_MAX) {
+		if (n < cap)
+			out_h[n] = orc_st_hash(seq + it.pos, k, gap, it.fh, it.rh);
+		++n;
+		orc_iter_next(&it);
+	}
+	return n;
+}
+
+void orc_stread_batch(const char* seqs, const uint64_t* off, size_t n, unsigned k, unsigned gap, unsigned rBits, unsigned sBits,
+    uint16_t* t, uint64_t* totKmer, int nthreads)
+{
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+	{
+		uint64_t loc = 0;
+#pragma omp for schedule(dynamic, 4096)
+		for (size_t i = 0; i < n; i++)
+			orc_stread_impl(seqs + off[i], off[i + 1] - off[i], k, gap, rBits, sBits, t, &loc, 1);
+#pragma omp atomic
+		totKmer[0] += loc;
+	}
+}
+
 /* compEst: ntcard.cpp:237-275.  f must hold 65536 doubles.  imax (2..65535)
  * truncates the recurrence; f[i] for i <= imax is identical to the full run
  * because f[i] depends only on f[j], j < i (ntcard.cpp:266-272).

@@ -94,6 +94,9 @@ class Oracle(_Lib):
         L.orc_table_digest.restype = C.c_uint64
         L.orc_table_digest.argtypes = [_u16p, C.c_uint64, _u64p, _u64p, _u32p, _u64p]
         L.orc_max_threads.restype = C.c_int
+        L.orc_st_hash_seq.restype = C.c_size_t
+        L.orc_st_hash_seq.argtypes = [C.c_char_p, C.c_size_t, C.c_uint, C.c_uint, _u64p, C.c_size_t]
+        L.orc_stread_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _u16p, _u64p, C.c_int]
 
     def srol_n(self, v, n):
         return self.lib.orc_srol_n(v, n)
@@ -124,6 +127,29 @@ class Oracle(_Lib):
         np.cumsum(lens, out=off[1:])
         buf = np.frombuffer(b"".join(reads) + b"\0", dtype=np.uint8)
         self.ntread_batch(buf, off, kList, rBits, sBits, sk, tot, nthreads)
+        return sk, tot
+
+    def _flat(self, reads):
+        lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        return np.frombuffer(b"".join(reads) + b"\0", dtype=np.uint8), off
+
+    def st_hash_seq(self, seq: bytes, k, gap):
+        """Gap-seed hashes (stHashIterator + NTMSM64) of a sequence, iterator order."""
+        cap = max(len(seq), 1)
+        h = np.zeros(cap, dtype=np.uint64)
+        self.lib.orc_st_hash_seq.restype = C.c_size_t
+        n = self.lib.orc_st_hash_seq(seq, C.c_size_t(len(seq)), C.c_uint(k), C.c_uint(gap), _ptr(h, _u64p), C.c_size_t(cap))
+        return h[:n].copy()
+
+    def sketch_reads_gap(self, reads, k, gap, rBits, sBits, nthreads=1):
+        """stRead (ntcard.cpp:160-171) over reads with the -g seed.  Returns (sketch uint16 [2*2^r], totKmer uint64 [1])."""
+        sk = self.new_sketch(1, rBits)
+        tot = np.zeros(1, dtype=np.uint64)
+        buf, off = self._flat(reads)
+        self.lib.orc_stread_batch(buf.ctypes.data, _ptr(off, _u64p), C.c_size_t(len(off) - 1), C.c_uint(k), C.c_uint(gap),
+                                  C.c_uint(rBits), C.c_uint(sBits), _ptr(sk, _u16p), _ptr(tot, _u64p), C.c_int(nthreads))
         return sk, tot
 
     def compest(self, sketch=None, p_hist=None, rBits=27, sBits=7, imax=65535):
@@ -174,6 +200,11 @@ class Reference(_Lib):
         L.ref_ntread_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, _u32p, C.c_uint, _u16p, _u64p, C.c_int]
         L.ref_compest.argtypes = [_u16p, _dblp, _dblp]
         L.ref_max_threads.restype = C.c_int
+        if hasattr(L, "ref_set_gap"):  # an oracle/_ref built before the gap-seed shims lacks them
+            L.ref_set_gap.argtypes = [C.c_uint, C.c_uint]
+            L.ref_st_hash_seq.restype = C.c_size_t
+            L.ref_st_hash_seq.argtypes = [C.c_char_p, C.c_size_t, C.c_uint, _u64p, C.c_size_t]
+            L.ref_stread_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_uint, _u16p, _u64p, C.c_int]
 
     @staticmethod
     def available():
@@ -204,6 +235,30 @@ class Reference(_Lib):
         np.cumsum(lens, out=off[1:])
         buf = np.frombuffer(b"".join(reads) + b"\0", dtype=np.uint8)
         self.ntread_batch(buf, off, kList, sk, tot, nthreads)
+        return sk, tot
+
+    def st_hash_seq(self, seq: bytes, k, gap):
+        self.lib.ref_set_gap(C.c_uint(k), C.c_uint(gap))
+        cap = max(len(seq), 1)
+        h = np.zeros(cap, dtype=np.uint64)
+        self.lib.ref_st_hash_seq.restype = C.c_size_t
+        n = self.lib.ref_st_hash_seq(seq, C.c_size_t(len(seq)), C.c_uint(k), _ptr(h, _u64p), C.c_size_t(cap))
+        self.lib.ref_set_gap(C.c_uint(k), C.c_uint(0))
+        return h[:n].copy()
+
+    def sketch_reads_gap(self, reads, k, gap, rBits, sBits, nthreads=1):
+        """The reference's own stRead with the seed main() builds for -g (ntcard.cpp:407-413)."""
+        self.set_opts(rBits, sBits, 1)
+        self.lib.ref_set_gap(C.c_uint(k), C.c_uint(gap))
+        sk = np.zeros(2 * (1 << rBits), dtype=np.uint16)
+        tot = np.zeros(1, dtype=np.uint64)
+        lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        buf = np.frombuffer(b"".join(reads) + b"\0", dtype=np.uint8)
+        self.lib.ref_stread_batch(buf.ctypes.data, _ptr(off, _u64p), C.c_size_t(len(off) - 1), C.c_uint(k), _ptr(sk, _u16p),
+                                  _ptr(tot, _u64p), C.c_int(nthreads))
+        self.lib.ref_set_gap(C.c_uint(k), C.c_uint(0))
         return sk, tot
 
     def compest(self, sketch, rBits, sBits):

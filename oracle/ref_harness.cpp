@@ -117,6 +117,54 @@ ref_ntread_batch(const char* seqs, const uint64_t* off, size_t n, const unsigned
 	return omp_get_wtime() - t0;
 }
 
+/* Gap-seed mode: the globals main() sets at ntcard.cpp:407-413, then the reference's own stRead (ntcard.cpp:160-171). */
+void
+ref_set_gap(unsigned k, unsigned gap)
+{
+	opt::gap = gap;
+	opt::seedSet.clear();
+	if (gap != 0) {
+		std::string g(gap, '0');
+		std::string nonGap((k - gap) / 2, '1');
+		std::vector<std::string> seedString;
+		seedString.push_back(nonGap + g + nonGap);
+		opt::seedSet = stHashIterator::parseSeed(seedString);
+	}
+}
+
+void
+ref_stread_batch(const char* seqs, const uint64_t* off, size_t n, unsigned k, uint16_t* t, uint64_t* totKmer, int nthreads)
+{
+	std::vector<unsigned> kl(1, k);
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+	{
+		size_t tot[1] = { 0 };
+		std::string s;
+#pragma omp for schedule(dynamic, 4096)
+		for (size_t i = 0; i < n; i++) {
+			s.assign(seqs + off[i], off[i + 1] - off[i]);
+			stRead(s, kl, t, tot);
+		}
+#pragma omp atomic
+		totKmer[0] += tot[0];
+	}
+}
+
+size_t
+ref_st_hash_seq(const char* seq, size_t len, unsigned k, uint64_t* out_h, size_t cap)
+{
+	std::string s(seq, len);
+	stHashIterator itr(s, opt::seedSet, 1, 1, k);
+	size_t n = 0;
+	while (itr != itr.end()) {
+		if (n < cap)
+			out_h[n] = (*itr)[0];
+		++n;
+		++itr;
+	}
+	return n;
+}
+
 void
 ref_compest(const uint16_t* t, double* F0Mean, double* fMean /* [65536] */)
 {

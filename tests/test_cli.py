@@ -35,8 +35,10 @@ def test_cli_usage_errors(tmp_path):
     assert r.returncode == 0 and "Usage: ntCard [OPTION]... FILE(S)..." in r.stderr
     r = run(["--version"])
     assert r.returncode == 0 and "ntCard 1.2.2" in r.stderr
-    r = run(["-k12", "-g", "2", "-p", "o", "x.fq"])
-    assert r.returncode == 1 and "gap" in r.stderr
+    r = run(["-k12", "-g", "3", "-p", "o", "x.fq"])          # ntcard.cpp:382-385
+    assert r.returncode == 1 and "Gap size and kmer must have the same modulus" in r.stderr
+    r = run(["-k12,32", "-g", "2", "-p", "o", "x.fq"])       # ntcard.cpp:397-400
+    assert r.returncode == 1 and "-g does not support multiple k currently" in r.stderr
 
 
 def write_inputs(td, cases):
