@@ -221,8 +221,7 @@ __device__ __forceinline__ bool append(const GroupSmem& sm, const HitArgs& a, ui
 	}
 	const uint32_t slot = atomicAdd(&sm.fill[b], 1u);
 	if (slot < kBlkEntries) {
-		if (!(P.dbg & 16u))
-			P.entries[(size_t)cu * kBlkEntries + slot] = idx;
+		P.entries[(size_t)cu * kBlkEntries + slot] = idx;
 		return true;
 	}
 	return false;
@@ -276,8 +275,7 @@ __device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs
 				uint32_t rec, rl, p;
 				decode(a, U, sm.queue[i], rec, rl, p);
 				const uint32_t* rw = kStaged ? sm.tile + rl * c.stride + 1 : c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1;
-				if (!(P.dbg & 32u))
-					h[u] = hit_issue<kStaged>(c, rw, p, last);
+				h[u] = hit_issue<kStaged>(c, rw, p, last);
 			}
 		}
 #pragma unroll
@@ -287,9 +285,7 @@ __device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs
 				uint32_t rec, rl, p;
 				decode(a, U, sm.queue[i], rec, rl, p);
 				const uint32_t* rw = kStaged ? sm.tile + rl * c.stride + 1 : c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1;
-				uint32_t idx = rec < a.n_rec ? hit_finish<kStaged>(c, h[u], rw, p, last) : kVoid;
-				if (P.dbg & 32u)
-					idx = (rec * 2654435761u + p * 40503u) & ((2u << P.rBits) - 1u);
+				const uint32_t idx = rec < a.n_rec ? hit_finish<kStaged>(c, h[u], rw, p, last) : kVoid;
 				uint32_t after = 0;
 				if (idx != kVoid && !append(sm, a, idx)) {
 					after = idx | kPendingBit;
@@ -458,7 +454,7 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_
 		}
 		if (!sm.scal[1]) {
 			const uint32_t n = sm.scal[0];
-			if (n && !(a.pool.dbg & 64u))
+			if (n)
 				process_queue<kStaged>(sm, a, c, n, U, g, gtid, sp);
 		} else {
 			// skewed data: more candidates than the queue holds -> two mask rows (<= 2048 candidates) per round
@@ -584,7 +580,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 		const size_t a0 = n16 * blockIdx.x / gridDim.x, a1 = n16 * (blockIdx.x + 1) / gridDim.x;
 		for (uint32_t si = 0; si < NS; si++) {
 			const uint32_t s = order ? order[si] : si;
-			if (si >= kApplyAhead && !(P.dbg & 4u)) { // L2 footprint: do not run more than kApplyAhead slices ahead of the appliers
+			if (si >= kApplyAhead) { // L2 footprint: do not run more than kApplyAhead slices ahead of the appliers
 				if (rtid == 0)
 					while (ld_acquire(P.apply_done + si - kApplyAhead) < gridDim.x)
 						__nanosleep(20);
@@ -592,9 +588,8 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 			}
 			uint4* p = reinterpret_cast<uint4*>(counters + (size_t)(s / P.nbins) * per_k + (size_t)(s % P.nbins) * slice_len);
 			if (zero_mode) {
-				if (!(P.dbg & 8u))
-					for (size_t i = a0 + rtid; i < a1; i += nrt)
-						p[i] = make_uint4(0u, 0u, 0u, 0u);
+				for (size_t i = a0 + rtid; i < a1; i += nrt)
+					p[i] = make_uint4(0u, 0u, 0u, 0u);
 				role_sync(role);
 				if (rtid == 0) {
 					__threadfence();
@@ -636,7 +631,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 			if (si + 1 < NS)
 				load_block(sn, j0, nbn, vn);
 			if (nb) {
-				if (zero_mode && !(P.dbg & 2u)) {
+				if (zero_mode) {
 					if (rtid == 0)
 						while (ld_acquire(P.zero_done + si) < gridDim.x)
 							__nanosleep(20);
@@ -645,7 +640,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 				uint32_t* ctr = counters + (size_t)(s / P.nbins) * per_k;
 #pragma unroll
 				for (int u = 0; u < kV; u++)
-					if (v[u] != kVoid && !(P.dbg & 1u))
+					if (v[u] != kVoid)
 						atomicAdd(ctr + v[u], 1u); // RED.ADD, L2 resident
 				for (uint32_t j = j0 + jstep; j < nb; j += jstep) { // more blocks than warps: the rest, unpipelined
 					load_block(s, j, nb, v);

@@ -21,6 +21,13 @@ struct BatchView {          // a packed record stream resident in device memory
 size_t piece_scan_temp_bytes(uint32_t n_items);
 cudaError_t launch_piece_tables(const BatchView& b, uint32_t kmin, uint32_t* d_piece_first, uint32_t* d_piece_rec, void* d_tmp,
     size_t tmp_bytes, cudaStream_t st);
+// Long ragged records -> uniform pieces of Lp bases every D bases (+ ragged tails); see sketch_kernels.cu.  After
+// launch_retile_count the three arrays hold exclusive prefix sums (entry n_rec = totals).
+cudaError_t launch_retile_count(const BatchView& b, uint32_t Lp, uint32_t D, uint32_t kmin, uint32_t* d_n_full, uint32_t* d_has_tail,
+    uint32_t* d_tail_words, void* d_tmp, size_t tmp_bytes, cudaStream_t st);
+cudaError_t launch_retile_fill(const BatchView& b, uint32_t Lp, uint32_t D, uint32_t stride, const uint32_t* d_full_first,
+    const uint32_t* d_tail_idx, const uint32_t* d_tail_first, uint32_t* d_out_uniform, uint32_t* d_out_tail_words, uint32_t* d_out_tail_off,
+    int n_sm, cudaStream_t st);
 cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
     const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t* d_counters, unsigned long long* d_f1, uint32_t kmask,
     int n_sm, cudaStream_t st);

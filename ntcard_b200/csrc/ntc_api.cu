@@ -77,6 +77,16 @@ struct ntc_ctx {
 	size_t cap_piece_rec = 0;
 	void* d_scan_tmp = nullptr;
 	size_t cap_scan_tmp = 0;
+	// re-tiling of long ragged records (sketch_kernels.cu)
+	uint32_t* d_rt_counts = nullptr;   // [3][n_rec + 1]: full pieces, tail flags, tail words (prefix sums)
+	size_t cap_rt_counts = 0;
+	uint32_t* d_rt_uniform = nullptr;
+	size_t cap_rt_uniform = 0;
+	uint32_t* d_rt_tail_words = nullptr;
+	size_t cap_rt_tail_words = 0;
+	uint32_t* d_rt_tail_off = nullptr;
+	size_t cap_rt_tail_off = 0;
+	uint64_t n_retiled = 0;
 	// sketch pipeline (scan -> hit log -> apply), pipeline.h
 	ntc::pl::Pool pool{};
 	uint32_t* d_pool_ctl_region = nullptr; // ctl + slice_nblk + zero_done + apply_done + cand, one allocation (zeroed by reset)
@@ -190,7 +200,6 @@ int pool_create(ntc_ctx* c)
 	P.rBits = c->rBits;
 	P.nK = c->nK;
 	P.ahead = getenv("NTC_APPLY_AHEAD") ? (uint32_t)atoi(getenv("NTC_APPLY_AHEAD")) : 2u;
-	P.dbg = getenv("NTC_PL_DEBUG") ? (uint32_t)strtoul(getenv("NTC_PL_DEBUG"), nullptr, 0) : 0u;
 	const uint32_t idx_bits = c->rBits + 1;
 	{
 		const uint32_t ss = getenv("NTC_SLICE_SHIFT") ? (uint32_t)atoi(getenv("NTC_SLICE_SHIFT")) : 23u; // 2^23 counters = 32 MiB
@@ -264,14 +273,14 @@ int flush(ntc_ctx* c)
 }
 
 struct PipeShape {
-	uint32_t ring = 0, nwarps = 0, npos_max = 0, rows_per_unit = 64, units_per_tile = 1, tiles_per_unit = 1;
+	uint32_t ring = 0, nwarps = 0, npos_max = 0, rows_per_unit = 64, units_per_tile = 1, tiles_per_unit = 1, start_limit = 0;
 	size_t smem = 0;
 };
 
 // Which k indices the scan -> hit -> apply pipeline can take for this batch.
-uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, PipeShape* shape)
+uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, PipeShape* shape, uint32_t min_rec = 1024)
 {
-	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || b.off || !record_is_piece || b.stride < 4 || (b.stride & 3u) || b.n_rec < 1024 ||
+	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || b.off || !record_is_piece || b.stride < 4 || (b.stride & 3u) || b.n_rec < min_rec ||
 	    (reinterpret_cast<uintptr_t>(b.words) & 15u))
 		return 0;
 	uint32_t kmask = 0;
@@ -360,6 +369,7 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	sa.L.ring = sh.ring;
 	sa.L.nwarps = sh.nwarps;
 	sa.L.npos_max = sh.npos_max;
+	sa.L.start_limit = sh.start_limit;
 	memcpy(sa.L.F0, c->kinit[ki].F0, sizeof sa.L.F0);
 	memcpy(sa.L.R0, c->kinit[ki].R0, sizeof sa.L.R0);
 	sa.masks = c->d_masks;
@@ -410,6 +420,106 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	return NTC_OK;
 }
 
+// The general kernel over one batch for the k indices in kmask (direct increments: the caller has flushed).
+int run_roll64(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, uint32_t kmask)
+{
+	int rc;
+	uint64_t bound = 0;
+	if (!record_is_piece) {
+		bound = (uint64_t)b.n_rec + (16 * b.n_words) / ntc::PIECE_STARTS + 1;
+		if (bound > 0xFFFFFFFFull)
+			return set_err(NTC_EINVAL, "batch too large: %llu pieces", (unsigned long long)bound);
+		if ((rc = grow(&c->d_piece_first, &c->cap_piece_first, (size_t)b.n_rec + 1, false)) ||
+		    (rc = grow(&c->d_piece_rec, &c->cap_piece_rec, (size_t)bound, false)))
+			return rc;
+		size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
+		char* t = (char*)c->d_scan_tmp;
+		if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
+			return rc;
+		c->d_scan_tmp = t;
+		CK(ntc::launch_piece_tables(b, c->kmin, c->d_piece_first, c->d_piece_rec, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
+		c->n_launches += 3;
+	}
+	CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters, c->d_f1, kmask, c->n_sm,
+	    c->stream));
+	c->n_launches += 1;
+	return NTC_OK;
+}
+
+// Long ragged records (long reads, contigs split at N): cut them on the device into equal pieces of Lp bases every D bases
+// for the pipeline, plus one ragged tail per record for the general kernel.  Returns the k indices that were handled.
+int run_retiled(ntc_ctx* c, const ntc::BatchView& b, uint32_t* handled)
+{
+	*handled = 0;
+	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || !b.off || b.n_rec == 0 || getenv("NTC_NO_RETILE"))
+		return NTC_OK;
+	if (b.n_words / b.n_rec < 40) // average record below ~600 bases: pieces would mostly be tails
+		return NTC_OK;
+	uint32_t kmask = 0, kmax = 0, kmin = 0xFFFFFFFFu;
+	for (unsigned ki = 0; ki < c->nK; ki++)
+		if (c->k[ki] <= 160 && ntc::pl::have_scan_kernel(c->k[ki], c->sBits)) {
+			kmask |= 1u << ki;
+			kmax = std::max(kmax, c->k[ki]);
+			kmin = std::min(kmin, c->k[ki]);
+		}
+	if (!kmask)
+		return NTC_OK;
+	// piece geometry: at least 4 kmax bases per piece (<= 25 % of the scan spent on overlap), 176 bases (the stride the
+	// shared-memory hit kernel takes) when that is enough
+	const uint32_t stride = std::max(12u, (1u + (4u * kmax + 15u) / 16u + 3u) & ~3u);
+	const uint32_t Lp = 16u * (stride - 1u), D = Lp - kmax + 1u;
+	int rc;
+	const size_t n1 = (size_t)b.n_rec + 1;
+	if ((rc = grow(&c->d_rt_counts, &c->cap_rt_counts, 3 * n1, false)))
+		return rc;
+	{
+		size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
+		char* t = (char*)c->d_scan_tmp;
+		if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
+			return rc;
+		c->d_scan_tmp = t;
+	}
+	uint32_t *d_full = c->d_rt_counts, *d_tidx = c->d_rt_counts + n1, *d_tw = c->d_rt_counts + 2 * n1;
+	CK(ntc::launch_retile_count(b, Lp, D, kmin, d_full, d_tidx, d_tw, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
+	uint32_t tot[3];
+	CK(cudaMemcpyAsync(&tot[0], d_full + b.n_rec, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(&tot[1], d_tidx + b.n_rec, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(&tot[2], d_tw + b.n_rec, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	const uint32_t n_full = tot[0], n_tail = tot[1], tail_words = tot[2];
+	if ((uint64_t)n_full * stride > 0xFFFFFFF0ull)
+		return set_err(NTC_EINVAL, "batch too large to re-tile: %u pieces", n_full);
+	if ((rc = grow(&c->d_rt_uniform, &c->cap_rt_uniform, (size_t)n_full * stride + 4, false)) ||
+	    (rc = grow(&c->d_rt_tail_words, &c->cap_rt_tail_words, (size_t)tail_words + 4, false)) ||
+	    (rc = grow(&c->d_rt_tail_off, &c->cap_rt_tail_off, (size_t)n_tail + 2, false)))
+		return rc;
+	CK(ntc::launch_retile_fill(b, Lp, D, stride, d_full, d_tidx, d_tw, c->d_rt_uniform, c->d_rt_tail_words, c->d_rt_tail_off, c->n_sm, c->stream));
+	c->n_launches += 5;
+	c->n_retiled++;
+	if (n_full) {
+		ntc::BatchView u{ c->d_rt_uniform, nullptr, stride, n_full, (uint64_t)n_full * stride, Lp };
+		PipeShape shape[NTC_MAX_K];
+		const uint32_t pm = pipeline_config(c, u, true, shape, /*min_rec=*/1);
+		for (unsigned ki = 0; ki < c->nK; ki++)
+			if ((kmask >> ki) & 1u) {
+				if (!((pm >> ki) & 1u))
+					return set_err(NTC_ECUDA, "internal: re-tiled batch not accepted by the pipeline (k index %u)", ki);
+				shape[ki].start_limit = D;
+				if ((rc = run_pipeline_k(c, u, ki, shape[ki])))
+					return rc;
+			}
+	}
+	if (n_tail) {
+		if ((rc = flush(c))) // the general kernel increments the counters in HBM directly
+			return rc;
+		ntc::BatchView t{ c->d_rt_tail_words, c->d_rt_tail_off, 0, n_tail, tail_words, 0 };
+		if ((rc = run_roll64(c, t, false, kmask)))
+			return rc;
+	}
+	*handled = kmask;
+	return NTC_OK;
+}
+
 // Run the sketch kernels over one device-resident batch on the compute stream.
 int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 {
@@ -421,38 +531,22 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		return rc;
 	CK(cudaEventRecord(e0, c->stream));
 	PipeShape shape[NTC_MAX_K];
-	const uint32_t pmask = pipeline_config(c, b, record_is_piece, shape);
+	uint32_t pmask = pipeline_config(c, b, record_is_piece, shape);
+	uint32_t retiled = 0;
+	if (!pmask && (rc = run_retiled(c, b, &retiled)))
+		return rc;
 	const uint32_t all = c->nK >= 32 ? 0xFFFFFFFFu : ((1u << c->nK) - 1);
-	const uint32_t roll_mask = all & ~pmask;
+	const uint32_t roll_mask = all & ~(pmask | retiled);
 	if (c->kernel == NTC_KERNEL_BITSLICE && roll_mask)
-		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", pmask);
+		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", pmask | retiled);
 	for (unsigned ki = 0; ki < c->nK; ki++)
 		if ((pmask >> ki) & 1u)
 			if ((rc = run_pipeline_k(c, b, ki, shape[ki])))
 				return rc;
 	if (roll_mask && (rc = flush(c))) // the general kernel increments the counters in HBM directly
 		return rc;
-	if (roll_mask) {
-		uint64_t bound = 0;
-		if (!record_is_piece) {
-			bound = (uint64_t)b.n_rec + (16 * b.n_words) / ntc::PIECE_STARTS + 1;
-			if (bound > 0xFFFFFFFFull)
-				return set_err(NTC_EINVAL, "batch too large: %llu pieces", (unsigned long long)bound);
-			if ((rc = grow(&c->d_piece_first, &c->cap_piece_first, (size_t)b.n_rec + 1, false)) ||
-			    (rc = grow(&c->d_piece_rec, &c->cap_piece_rec, (size_t)bound, false)))
-				return rc;
-			size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
-			char* t = (char*)c->d_scan_tmp;
-			if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
-				return rc;
-			c->d_scan_tmp = t;
-			CK(ntc::launch_piece_tables(b, c->kmin, c->d_piece_first, c->d_piece_rec, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
-			c->n_launches += 3;
-		}
-		CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters, c->d_f1,
-		    roll_mask, c->n_sm, c->stream));
-		c->n_launches += 1;
-	}
+	if (roll_mask && (rc = run_roll64(c, b, record_is_piece, roll_mask)))
+		return rc;
 	CK(cudaEventRecord(e1, c->stream));
 	c->timing.emplace_back(e0, e1);
 	c->n_batches++;
@@ -634,6 +728,10 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->d_piece_first) cudaFree(c->d_piece_first);
 	if (c->d_piece_rec) cudaFree(c->d_piece_rec);
 	if (c->d_scan_tmp) cudaFree(c->d_scan_tmp);
+	if (c->d_rt_counts) cudaFree(c->d_rt_counts);
+	if (c->d_rt_uniform) cudaFree(c->d_rt_uniform);
+	if (c->d_rt_tail_words) cudaFree(c->d_rt_tail_words);
+	if (c->d_rt_tail_off) cudaFree(c->d_rt_tail_off);
 	if (c->d_narrow) cudaFree(c->d_narrow);
 	if (c->d_phist) cudaFree(c->d_phist);
 	if (c->d_f1) cudaFree(c->d_f1);

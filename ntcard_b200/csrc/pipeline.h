@@ -47,12 +47,12 @@ struct Pool {                    // device pointers + geometry, passed by value
 	uint32_t* gstate;            // [nK][max_groups][1 + 5 * nbins]: open / spare blocks of every hit group, kept over launches
 	uint32_t max_groups, epoch;  // epoch: bumped by ntc_reset (host); with CTL_FLUSHES it dates gstate
 	uint32_t ahead;              // apply kernel: slices the stagers may run ahead of the appliers (L2 footprint)
-	uint32_t dbg;                // timing experiments (NTC_PL_DEBUG): wrong results when non-zero
 };
 
 struct ScanLaunch {              // per-k constants of the scan kernel, passed by value
 	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (k + 16 rounded up to a multiple of 16)
 	uint32_t npos_max;           // mask rows per tile
+	uint32_t start_limit;        // != 0: hash only the k-mers starting in the first start_limit positions of a record (re-tiled pieces)
 	uint32_t F0[31], R0[31];     // initial bit-sliced state (bitslice_core.cuh init_state)
 };
 

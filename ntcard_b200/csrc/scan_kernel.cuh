@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			zero_rows(masks, tile, 0, L.npos_max, lane);
 			continue;
 		}
-		const int n = (int)len0;
+		int n = (int)len0;
+		if (n >= k && L.start_limit) // re-tiled pieces: only the first start_limit windows belong to this record
+			n = min(n, (int)L.start_limit + k - 1);
 		if (n < k) {
 			if (lane == 0)
 				tile_info[tile] = 0;

@@ -45,6 +45,80 @@ __global__ void piece_fill_kernel(const uint32_t* __restrict__ piece_first, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// re-tiling of long ragged records (long reads, N-split contigs) into fixed-length pieces, so that they can take
+// the scan -> hit -> apply pipeline, which wants uniform-stride batches of equal-length records.
+// Piece j of a record covers bases [j*D, j*D + Lp): Lp = 16 * (stride - 1) bases, D = Lp - kmax + 1 k-mer starts; the
+// pipeline hashes the k-mers starting in the first D positions of every piece (for every k <= kmax that keeps each window
+// inside its piece and counts each start once).  What is left of a record behind its last full piece -- bases
+// [n_full * D, len), if at least kmin long -- becomes a "tail" record of a ragged batch for the general kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void retile_count_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ off, uint32_t n_rec, uint32_t Lp, uint32_t D,
+    uint32_t kmin, uint32_t* __restrict__ n_full /* [n_rec + 1] */, uint32_t* __restrict__ has_tail, uint32_t* __restrict__ tail_words)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > n_rec)
+		return;
+	uint32_t nf = 0, ht = 0, tw = 0;
+	if (i < n_rec) {
+		const uint32_t len = __ldg(words + __ldg(off + i));
+		nf = len >= Lp ? (len - Lp) / D + 1 : 0;
+		const uint32_t tl = len - nf * D;
+		if (tl >= kmin && len >= kmin) {
+			ht = 1;
+			tw = 1 + (tl + 15) / 16;
+		}
+	}
+	n_full[i] = nf;
+	has_tail[i] = ht;
+	tail_words[i] = tw;
+}
+
+// 16 bases starting at base `bo` of a record whose base words are b[0 .. nw)
+__device__ __forceinline__ uint32_t bases16(const uint32_t* __restrict__ b, uint32_t nw, uint32_t bo)
+{
+	const uint32_t s = bo >> 4, sh = (bo & 15u) * 2u;
+	const uint32_t lo = s < nw ? __ldg(b + s) : 0u, hi = s + 1 < nw ? __ldg(b + s + 1) : 0u;
+	return __funnelshift_r(lo, hi, sh);
+}
+
+// one warp per record: the lanes write the record's output words
+__global__ void __launch_bounds__(256) retile_fill_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ off, uint32_t n_rec,
+    uint32_t Lp, uint32_t D, uint32_t stride, const uint32_t* __restrict__ full_first, const uint32_t* __restrict__ tail_idx,
+    const uint32_t* __restrict__ tail_first, uint32_t* __restrict__ out_uniform, uint32_t* __restrict__ out_tail_words,
+    uint32_t* __restrict__ out_tail_off)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t i = warp; i < n_rec; i += nwarps) {
+		const uint32_t* r = words + __ldg(off + i);
+		const uint32_t len = __ldg(r), nw = (len + 15) / 16;
+		const uint32_t f0 = full_first[i], nf = full_first[i + 1] - f0;
+		uint32_t* ou = out_uniform + (size_t)f0 * stride;
+		for (uint32_t x = lane; x < nf * stride; x += 32) {
+			const uint32_t j = x / stride, w = x - j * stride;
+			ou[x] = w == 0 ? Lp : bases16(r + 1, nw, j * D + (w - 1) * 16);
+		}
+		if (tail_idx[i + 1] != tail_idx[i]) {
+			const uint32_t t0 = tail_first[i], tw = tail_first[i + 1] - t0, tl = len - nf * D;
+			if (lane == 0)
+				out_tail_off[tail_idx[i]] = t0;
+			for (uint32_t w = lane; w < tw; w += 32) {
+				uint32_t v = tl;
+				if (w) {
+					v = bases16(r + 1, nw, nf * D + (w - 1) * 16);
+					const uint32_t left = tl - (w - 1) * 16;
+					if (left < 16)
+						v &= (1u << (2 * left)) - 1u;
+				}
+				out_tail_words[t0 + w] = v;
+			}
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		out_tail_off[tail_idx[n_rec]] = tail_first[n_rec]; // end of the last tail record
+}
+
+// ------------------------------------------------------------------------------------------------
 // roll64: the straightforward kernel.  ntRead's loops (ntcard.cpp:147-158) with the iterator's
 // rolling update (ntHashIterator.hpp:85 -> NTC64, nthash.hpp:275-279); records hold valid bases
 // only, so the N-restart branch (ntHashIterator.hpp:80-83) never fires on the device.
@@ -236,6 +310,30 @@ cudaError_t launch_piece_tables(const BatchView& b, uint32_t kmin, uint32_t* d_p
 	if (e != cudaSuccess)
 		return e;
 	piece_fill_kernel<<<(b.n_rec + 255) / 256, 256, 0, st>>>(d_piece_first, b.n_rec, d_piece_rec);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_retile_count(const BatchView& b, uint32_t Lp, uint32_t D, uint32_t kmin, uint32_t* d_n_full, uint32_t* d_has_tail,
+    uint32_t* d_tail_words, void* d_tmp, size_t tmp_bytes, cudaStream_t st)
+{
+	const uint32_t n = b.n_rec + 1;
+	retile_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.words, b.off, b.n_rec, Lp, D, kmin, d_n_full, d_has_tail, d_tail_words);
+	cudaError_t e;
+	if ((e = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_n_full, d_n_full, (int)n, st)) != cudaSuccess ||
+	    (e = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_has_tail, d_has_tail, (int)n, st)) != cudaSuccess ||
+	    (e = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_tail_words, d_tail_words, (int)n, st)) != cudaSuccess)
+		return e;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_retile_fill(const BatchView& b, uint32_t Lp, uint32_t D, uint32_t stride, const uint32_t* d_full_first,
+    const uint32_t* d_tail_idx, const uint32_t* d_tail_first, uint32_t* d_out_uniform, uint32_t* d_out_tail_words, uint32_t* d_out_tail_off,
+    int n_sm, cudaStream_t st)
+{
+	const unsigned cap = (unsigned)n_sm * 16u;
+	const unsigned grid = grid_for((uint64_t)b.n_rec * 32, 256, cap);
+	retile_fill_kernel<<<grid, 256, 0, st>>>(b.words, b.off, b.n_rec, Lp, D, stride, d_full_first, d_tail_idx, d_tail_first, d_out_uniform,
+	    d_out_tail_words, d_out_tail_off);
 	return cudaGetLastError();
 }
 

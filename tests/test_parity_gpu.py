@@ -375,3 +375,20 @@ def test_pipeline_general_hit_kernel_long_reads(oracle):
             sk.submit(words, None, n, stride)
             t, f1, _ = sk.finish(counters=True, hist=False)
         assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
+
+
+def test_long_ragged_records_are_retiled_exactly(oracle):
+    """Long ragged records (long reads with N runs, mixed with short ones) are cut on the device into equal pieces for
+    the pipeline plus ragged tails for the general kernel; every k-mer must still be counted exactly once, for every k."""
+    rng = random.Random(123)
+    a = oracle.gen_reads(21, 0, 400, 6000, 2, 0)
+    reads = [bytes(a[i * 6000:(i + 1) * 6000]) for i in range(400)]
+    for _ in range(300):                                        # odd lengths around the piece geometry
+        L = rng.choice((0, 5, 31, 32, 145, 146, 147, 175, 176, 177, 321, 322, 323, 700, 1500, 2999))
+        reads.append(bytes(rng.choice(b"ACGT") for _ in range(L)))
+    rng.shuffle(reads)
+    for kList, rBits, sBits in (([31], 20, 11), ([12, 32, 64], 18, 7), ([32, 96, 128], 18, 7), ([31, 33], 16, 7)):
+        want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+        t, f1, _ = run_gpu(reads, kList, rBits, sBits, nt.KERNEL_AUTO, batches=2)
+        assert np.array_equal(f1, wf1), (kList, f1, wf1)
+        assert np.array_equal(t.reshape(-1), want), kList
