@@ -392,3 +392,34 @@ def test_long_ragged_records_are_retiled_exactly(oracle):
         t, f1, _ = run_gpu(reads, kList, rBits, sBits, nt.KERNEL_AUTO, batches=2)
         assert np.array_equal(f1, wf1), (kList, f1, wf1)
         assert np.array_equal(t.reshape(-1), want), kList
+
+
+@pytest.mark.parametrize("n,kList,sBits,name", [(100_000_000, [32, 64, 96, 128], 7, "config 3"),
+                                                (125_000_000, [64], 11, "config 4, one GPU's shard")])
+def test_full_size_configs_pipeline_equals_general_kernel(n, kList, sBits, name):
+    """BASELINE configs 3 and 4 at full size (device-resident synthetic reads, r=27).  Size-independent properties: F1 is
+    analytic for every k; the two independent device implementations -- the scan/hit/apply pipeline and the 64-bit
+    general kernel, each checked against the oracle at small sizes -- must give the same counter-value histogram
+    (and therefore the same F0 / f_i); the histogram must account for every bucket."""
+    import torch
+    L, stride = 150, nt.stride_words(150)
+    d = torch.empty(n * stride, dtype=torch.int32, device="cuda")
+    hists = {}
+    with nt.Sketch(kList, rBits=27, sBits=sBits) as sk:
+        sk.gen_packed_device(2, 0, n, L, 0, 0, stride, d.data_ptr())
+        for kernel in (nt.KERNEL_AUTO, nt.KERNEL_ROLL64):
+            sk.reset()
+            sk.set_kernel(kernel)
+            half = (n // 2 // 1024) * 1024 + 7                      # two batches, the first ends inside a tile
+            sk.submit_device(d.data_ptr(), half * stride, half, stride)
+            sk.submit_device(d.data_ptr() + half * stride * 4, (n - half) * stride, n - half, stride)
+            _, f1, p = sk.finish(counters=False, hist=True)
+            assert [int(x) for x in f1] == [n * (L - k + 1) for k in kList], name
+            hists[kernel] = p
+    a, b = hists[nt.KERNEL_AUTO], hists[nt.KERNEL_ROLL64]
+    assert np.array_equal(a, b), name
+    assert (a.sum(axis=2, dtype=np.uint64) == (1 << 27)).all()
+    for ki, k in enumerate(kList):
+        F0, f = nt.estimate(p_hist=a[ki], rBits=27, sBits=sBits, covMax=4)
+        distinct = n * (L - k + 1)                                   # uniform random reads: (almost) every k-mer is new
+        assert abs(F0 - distinct) / distinct < 0.02, (name, k, F0, distinct)
