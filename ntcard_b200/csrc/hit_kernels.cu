@@ -734,8 +734,11 @@ int apply_max_grid(int n_sm)
 cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32_t reserve_blocks, unsigned grid, cudaStream_t st,
     const uint32_t* d_order, uint32_t n_order)
 {
-	apply_kernel<<<grid, kApplyThreads, 0, st>>>(pool, counters, force, reserve_blocks, d_order, n_order);
-	return cudaGetLastError();
+	// Cooperative launch: the stagers and appliers of different CTAs wait for each other through counters in global
+	// memory, so every CTA of the grid must be resident at once -- also when another context's kernels share the GPU.
+	Pool p = pool;
+	void* args[] = { &p, &counters, &force, &reserve_blocks, &d_order, &n_order };
+	return cudaLaunchCooperativeKernel((const void*)apply_kernel, dim3(grid), dim3(kApplyThreads), args, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------------
