@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			tile_info[tile] = (uint32_t)(n - k + 1);
 		const uint32_t nwords = (uint32_t)(n + 15) >> 4;
 		const uint32_t ngroups = (nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
-		uint32_t* mrow = masks + ((long long)tile * L.npos_max - (k - 1)) * 32 + lane; // row of position q: mrow + 32 q
+		// mask row of the block's first position: a running pointer (not recomputed from tile / lane per store)
+		uint32_t* mptr = masks + ((long long)tile * L.npos_max - (k - 1)) * 32 + lane;
 		bs::State st;
 #pragma unroll
 		for (int j = 0; j < 31; j++) {
@@ -224,8 +225,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			for (int qb = q0; qb < q0 + nq; qb += kScanBlock) {
 				int ob = cout + (qb - q0);
 				ob = ob >= R ? ob - R : ob; // a block may start up to 3 slots before the end of the ring: mirror slots
-				ScanBlock<KM, S, 0>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, mrow + qb * 32, qb, k, n, cand);
+				ScanBlock<KM, S, 0>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, mptr, qb, k, n, cand);
 				scan_rotate_home(st);
+				mptr += kScanBlock * 32;
 			}
 			cin = cin + 16 == R ? 0 : cin + 16;
 			cout = cout + 16 >= R ? cout + 16 - R : cout + 16;
