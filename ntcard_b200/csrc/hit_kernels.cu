@@ -322,10 +322,11 @@ __device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs
 
 __device__ __forceinline__ void emit_bits(const GroupSmem& sm, uint32_t x, uint32_t w, uint32_t& at)
 {
+	const uint32_t hi = w << 5;
 	while (x) {
-		const uint32_t s = __ffs(x) - 1;
-		x &= x - 1;
-		sm.queue[at++] = s | (w << 5);
+		const uint32_t s = 31u - (uint32_t)__clz(x); // highest set bit: one FLO (the lowest needs a BREV first)
+		x ^= 1u << s;
+		sm.queue[at++] = s | hi;
 	}
 }
 

@@ -761,7 +761,12 @@ int ntc_reset(ntc_ctx* c)
 	// applies the slice's increments (apply_kernel, state 0), which saves one full pass over the 1 GiB/k sketch.
 	CK(cudaMemsetAsync(c->d_pool_ctl_region, 0, c->pool_ctl_bytes, c->stream)); // empty log, state = not materialised
 	CK(cudaMemsetAsync(c->d_f1, 0, NTC_MAX_K * sizeof(unsigned long long), c->stream));
-	c->pool.epoch = (c->pool.epoch + 1) & 0xFFFFu; // outdates the hit groups' saved blocks
+	{ // the hit groups' saved open / spare blocks belong to the old log: invalidate their generation words
+		const ntc::pl::Pool& P = c->pool;
+		const size_t pitch = (1 + 5 * (size_t)P.nbins) * sizeof(uint32_t);
+		CK(cudaMemset2DAsync(P.gstate, pitch, 0, sizeof(uint32_t), (size_t)c->nK * P.max_groups, c->stream));
+	}
+	c->pool.epoch = (c->pool.epoch + 1) & 0xFFFFu; // (and date the new ones differently)
 	if (c->pool.epoch == 0)
 		c->pool.epoch = 1;
 	c->totals_overridden = false;
