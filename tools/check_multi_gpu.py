@@ -25,7 +25,7 @@ def main():
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
     orc = Oracle()
-    kList, rBits, sBits, L, n = [32, 64], 22, 7, 150, 400_000
+    kList, rBits, sBits, L, n = [32, 64], 25, 7, 150, 400_000   # 16 sketch slices: enough for 8 ranks
     wrap = orc.gen_read(9, 0, 40, 0, 0)
     a = orc.gen_reads(3, 0, n, L, 1, n // 8)
     lo, hi = shard_range(n, rank, world)
