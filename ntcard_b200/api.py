@@ -203,6 +203,7 @@ class Sketch:
                               C.c_void_p(d_counters) if d_counters else None,
                               C.c_void_p(stream) if stream else None))
         self.h = h
+        self.stream_handle = int(stream) if stream else None   # the CUDA stream all device work is ordered on (None: own)
 
     def close(self):
         if getattr(self, "h", None):

@@ -100,8 +100,13 @@ struct ntc_ctx {
 	bool partial = false;     // after ntc_flush_slices: only the owned slices of the sketch are defined (until ntc_reset)
 	std::vector<uint32_t> h_nblk; // block counts per slice as of the last ntc_log_counts
 	uint32_t log_used = 0;
-	uint32_t* d_runs = nullptr;
-	size_t cap_runs = 0;
+	static constexpr int kRunSlots = 8;
+	struct RunSlot {
+		uint32_t *h = nullptr, *d = nullptr;
+		size_t cap_h = 0, cap_d = 0;
+		cudaEvent_t done = nullptr;
+	} run_slot[kRunSlots];
+	unsigned next_run_slot = 0;
 	unsigned apply_grid = 0, hit_grid_max = 0;
 	unsigned chunk_waves = 0; // scan waves per pipeline chunk (0 = whole batch; chunking measured slower, kept for experiments)
 	uint64_t n_flush_launches = 0;
@@ -742,7 +747,11 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->pool.gstate) cudaFree(c->pool.gstate);
 	if (c->d_pool_ctl_region) cudaFree(c->d_pool_ctl_region);
 	if (c->d_masks) cudaFree(c->d_masks);
-	if (c->d_runs) cudaFree(c->d_runs);
+	for (auto& rs : c->run_slot) {
+		if (rs.h) cudaFreeHost(rs.h);
+		if (rs.d) cudaFree(rs.d);
+		if (rs.done) cudaEventDestroy(rs.done);
+	}
 	if (c->d_tile_info) cudaFree(c->d_tile_info);
 	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -974,13 +983,21 @@ int ntc_log_counts(ntc_ctx* c, uint32_t* nblk, int* exportable, uint32_t* pool_i
 	return NTC_OK;
 }
 
-static int upload_runs(ntc_ctx* c, const std::vector<uint32_t>& runs)
+// Small host tables (runs of slices, slice orders) for the kernels of the exchange / partial flush: staged in a ring of
+// pinned buffers and copied asynchronously, so the calls do not drain the stream.  Each slot has its own device copy.
+static int upload_runs(ntc_ctx* c, const std::vector<uint32_t>& runs, const uint32_t** d_out)
 {
+	ntc_ctx::RunSlot& s = c->run_slot[c->next_run_slot++ % ntc_ctx::kRunSlots];
 	int rc;
-	if ((rc = grow(&c->d_runs, &c->cap_runs, runs.size() + 2, false)))
+	if (!s.done)
+		CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+	CK(cudaEventSynchronize(s.done)); // the slot's previous copy has executed (long ago)
+	if ((rc = grow(&s.h, &s.cap_h, runs.size() + 2, true)) || (rc = grow(&s.d, &s.cap_d, runs.size() + 2, false)))
 		return rc;
-	CK(cudaMemcpyAsync(c->d_runs, runs.data(), runs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaStreamSynchronize(c->stream)); // `runs` is a host temporary
+	memcpy(s.h, runs.data(), runs.size() * sizeof(uint32_t));
+	CK(cudaMemcpyAsync(s.d, s.h, runs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaEventRecord(s.done, c->stream));
+	*d_out = s.d;
 	return NTC_OK;
 }
 
@@ -1006,9 +1023,10 @@ int ntc_log_export(ntc_ctx* c, const uint32_t* slices, uint32_t n, void* d_block
 		return NTC_OK;
 	if (!d_blocks)
 		return set_err(NTC_EINVAL, "ntc_log_export: null output buffer");
-	if ((rc = upload_runs(c, runs)))
+	const uint32_t* d_runs = nullptr;
+	if ((rc = upload_runs(c, runs, &d_runs)))
 		return rc;
-	CK(ntc::pl::launch_export(c->pool, c->d_runs, (uint32_t)runs.size() / 2, total, (uint32_t*)d_blocks, c->stream));
+	CK(ntc::pl::launch_export(c->pool, d_runs, (uint32_t)runs.size() / 2, total, (uint32_t*)d_blocks, c->stream));
 	c->n_launches++;
 	return NTC_OK;
 }
@@ -1042,12 +1060,13 @@ int ntc_log_import(ntc_ctx* c, const void* d_blocks, uint32_t n_blocks, const ui
 	}
 	if (total != n_blocks)
 		return set_err(NTC_EINVAL, "ntc_log_import: runs cover %u blocks, n_blocks = %u", total, n_blocks);
-	if ((rc = upload_runs(c, runs)))
+	const uint32_t* d_runs = nullptr;
+	if ((rc = upload_runs(c, runs, &d_runs)))
 		return rc;
 	// wire blocks (260 words) -> pool blocks (256 words)
 	CK(cudaMemcpy2DAsync(P.entries + (size_t)c->log_used * ntc::pl::kBlkEntries, ntc::pl::kBlkEntries * sizeof(uint32_t), d_blocks,
 	    ntc::pl::kWireBlkWords * sizeof(uint32_t), ntc::pl::kBlkEntries * sizeof(uint32_t), n_blocks, cudaMemcpyDeviceToDevice, c->stream));
-	CK(ntc::pl::launch_import(P, c->d_runs, (uint32_t)runs.size() / 2, n_blocks, c->log_used, (const uint32_t*)d_blocks, c->stream));
+	CK(ntc::pl::launch_import(P, d_runs, (uint32_t)runs.size() / 2, n_blocks, c->log_used, (const uint32_t*)d_blocks, c->stream));
 	c->log_used += n_blocks;
 	c->n_launches++;
 	c->pending = true;
@@ -1078,7 +1097,8 @@ int ntc_flush_slices(ntc_ctx* c, const uint8_t* owned)
 			order.push_back(s);
 	const uint32_t n = (uint32_t)order.size();
 	order.push_back(0); // never an empty upload
-	if ((rc = upload_runs(c, order)))
+	const uint32_t* d_order = nullptr;
+	if ((rc = upload_runs(c, order, &d_order)))
 		return rc;
 	cudaEvent_t e0, e1;
 	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
@@ -1086,7 +1106,7 @@ int ntc_flush_slices(ntc_ctx* c, const uint8_t* owned)
 	CK(cudaEventRecord(e0, c->stream));
 	if ((rc = stage_begin(c, 2)))
 		return rc;
-	CK(ntc::pl::launch_apply(c->pool, c->d_counters, 1, 0, c->apply_grid, c->stream, c->d_runs, n));
+	CK(ntc::pl::launch_apply(c->pool, c->d_counters, 1, 0, c->apply_grid, c->stream, d_order, n));
 	if ((rc = stage_end(c)))
 		return rc;
 	CK(cudaEventRecord(e1, c->stream));
@@ -1122,9 +1142,10 @@ int ntc_hist_slices(ntc_ctx* c, const uint8_t* owned, uint32_t* p_hist, void* d_
 			order.push_back(s);
 	const uint32_t n = (uint32_t)order.size();
 	order.push_back(0);
-	if ((rc = upload_runs(c, order)))
+	const uint32_t* d_order = nullptr;
+	if ((rc = upload_runs(c, order, &d_order)))
 		return rc;
-	cudaError_t e = ntc::pl::launch_hist_slices(P, c->d_counters, c->d_runs, n, dst, c->stream);
+	cudaError_t e = ntc::pl::launch_hist_slices(P, c->d_counters, d_order, n, dst, c->stream);
 	if (e == cudaErrorInvalidValue)
 		return set_err(NTC_EINVAL, "ntc_hist_slices: rBits too small for the histogram chunk");
 	CK(e);

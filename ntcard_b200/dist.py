@@ -68,19 +68,21 @@ def plan_exchange(counts: np.ndarray, rank: int):
     this rank sends, to every other rank d, the blocks of d's slices in increasing slice order, and receives
     from every other rank q the blocks of its own slices in the same order (runs, in arrival order)."""
     world, n_slices = counts.shape
-    owned = np.fromiter((s % world == rank for s in range(n_slices)), dtype=np.uint8, count=n_slices)
+    owner = np.arange(n_slices) % world
+    owned = (owner == rank).astype(np.uint8)
+    mine = counts[rank]
     send_slices, send_splits, recv_splits, runs = [], [], [], []
     for d in range(world):
-        sl = [s for s in range(n_slices) if d != rank and s % world == d and counts[rank, s] > 0]
-        send_slices += sl
-        send_splits.append(int(sum(int(counts[rank, s]) for s in sl)))
+        sl = np.nonzero((owner == d) & (mine > 0))[0] if d != rank else np.zeros(0, dtype=np.int64)
+        send_slices += [int(x) for x in sl]
+        send_splits.append(int(mine[sl].sum()))
+    own = np.nonzero(owner == rank)[0]
     for q in range(world):
         tot = 0
         if q != rank:
-            for s in range(n_slices):
-                if s % world == rank and counts[q, s] > 0:
-                    runs.append((s, int(counts[q, s])))
-                    tot += int(counts[q, s])
+            sl = own[counts[q, own] > 0]
+            runs += [(int(s), int(counts[q, s])) for s in sl]
+            tot = int(counts[q, sl].sum())
         recv_splits.append(tot)
     return owned, send_slices, send_splits, recv_splits, runs
 
@@ -142,16 +144,20 @@ def exchange_hist(sketch, rBits: int, device, totals_out=None):
     recv = _buffer(device, "recv", n_recv * W)
     hist = _buffer(device, "hist", sketch.nK * 2 * 65536)
     lap("plan + buffers")
+    same_stream = getattr(sketch, "stream_handle", None) == torch.cuda.current_stream(device).cuda_stream
     sketch.log_export(send_slices, send.data_ptr())
-    sketch.stream_sync()                                   # the export ran on the sketch's stream
+    if not same_stream:
+        sketch.stream_sync()                               # the export ran on the sketch's own stream
     lap("export")
     dist.all_to_all_single(recv[:n_recv * W], send[:n_send * W], [x * W for x in recv_splits], [x * W for x in send_splits])
-    torch.cuda.current_stream(device).synchronize()        # the import runs on the sketch's stream
+    if not same_stream:
+        torch.cuda.current_stream(device).synchronize()    # the import runs on the sketch's own stream
     lap(f"all_to_all ({n_send * W * 4 / 1e6:.1f} MB out)")
     sketch.log_import(recv.data_ptr(), n_recv, runs)
     sketch.flush_slices(owned)
     sketch.hist_slices(owned, d_out=hist.data_ptr())
-    sketch.stream_sync()
+    if not same_stream:
+        sketch.stream_sync()
     lap("import + flush_slices + hist_slices")
     h = hist[:sketch.nK * 2 * 65536]
     dist.all_reduce(h, op=dist.ReduceOp.SUM)               # int32 on the device: a bin counts at most 2^rBits buckets
