@@ -423,3 +423,60 @@ def test_full_size_configs_pipeline_equals_general_kernel(n, kList, sBits, name)
         F0, f = nt.estimate(p_hist=a[ki], rBits=27, sBits=sBits, covMax=4)
         distinct = n * (L - k + 1)                                   # uniform random reads: (almost) every k-mer is new
         assert abs(F0 - distinct) / distinct < 0.02, (name, k, F0, distinct)
+
+
+def test_hit_log_exchange_between_two_contexts_on_one_gpu(oracle):
+    """The multi-GPU sparse reduction (ntc_log_counts / export / import / flush_slices / hist_slices) exercised on ONE
+    device: two contexts play two ranks, each sketches half of the reads, they swap the log blocks of the slices the
+    other one owns (slice s belongs to rank s % 2) through plain device buffers, each materialises and histograms only
+    its own slices; the summed histogram must equal the histogram of one sketch of all reads."""
+    import torch
+    from ntcard_b200.dist import exchange_feasible, plan_exchange
+    n, L, kList, rBits, sBits = 40960, 150, [32, 64], 25, 7
+    stride = nt.stride_words(L)
+    words = nt.gen_packed(61, 0, n, L, 1, n // 4, stride)
+    a = oracle.gen_reads(61, 0, n, L, 1, n // 4)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+    rB = 1 << rBits
+    want_p = np.stack([np.bincount(want[t * rB:(t + 1) * rB], minlength=65536) for t in range(2 * len(kList))]).reshape(len(kList), 2, 65536)
+    half = n // 2
+    W = nt.Sketch.WIRE_BLOCK_WORDS
+    with nt.Sketch(kList, rBits=rBits, sBits=sBits) as s0, nt.Sketch(kList, rBits=rBits, sBits=sBits) as s1:
+        ranks = [s0, s1]
+        s0.submit(words[:half * stride], None, half, stride)
+        s1.submit(words[half * stride:], None, n - half, stride)
+        got = [r.log_counts() for r in ranks]
+        assert all(ok for _, ok, _ in got)
+        counts = np.stack([c.astype(np.int64) for c, _, _ in got])
+        infos = np.array([i for _, _, i in got], dtype=np.int64)
+        n_slices = counts.shape[1]
+        assert n_slices == len(kList) * 8 and exchange_feasible(counts, infos)
+        plans = [plan_exchange(counts, r) for r in range(2)]
+        bufs = []
+        for r in range(2):
+            _, send_slices, send_splits, _, _ = plans[r]
+            buf = torch.zeros(max(sum(send_splits), 1) * W, dtype=torch.int32, device="cuda")
+            ranks[r].log_export(send_slices, buf.data_ptr())
+            ranks[r].stream_sync()
+            bufs.append(buf)
+        total = np.zeros((len(kList), 2, 65536), dtype=np.uint64)
+        for r in range(2):
+            owned, _, _, recv_splits, runs = plans[r]
+            assert sum(recv_splits) == plans[1 - r][2][r]
+            ranks[r].log_import(bufs[1 - r].data_ptr(), sum(recv_splits), runs)
+            ranks[r].flush_slices(owned)
+            total += ranks[r].hist_slices(owned)
+            with pytest.raises(nt.NtcError):
+                ranks[r].finish(counters=True)              # only the owned slices are defined now
+        total[:, :, 0] = rB - total[:, :, 1:].sum(axis=2)
+        assert np.array_equal(total, want_p.astype(np.uint64))
+        f1 = s0.totals_nosync() + s1.totals_nosync()
+        assert np.array_equal(f1, wf1)
+        # a context is usable again after a reset, and a flushed log is no longer exportable
+        s0.reset()
+        s0.submit(words, None, n, stride)
+        s0.flush()
+        assert s0.log_counts()[1] is False
+        t, f1b, _ = s0.finish(counters=True, hist=False)
+        assert np.array_equal(t.reshape(-1), want) and np.array_equal(f1b, wf1)
