@@ -216,6 +216,13 @@ int main(int argc, char** argv)
 	if (totalSize < 50000000000ULL)
 		opt::sBits = 7;
 
+	const bool timing = getenv("NTC_CLI_TIMING") != NULL; // phase times on stderr (not part of the reference's output)
+	auto lap = [&](const char* what) {
+		if (timing)
+			std::cerr << "  [timing] " << what << ": " << std::setprecision(3) << std::fixed
+			          << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s since start\n";
+	};
+	lap("options parsed");
 	ntc_ctx* ctx = NULL;
 	if (ntc_create(&ctx, kList.data(), (unsigned)kList.size(), opt::rBits, opt::sBits, opt::gpu, NULL, NULL))
 		die_ntc("cannot create the device sketch");
@@ -223,6 +230,7 @@ int main(int argc, char** argv)
 		die_ntc("kernel");
 	if (opt::gap != 0 && ntc_set_gap(ctx, opt::gap)) // stRead instead of ntRead, ntcard.cpp:184-185, 204-205, 231-232
 		die_ntc("gap seed");
+	lap("device context created");
 	unsigned kmin = kList[0];
 	for (unsigned k : kList)
 		kmin = k < kmin ? k : kmin;
@@ -233,8 +241,26 @@ int main(int argc, char** argv)
 	unsigned nthreads = opt::nThrd < 1 ? 1 : opt::nThrd;
 	if (nthreads > inFiles.size())
 		nthreads = (unsigned)inFiles.size();
+	std::atomic<int> worker_id(0);
 	auto worker = [&]() {
+		const auto w0 = std::chrono::steady_clock::now();
 		ntcb::BatchSubmitter sub(ctx, kmin, &submit_mu);
+		const auto w1 = std::chrono::steady_clock::now();
+		struct Report {
+			bool on;
+			int id;
+			std::chrono::steady_clock::time_point w0, w1;
+			ntcb::BatchSubmitter* sub;
+			~Report()
+			{
+				if (on) {
+					const auto w2 = std::chrono::steady_clock::now();
+					std::cerr << "  [timing] reader " << id << ": pinned buffers " << std::setprecision(3) << std::fixed
+					          << std::chrono::duration<double>(w1 - w0).count() << " s, files " << std::chrono::duration<double>(w2 - w1).count()
+					          << " s of which inside ntc_submit/ntc_wait " << sub->seconds_in_submit() << " s\n";
+				}
+			}
+		} report{ timing, worker_id.fetch_add(1), w0, w1, &sub };
 		for (;;) {
 			size_t i = next_file.fetch_add(1);
 			if (i >= inFiles.size())
@@ -257,14 +283,17 @@ int main(int argc, char** argv)
 			t.join();
 	}
 
+	lap("files read, packed and submitted");
 	std::vector<uint64_t> totalKmers(kList.size(), 0);
 	std::vector<uint32_t> p_hist(kList.size() * 2 * 65536);
 	if (ntc_finish(ctx, NULL, totalKmers.data(), p_hist.data()))
 		die_ntc("finish");
+	lap("finish (flush + histogram)");
 	if (opt::output.empty())
 		write_default(kList, totalKmers.data(), p_hist.data());
 	else
 		write_compact(kList, totalKmers.data(), p_hist.data());
+	lap("estimates written");
 	ntc_destroy(ctx);
 	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
 	std::cerr << "Runtime(sec): " << std::setprecision(4) << std::fixed << secs << "\n"; // ntcard.cpp:476

@@ -2,6 +2,7 @@
 #include "reader.h"
 
 #include <cctype>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -158,6 +159,11 @@ void BatchSubmitter::release(Buf& b)
 
 void BatchSubmitter::flush_stream(Stream& st)
 {
+	struct Timer {
+		double* acc;
+		std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+		~Timer() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+	} timer{ &submit_seconds_ };
 	Buf& b = st.buf[st.cur];
 	if (b.n_rec > 0) {
 		std::lock_guard<std::mutex> lk(*mu_);

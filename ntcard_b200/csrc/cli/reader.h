@@ -38,13 +38,15 @@ private:
 // bit-sliced kernel; everything else (segments cut short by an N, odd lengths) goes into a ragged batch.
 class BatchSubmitter {
 public:
-	BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer = (size_t)8 << 20);
+	BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer = (size_t)2 << 20); // 8 MB per pinned buffer: pinning is slow (~1 GB/s), 16 reader threads x 84 MB cost 1 s
 	~BatchSubmitter();
 	void add(const char* seq, size_t len); // == one ntRead(seq, ...) call of the reference
 	void flush();                           // submit what is buffered (both streams)
+	double seconds_in_submit() const { return submit_seconds_; } // time spent in ntc_submit / ntc_wait incl. the lock
 	void finish();                          // wait until the device no longer needs our buffers
 
 private:
+	double submit_seconds_ = 0;
 	struct Buf {
 		uint32_t* words = nullptr;
 		uint32_t* off = nullptr;
