@@ -526,9 +526,9 @@ int run_retiled(ntc_ctx* c, const ntc::BatchView& b, uint32_t* handled)
 }
 
 // Run the sketch kernels over one device-resident batch on the compute stream.
-int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
+int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 {
-	if (b.n_rec == 0)
+	if (b_in.n_rec == 0)
 		return NTC_OK;
 	cudaEvent_t e0, e1;
 	int rc;
@@ -536,6 +536,24 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		return rc;
 	CK(cudaEventRecord(e0, c->stream));
 	PipeShape shape[NTC_MAX_K];
+	ntc::BatchView b = b_in;
+	if (!b.off && (b.stride & 3u) && b.stride >= 2 && b.n_rec >= 1024 && c->use_pipeline && !c->gap && c->kernel != NTC_KERNEL_ROLL64 &&
+	    record_is_piece) {
+		// tightly packed uniform batch: pad every record to a multiple of 4 words on the device, then it can take the pipeline
+		const uint32_t s4 = (b.stride + 3u) & ~3u;
+		bool any = false;
+		for (unsigned ki = 0; ki < c->nK; ki++)
+			any = any || (c->k[ki] < 288 && ntc::pl::have_scan_kernel(c->k[ki], c->sBits));
+		if (any && (uint64_t)b.n_rec * s4 <= 0xFFFFFFF0ull) {
+			if ((rc = grow(&c->d_rt_uniform, &c->cap_rt_uniform, (size_t)b.n_rec * s4 + 4, false)))
+				return rc;
+			CK(ntc::launch_restride(b.words, b.stride, s4, b.n_rec, c->d_rt_uniform, c->n_sm, c->stream));
+			c->n_launches++;
+			b.words = c->d_rt_uniform;
+			b.stride = s4;
+			b.n_words = (uint64_t)b.n_rec * s4;
+		}
+	}
 	uint32_t pmask = pipeline_config(c, b, record_is_piece, shape);
 	uint32_t retiled = 0;
 	if (!pmask && (rc = run_retiled(c, b, &retiled)))

@@ -313,6 +313,27 @@ cudaError_t launch_piece_tables(const BatchView& b, uint32_t kmin, uint32_t* d_p
 	return cudaGetLastError();
 }
 
+// uniform-stride batch whose stride is not a multiple of 4 words (tightly packed: 44 bytes per 150 bp read) -> the same
+// records at the next multiple of 4, which is what the scan kernel's 128-bit loads need
+__global__ void __launch_bounds__(256) restride_kernel(const uint32_t* __restrict__ in, uint32_t stride_in, uint32_t stride_out, uint64_t n_out_words,
+    uint32_t* __restrict__ out)
+{
+	for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_out_words; x += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t rec = x / stride_out;
+		const uint32_t w = (uint32_t)(x - rec * stride_out);
+		out[x] = w < stride_in ? __ldg(in + rec * stride_in + w) : 0u;
+	}
+}
+
+cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t stride_out, uint32_t n_rec, uint32_t* d_out, int n_sm, cudaStream_t st)
+{
+	const uint64_t n = (uint64_t)n_rec * stride_out;
+	if (n == 0)
+		return cudaSuccess;
+	restride_kernel<<<grid_for(n, 256, (unsigned)n_sm * 32u), 256, 0, st>>>(d_in, stride_in, stride_out, n, d_out);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_retile_count(const BatchView& b, uint32_t Lp, uint32_t D, uint32_t kmin, uint32_t* d_n_full, uint32_t* d_has_tail,
     uint32_t* d_tail_words, void* d_tmp, size_t tmp_bytes, cudaStream_t st)
 {

@@ -480,3 +480,20 @@ def test_hit_log_exchange_between_two_contexts_on_one_gpu(oracle):
         assert s0.log_counts()[1] is False
         t, f1b, _ = s0.finish(counters=True, hist=False)
         assert np.array_equal(t.reshape(-1), want) and np.array_equal(f1b, wf1)
+
+
+def test_tightly_packed_uniform_batches_take_the_pipeline(oracle):
+    """Uniform-stride batches whose stride is not a multiple of 4 words (44 bytes per 150 bp read) are padded on the
+    device and hashed by the pipeline; forced NTC_KERNEL_BITSLICE must accept them and the result stays exact."""
+    for L, kList in ((150, [32, 64]), (120, [31]), (171, [12, 32])):
+        n = 5000
+        stride = nt.stride_words(L, False)
+        assert stride % 4 != 0 or L == 171
+        words, _, want, wf1 = _uniform_case(oracle, 83, n, L, kList, 19, 7)       # aligned copy, for the oracle result
+        tight = nt.gen_packed(83, 0, n, L, 1, max(1, n // 4), stride)
+        with nt.Sketch(kList, rBits=19, sBits=7) as sk:
+            sk.set_kernel(nt.KERNEL_BITSLICE)
+            sk.submit(tight[:2000 * stride], None, 2000, stride)
+            sk.submit(tight[2000 * stride:], None, n - 2000, stride)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+        assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want), L
