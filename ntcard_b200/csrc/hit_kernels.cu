@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(256) hist_slices_kernel(const uint32_t* __rest
 	const uint64_t slice_len = (uint64_t)1 << bin_shift, per_k = (uint64_t)2 << rBits;
 	const uint32_t chunk = (uint32_t)min((uint64_t)kHistChunk, slice_len);
 	const uint32_t chunks_per_slice = (uint32_t)(slice_len / chunk);
-	const uint32_t s = order[blockIdx.x / chunks_per_slice];
+	const uint32_t s = order ? order[blockIdx.x / chunks_per_slice] : blockIdx.x / chunks_per_slice; // no list: every slice
 	const uint64_t first = (uint64_t)(s / nbins) * per_k + (uint64_t)(s % nbins) * slice_len + (uint64_t)(blockIdx.x % chunks_per_slice) * chunk;
 	uint32_t* ph = p_hist + (first >> rBits) * 65536; // a chunk lies inside one table (chunk <= 2^rBits: the host checks)
 	auto count = [&](uint32_t v) {
@@ -863,6 +863,8 @@ __global__ void __launch_bounds__(256) hist_slices_kernel(const uint32_t* __rest
 
 cudaError_t launch_hist_slices(const Pool& pool, const uint32_t* counters, const uint32_t* d_order, uint32_t n_order, uint32_t* d_phist, cudaStream_t st)
 {
+	if (!d_order)
+		n_order = pool.n_slices; // all of the sketch
 	if (n_order == 0)
 		return cudaSuccess;
 	const uint64_t slice_len = (uint64_t)1 << pool.bin_shift;

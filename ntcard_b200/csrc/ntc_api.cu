@@ -1253,7 +1253,10 @@ int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_h
 			CK(cudaMalloc((void**)&c->d_phist, (size_t)n_tables * 65536 * sizeof(uint32_t)));
 		CK(cudaMemsetAsync(c->d_phist, 0, (size_t)n_tables * 65536 * sizeof(uint32_t), c->stream));
 	}
-	if (t_Counter || p_hist) {
+	if (!t_Counter && p_hist && ntc::pl::launch_hist_slices(c->pool, c->d_counters, nullptr, 0, c->d_phist, c->stream) == cudaSuccess) {
+		c->n_launches++; // histogram only: the vectorised kernel, slice by slice
+	} else if (t_Counter || p_hist) {
+		cudaGetLastError();
 		CK(ntc::launch_narrow_hist(c->d_counters, n_tables, n_per_table, t_Counter ? c->d_narrow : nullptr,
 		    p_hist ? c->d_phist : nullptr, c->stream));
 		c->n_launches++;
