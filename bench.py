@@ -35,6 +35,7 @@ WORKLOADS = {
     "small": (1_000_000, 150, [32], 7, "dev: 1M synthetic 150 bp reads, k=32, s=7, r=27"),
     "multik": (10_000_000, 150, [32, 64, 96, 128], 7, "dev: 10M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27"),
     "k64s11": (10_000_000, 150, [64], 11, "dev: 10M synthetic 150 bp reads, k=64, s=11, r=27"),
+    "long10k": (200_000, 10_000, [31], 11, "dev (config 5 shape): 200k synthetic 10 kbp reads without N, k=31, s=11, r=27"),
 }
 RBITS = 27
 METRIC = "k-mers hashed/sec at k=32 on 150bp reads"

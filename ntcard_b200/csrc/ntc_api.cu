@@ -86,6 +86,8 @@ struct ntc_ctx {
 	size_t cap_rt_tail_words = 0;
 	uint32_t* d_rt_tail_off = nullptr;
 	size_t cap_rt_tail_off = 0;
+	uint32_t* d_rt_off = nullptr;      // offsets made up for uniform-stride batches of long records
+	size_t cap_rt_off = 0;
 	uint64_t n_retiled = 0;
 	// sketch pipeline (scan -> hit log -> apply), pipeline.h
 	ntc::pl::Pool pool{};
@@ -453,13 +455,23 @@ int run_roll64(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, uint32
 
 // Long ragged records (long reads, contigs split at N): cut them on the device into equal pieces of Lp bases every D bases
 // for the pipeline, plus one ragged tail per record for the general kernel.  Returns the k indices that were handled.
-int run_retiled(ntc_ctx* c, const ntc::BatchView& b, uint32_t* handled)
+int run_retiled(ntc_ctx* c, const ntc::BatchView& b_in, uint32_t* handled)
 {
 	*handled = 0;
-	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || !b.off || b.n_rec == 0 || getenv("NTC_NO_RETILE"))
+	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || b_in.n_rec == 0 || getenv("NTC_NO_RETILE"))
 		return NTC_OK;
-	if (b.n_words / b.n_rec < 40) // average record below ~600 bases: pieces would mostly be tails
+	if (b_in.n_words / b_in.n_rec < 40) // average record below ~600 bases: pieces would mostly be tails
 		return NTC_OK;
+	ntc::BatchView b = b_in;
+	if (!b.off) { // long records at a uniform stride: give them explicit offsets and treat them like a ragged batch
+		if ((uint64_t)b.n_rec * b.stride > 0xFFFFFFF0ull)
+			return NTC_OK;
+		int rc0;
+		if ((rc0 = grow(&c->d_rt_off, &c->cap_rt_off, (size_t)b.n_rec + 1, false)))
+			return rc0;
+		CK(ntc::launch_stride_offsets(b.stride, b.n_rec, c->d_rt_off, c->stream));
+		b.off = c->d_rt_off;
+	}
 	uint32_t kmask = 0, kmax = 0, kmin = 0xFFFFFFFFu;
 	for (unsigned ki = 0; ki < c->nK; ki++)
 		if (c->k[ki] <= 160 && ntc::pl::have_scan_kernel(c->k[ki], c->sBits)) {
@@ -755,6 +767,7 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->d_rt_uniform) cudaFree(c->d_rt_uniform);
 	if (c->d_rt_tail_words) cudaFree(c->d_rt_tail_words);
 	if (c->d_rt_tail_off) cudaFree(c->d_rt_tail_off);
+	if (c->d_rt_off) cudaFree(c->d_rt_off);
 	if (c->d_narrow) cudaFree(c->d_narrow);
 	if (c->d_phist) cudaFree(c->d_phist);
 	if (c->d_f1) cudaFree(c->d_f1);

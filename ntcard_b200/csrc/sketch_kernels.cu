@@ -334,6 +334,20 @@ cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t s
 	return cudaGetLastError();
 }
 
+__global__ void stride_offsets_kernel(uint32_t stride, uint32_t n_rec, uint32_t* __restrict__ off /* [n_rec + 1] */)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i <= n_rec)
+		off[i] = i * stride;
+}
+
+// word offsets of a uniform-stride batch, so that it can go through the kernels written for ragged batches
+cudaError_t launch_stride_offsets(uint32_t stride, uint32_t n_rec, uint32_t* d_off, cudaStream_t st)
+{
+	stride_offsets_kernel<<<(n_rec + 1 + 255) / 256, 256, 0, st>>>(stride, n_rec, d_off);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_retile_count(const BatchView& b, uint32_t Lp, uint32_t D, uint32_t kmin, uint32_t* d_n_full, uint32_t* d_has_tail,
     uint32_t* d_tail_words, void* d_tmp, size_t tmp_bytes, cudaStream_t st)
 {

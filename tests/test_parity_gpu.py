@@ -497,3 +497,16 @@ def test_tightly_packed_uniform_batches_take_the_pipeline(oracle):
             sk.submit(tight[2000 * stride:], None, n - 2000, stride)
             t, f1, _ = sk.finish(counters=True, hist=False)
         assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want), L
+
+
+def test_long_uniform_stride_records_are_retiled(oracle):
+    """Long reads at a uniform stride (device generators, fixed-length long-read batches) get explicit offsets and go
+    through the same re-tiling as ragged long records."""
+    n, L, kList = 1500, 3000, [32, 64]
+    words, stride, want, wf1 = _uniform_case(oracle, 91, n, L, kList, 20, 7, mode=0)
+    for kernel in (nt.KERNEL_AUTO, nt.KERNEL_ROLL64):
+        with nt.Sketch(kList, rBits=20, sBits=7) as sk:
+            sk.set_kernel(kernel)
+            sk.submit(words, None, n, stride)
+            t, f1, _ = sk.finish(counters=True, hist=False)
+        assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want), kernel
