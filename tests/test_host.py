@@ -119,3 +119,15 @@ def test_sbits_rule():
     # ntcard.cpp:427-431
     assert nt.apply_sbits_rule(49_999_999_999) == 7 and nt.apply_sbits_rule(50_000_000_000) == 11
     assert nt.apply_sbits_rule(60_000_000_000, sBits=9) == 9
+
+
+def test_bitslice_filter_selftest_on_cpu(tmp_path):
+    """tools/bitslice_selftest.cu, compiled as plain C++: the bit-sliced upper-ring filter of the scan kernel
+    (bitslice_core.cuh: step / sampled_mask / init_state / transpose32) marks exactly the k-mers ntComp samples
+    (ntcard.cpp:132-145), for k in {5, 12, 31, 32, 63, 64, 96, 128} and several sBits, on random reads."""
+    import subprocess
+    exe = os.path.join(str(tmp_path), "bs_selftest")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-x", "c++", "-o", exe, os.path.join(ROOT, "tools", "bitslice_selftest.cu")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert "ALL OK" in out and " 0 mismatches" in out and "mismatches" in out
+    assert all(" 0 mismatches" in l for l in out.splitlines() if "mismatches" in l)
