@@ -1,4 +1,4 @@
-# Builds the product: ntcard_b200/libntcard_b200.so (C-ABI + sm_100a kernels) and bin/ntcard (host CLI).
+# Builds the product: ntcard_b200/libntcard_b200.so (C-ABI + sm_100a kernels) and the host CLIs bin/ntcard, bin/nthll.
 # The checkers under oracle/ have their own Makefile.
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX = g++
@@ -11,14 +11,13 @@ BUILD = build
 # k mod 31 variants of the bit-sliced kernel to compile (each is one translation unit)
 BS_KMS ?= 0 1 2 3 4 12
 BS_KM_LIST = $(foreach n,$(BS_KMS),X($(n)))
-CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(SRC)/hit_kernels.cu $(SRC)/bitslice_dispatch.cu
+CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(SRC)/hit_kernels.cu $(SRC)/hll_kernels.cu $(SRC)/bitslice_dispatch.cu
 BS_OBJS = $(foreach n,$(BS_KMS),$(BUILD)/bitslice_km$(n).o)
 CPP_SRCS = $(SRC)/host_util.cpp
 CU_OBJS = $(patsubst $(SRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS))
 CPP_OBJS = $(patsubst $(SRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS))
 HDRS = $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)
 LIB = ntcard_b200/libntcard_b200.so
-CLI_SRCS = $(wildcard $(SRC)/cli/*.cpp)
 
 all: $(LIB) cli
 
@@ -43,14 +42,14 @@ $(BUILD)/%.o: $(SRC)/%.cpp $(HDRS)
 $(LIB): $(CU_OBJS) $(BS_OBJS) $(CPP_OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -Xlinker --exclude-libs,ALL
 
-ifneq ($(CLI_SRCS),)
-cli: bin/ntcard
-bin/ntcard: $(CLI_SRCS) $(LIB) $(HDRS)
+CLI_LINK = -Lntcard_b200 -lntcard_b200 -Wl,-rpath,'$$ORIGIN/../ntcard_b200' -lpthread
+cli: bin/ntcard bin/nthll
+bin/ntcard: $(SRC)/cli/ntcard_main.cpp $(SRC)/cli/reader.cpp $(SRC)/cli/reader.h $(LIB) $(HDRS)
 	@mkdir -p bin
-	$(CXX) $(CXXFLAGS) -fopenmp -Iinclude -o $@ $(CLI_SRCS) -Lntcard_b200 -lntcard_b200 -Wl,-rpath,'$$ORIGIN/../ntcard_b200' -lpthread
-else
-cli:
-endif
+	$(CXX) $(CXXFLAGS) -fopenmp -Iinclude -o $@ $(SRC)/cli/ntcard_main.cpp $(SRC)/cli/reader.cpp $(CLI_LINK)
+bin/nthll: $(SRC)/cli/nthll_main.cpp $(SRC)/cli/reader.cpp $(SRC)/cli/reader.h $(LIB) $(HDRS)
+	@mkdir -p bin
+	$(CXX) $(CXXFLAGS) -Iinclude -o $@ $(SRC)/cli/nthll_main.cpp $(SRC)/cli/reader.cpp $(CLI_LINK)
 
 clean:
 	rm -rf $(BUILD) $(LIB) bin

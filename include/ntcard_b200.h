@@ -166,6 +166,28 @@ int ntc_finish(ntc_ctx* ctx, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p
 int ntc_estimate(const uint32_t* p_hist, const uint16_t* t_Counter, unsigned rBits, unsigned sBits, unsigned covMax,
     double* F0, double* f);
 
+/* ---- nthll: the HyperLogLog F0 estimator that ships beside ntcard -------------------------
+ * Replaces, batch oriented like the sketch above:
+ *   ntRead(const string& seq, uint8_t* mVec)      nthll.cpp:99-104   every canonical ntHash of the sequence ...
+ *   ntComp(hVal, mVec)                            nthll.cpp:92-97    ... raises register hVal & (nBuck-1) to
+ *                                                                    clz(hVal & ~(nBuck-1)) when those upper bits are not all 0
+ *   tVec[j] = max over threads of mVec[j]         nthll.cpp:234-239
+ *   the estimate main() prints                    nthll.cpp:243-254
+ * ntc_hll_create makes a context in nthll mode (k = opt::kmLen, nBits = opt::nBits, nthll.cpp:45-48): batches go in
+ * through the same ntc_submit / ntc_submit_device / ntc_wait / ntc_sync / ntc_reset / ntc_totals as above (the readers'
+ * `seq.length() >= k` test, nthll.cpp:112,129,146, is implied: shorter records hold no k-mer); the entry points of the
+ * ntCard sketch (ntc_finish, ntc_counters_device, ntc_log_*, ...) return NTC_ESTATE on it, and ntc_hll_* return
+ * NTC_ESTATE on a sketch context.  d_regs: optional caller-owned DEVICE buffer of max(4, 2^nBits) bytes (e.g. a torch
+ * uint8 tensor that torch.distributed will max-all-reduce), NULL lets the context allocate it. */
+int ntc_hll_create(ntc_ctx** out, unsigned k, unsigned nBits, int device, void* d_regs, void* cuda_stream);
+/* The registers on the device (uint8 [2^nBits]); multi-GPU: wait (ntc_sync), max-all-reduce them, then ntc_hll_finish. */
+int ntc_hll_registers_device(ntc_ctx* ctx, void** d_regs, size_t* n_regs);
+/* Wait for the device; regs: [2^nBits] uint8, host, may be NULL; totKmer: [1] number of k-mers hashed, may be NULL. */
+int ntc_hll_finish(ntc_ctx* ctx, uint8_t* regs, uint64_t* totKmer);
+/* Host side, no device needed: the reference's arithmetic in the reference's order (nthll.cpp:243-254); canon != 0
+ * halves alpha (the reference always does, nthll.cpp:52,245).  nthll prints (unsigned long long)*est. */
+int ntc_hll_estimate(const uint8_t* regs, unsigned nBits, int canon, double* est);
+
 /* ---- host helpers ----------------------------------------------------------- */
 /* Pinned host memory for zero-copy submission. */
 void* ntc_host_alloc(size_t bytes);

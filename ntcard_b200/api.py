@@ -24,6 +24,7 @@ SYMBOLS = [
     "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
     "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_stage_times", "ntc_device_count",
     "ntc_last_error", "ntc_version",
+    "ntc_hll_create", "ntc_hll_registers_device", "ntc_hll_finish", "ntc_hll_estimate",
 ]
 
 
@@ -81,6 +82,10 @@ def _load():
         "ntc_device_count": (C.c_int, []),
         "ntc_last_error": (C.c_char_p, []),
         "ntc_version": (C.c_char_p, []),
+        "ntc_hll_create": (C.c_int, [C.POINTER(vp), C.c_uint, C.c_uint, C.c_int, vp, vp]),
+        "ntc_hll_registers_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "ntc_hll_finish": (C.c_int, [vp, vp, u64p]),
+        "ntc_hll_estimate": (C.c_int, [vp, C.c_uint, C.c_int, dblp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -360,6 +365,47 @@ class Sketch:
         ms, n = C.c_double(), C.c_uint64()
         _check(lib.ntc_kernel_time(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+def hll_estimate(regs, nBits=16, canon=True):
+    """The estimate nthll prints (nthll.cpp:243-254) from uint8 registers; host arithmetic, no device."""
+    regs = np.ascontiguousarray(regs, dtype=np.uint8)
+    if len(regs) != 1 << nBits:
+        raise ValueError("hll_estimate: need 2^nBits registers")
+    e = C.c_double()
+    _check(lib.ntc_hll_estimate(regs.ctypes.data, nBits, 1 if canon else 0, C.byref(e)))
+    return e.value
+
+
+class HllSketch(Sketch):
+    """nthll's HyperLogLog registers on one GPU (nthll.cpp:92-104): a context in nthll mode.  Batches go in through the
+    same submit / submit_device / submit_reads / wait / sync / reset as Sketch; the ntCard-sketch calls raise NtcError.
+
+    h = HllSketch(k=64, nBits=16)
+    h.submit_reads(reads)
+    regs, n_kmers = h.finish()              # uint8 [2^nBits], k-mers hashed
+    F0 = hll_estimate(regs, 16)             # nthll prints int(F0)
+    """
+
+    def __init__(self, k=64, nBits=16, device=0, d_regs=None, stream=None):
+        self.kList, self.nK, self.rBits, self.sBits, self.device, self.nBits = [int(k)], 1, 0, 0, device, nBits
+        h = C.c_void_p()
+        _check(lib.ntc_hll_create(C.byref(h), int(k), nBits, device, C.c_void_p(d_regs) if d_regs else None,
+                                  C.c_void_p(stream) if stream else None))
+        self.h = h
+        self.stream_handle = int(stream) if stream else None
+
+    def registers_device(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib.ntc_hll_registers_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def finish(self, registers=True):
+        """Returns (registers uint8 [2^nBits] or None, number of k-mers hashed)."""
+        regs = np.empty(1 << self.nBits, dtype=np.uint8) if registers else None
+        tot = np.zeros(1, dtype=np.uint64)
+        _check(lib.ntc_hll_finish(self.h, regs.ctypes.data if registers else None, tot.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return regs, int(tot[0])
 
 
 def write_hist(path, F1, F0, f, covMax):

@@ -363,11 +363,11 @@ static void read_sam(LineReader& in, BatchSubmitter& sub, bool has_header, const
 	}
 }
 
-bool read_file(const std::string& path, BatchSubmitter& sub)
+bool read_file(const std::string& path, BatchSubmitter& sub, bool nthll_rules)
 {
 	LineReader in(path);
 	if (!in.ok())
-		return false;
+		return nthll_rules; // nthll never checks the stream: an unreadable file contributes nothing (nthll.cpp:219-229)
 	const char* l;
 	size_t n;
 	std::string h;
@@ -392,6 +392,10 @@ bool read_file(const std::string& path, BatchSubmitter& sub)
 	size_t n2, n5;
 	if (token_at(h.data(), h.size(), 1, &t2, &n2) && token_at(h.data(), h.size(), 4, &t5, &n5) &&
 	    all_digits(std::string(t2, n2)) && all_digits(std::string(t5, n5))) {
+		read_sam(in, sub, false, h);
+		return true;
+	}
+	if (nthll_rules) { // nthll's getftype has no "unknown" answer: everything else is header-less SAM (nthll.cpp:86-88)
 		read_sam(in, sub, false, h);
 		return true;
 	}

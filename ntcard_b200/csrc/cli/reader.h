@@ -72,6 +72,8 @@ private:
 
 // Sniff the format on the first line and feed every sequence of the file to `sub`.
 // Returns false when the format is not recognised / the file cannot be read (ntcard.cpp:459-462).
-bool read_file(const std::string& path, BatchSubmitter& sub);
+// nthll_rules: the sniffer of nthll.cpp:73-90 instead -- the same three formats, but whatever is not FASTA / FASTQ /
+// SAM-with-header is read as header-less SAM, and unreadable files are skipped silently; never returns false.
+bool read_file(const std::string& path, BatchSubmitter& sub, bool nthll_rules = false);
 
 } // namespace ntcb

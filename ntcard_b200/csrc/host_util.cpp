@@ -256,4 +256,26 @@ int ntc_estimate(const uint32_t* p_hist, const uint16_t* t_Counter, unsigned rBi
 	return NTC_OK;
 }
 
+// The estimate nthll prints, nthll.cpp:243-254, in the reference's operation order: alpha = 1.4426 / (1 + 1.079 / nBuck),
+// halved for canonical k-mers (:245; the reference's opt::canon is always true), harmonic mean of 2^register.
+int ntc_hll_estimate(const uint8_t* regs, unsigned nBits, int canon, double* est)
+{
+	if (!regs || !est || nBits < 1 || nBits > 30)
+		return set_err(NTC_EINVAL, "ntc_hll_estimate: bad argument");
+	const unsigned nBuck = ((unsigned)1) << nBits;
+	double pEst = 0.0, zEst = 0.0, eEst = 0.0, alpha = 0.0;
+	alpha = 1.4426 / (1 + 1.079 / nBuck);
+	if (canon)
+		alpha /= 2;
+	for (unsigned j = 0; j < nBuck; j++) {
+		if (regs[j] > 63)
+			return set_err(NTC_EINVAL, "ntc_hll_estimate: register %u holds %u (> 63)", j, (unsigned)regs[j]);
+		pEst += 1.0 / ((uint64_t)1 << regs[j]);
+	}
+	zEst = 1.0 / pEst;
+	eEst = alpha * nBuck * nBuck * zEst;
+	*est = eEst;
+	return NTC_OK;
+}
+
 } // extern "C"

@@ -33,6 +33,10 @@ cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t s
 cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
     const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t* d_counters, unsigned long long* d_f1, uint32_t kmask,
     int n_sm, cudaStream_t st);
+// nthll's HyperLogLog registers (hll_kernels.cu): d_regs = 2^nBits one-byte registers (at least 4 bytes, 4-byte aligned)
+cudaError_t launch_hll(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
+    const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t nBits, uint8_t* d_regs, unsigned long long* d_f1, int n_sm,
+    cudaStream_t st);
 cudaError_t launch_narrow_hist(const uint32_t* d_counters, uint32_t n_tables, uint64_t n_per_table, uint16_t* d_narrow,
     uint32_t* d_phist, cudaStream_t st);
 cudaError_t launch_hist_range(const uint32_t* d_src, uint64_t first, uint64_t n, uint32_t rBits, uint32_t* d_phist, cudaStream_t st);

@@ -56,6 +56,11 @@ struct ntc_ctx {
 	unsigned k[NTC_MAX_K] = {};
 	int kernel = NTC_KERNEL_AUTO;
 	unsigned gap = 0;  // -g: spaced seed with `gap` don't-care bases in the middle (general kernel only)
+	// nthll mode (ntc_hll_create): HyperLogLog registers instead of the ntCard sketch; no counters, no hit log
+	unsigned hll_bits = 0;
+	uint8_t* d_hll = nullptr; // 2^hll_bits one-byte registers
+	bool own_hll = false;
+	size_t hll_bytes = 0;
 	uint32_t* d_counters = nullptr;
 	bool own_counters = false;
 	size_t n_counters = 0;
@@ -427,27 +432,48 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	return NTC_OK;
 }
 
+// Piece tables of a batch whose records may be longer than one piece (general kernel, HLL kernel).
+int prepare_pieces(ntc_ctx* c, const ntc::BatchView& b, uint64_t* bound_out)
+{
+	int rc;
+	const uint64_t bound = (uint64_t)b.n_rec + (16 * b.n_words) / ntc::PIECE_STARTS + 1;
+	if (bound > 0xFFFFFFFFull)
+		return set_err(NTC_EINVAL, "batch too large: %llu pieces", (unsigned long long)bound);
+	if ((rc = grow(&c->d_piece_first, &c->cap_piece_first, (size_t)b.n_rec + 1, false)) ||
+	    (rc = grow(&c->d_piece_rec, &c->cap_piece_rec, (size_t)bound, false)))
+		return rc;
+	size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
+	char* t = (char*)c->d_scan_tmp;
+	if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
+		return rc;
+	c->d_scan_tmp = t;
+	CK(ntc::launch_piece_tables(b, c->kmin, c->d_piece_first, c->d_piece_rec, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
+	c->n_launches += 3;
+	*bound_out = bound;
+	return NTC_OK;
+}
+
 // The general kernel over one batch for the k indices in kmask (direct increments: the caller has flushed).
 int run_roll64(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, uint32_t kmask)
 {
 	int rc;
 	uint64_t bound = 0;
-	if (!record_is_piece) {
-		bound = (uint64_t)b.n_rec + (16 * b.n_words) / ntc::PIECE_STARTS + 1;
-		if (bound > 0xFFFFFFFFull)
-			return set_err(NTC_EINVAL, "batch too large: %llu pieces", (unsigned long long)bound);
-		if ((rc = grow(&c->d_piece_first, &c->cap_piece_first, (size_t)b.n_rec + 1, false)) ||
-		    (rc = grow(&c->d_piece_rec, &c->cap_piece_rec, (size_t)bound, false)))
-			return rc;
-		size_t tmp = ntc::piece_scan_temp_bytes(b.n_rec + 1);
-		char* t = (char*)c->d_scan_tmp;
-		if ((rc = grow(&t, &c->cap_scan_tmp, tmp, false)))
-			return rc;
-		c->d_scan_tmp = t;
-		CK(ntc::launch_piece_tables(b, c->kmin, c->d_piece_first, c->d_piece_rec, c->d_scan_tmp, c->cap_scan_tmp, c->stream));
-		c->n_launches += 3;
-	}
+	if (!record_is_piece && (rc = prepare_pieces(c, b, &bound)))
+		return rc;
 	CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters, c->d_f1, kmask, c->n_sm,
+	    c->stream));
+	c->n_launches += 1;
+	return NTC_OK;
+}
+
+// nthll mode: every canonical hash of the batch into the HyperLogLog registers (hll_kernels.cu)
+int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
+{
+	int rc;
+	uint64_t bound = 0;
+	if (!record_is_piece && (rc = prepare_pieces(c, b, &bound)))
+		return rc;
+	CK(ntc::launch_hll(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->hll_bits, c->d_hll, c->d_f1, c->n_sm,
 	    c->stream));
 	c->n_launches += 1;
 	return NTC_OK;
@@ -547,6 +573,14 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
 		return rc;
 	CK(cudaEventRecord(e0, c->stream));
+	if (c->hll_bits) {
+		if ((rc = run_hll(c, b_in, record_is_piece)))
+			return rc;
+		CK(cudaEventRecord(e1, c->stream));
+		c->timing.emplace_back(e0, e1);
+		c->n_batches++;
+		return NTC_OK;
+	}
 	PipeShape shape[NTC_MAX_K];
 	ntc::BatchView b = b_in;
 	if (!b.off && (b.stride & 3u) && b.stride >= 2 && b.n_rec >= 1024 && c->use_pipeline && !c->gap && c->kernel != NTC_KERNEL_ROLL64 &&
@@ -622,6 +656,18 @@ bool single_piece_records(const ntc_ctx* c, uint32_t max_rec_words)
 
 } // namespace
 
+// entry points of the ntCard sketch are not valid on a context made by ntc_hll_create, and vice versa
+#define SKETCH_ONLY(c, name)                                                                               \
+	do {                                                                                                   \
+		if ((c)->hll_bits)                                                                                 \
+			return set_err(NTC_ESTATE, name ": not valid on an nthll context (ntc_hll_create)");           \
+	} while (0)
+#define HLL_ONLY(c, name)                                                                                  \
+	do {                                                                                                   \
+		if (!(c)->hll_bits)                                                                                \
+			return set_err(NTC_ESTATE, name ": needs a context made by ntc_hll_create");                   \
+	} while (0)
+
 extern "C" {
 
 const char* ntc_last_error(void) { return ntc::last_err(); }
@@ -637,8 +683,8 @@ int ntc_device_count(void)
 	return n;
 }
 
-int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits, unsigned sBits, int device, void* d_counters,
-    void* cuda_stream)
+static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits, unsigned sBits, int device, void* d_counters,
+    void* cuda_stream, unsigned hll_bits, void* d_hll)
 {
 	if (!out || !kList || nK == 0 || nK > NTC_MAX_K)
 		return set_err(NTC_EINVAL, "ntc_create: need 1..%d k values", NTC_MAX_K);
@@ -663,7 +709,9 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 		c->kmin = std::min(c->kmin, kList[i]);
 		c->kmax = std::max(c->kmax, kList[i]);
 	}
-	c->n_counters = (size_t)nK * NTC_NSAMP << rBits;
+	c->n_counters = hll_bits ? 0 : (size_t)nK * NTC_NSAMP << rBits;
+	c->hll_bits = hll_bits;
+	c->hll_bytes = hll_bits ? std::max((size_t)4, (size_t)1 << hll_bits) : 0;
 	int rc = NTC_OK;
 	auto fail = [&](int code) {
 		ntc_destroy(c);
@@ -690,7 +738,14 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 		c->own_stream = true;
 	}
 	CKF(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-	if (d_counters) {
+	if (hll_bits) {
+		if (d_hll) {
+			c->d_hll = (uint8_t*)d_hll;
+		} else {
+			CKF(cudaMalloc((void**)&c->d_hll, c->hll_bytes));
+			c->own_hll = true;
+		}
+	} else if (d_counters) {
 		c->d_counters = (uint32_t*)d_counters;
 	} else {
 		CKF(cudaMalloc((void**)&c->d_counters, c->n_counters * sizeof(uint32_t)));
@@ -701,7 +756,7 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 	ntc::DevParams hp;
 	build_params(c, &hp);
 	CKF(cudaMemcpy(c->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
-	{
+	if (!hll_bits) {
 		std::vector<uint32_t> tab(8 * 256 * 4);
 		ntc::pl::build_tables(tab.data());
 		CKF(cudaMalloc((void**)&c->d_bs_tab, tab.size() * sizeof(uint32_t)));
@@ -719,7 +774,7 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 	c->use_pipeline = !(getenv("NTC_PIPELINE") && atoi(getenv("NTC_PIPELINE")) == 0);
 	if (getenv("NTC_CHUNK_WAVES"))
 		c->chunk_waves = (unsigned)atoi(getenv("NTC_CHUNK_WAVES"));
-	if ((rc = pool_create(c)))
+	if (!hll_bits && (rc = pool_create(c)))
 		return fail(rc);
 	for (int i = 0; i < NBUF; i++) {
 		CKF(cudaEventCreateWithFlags(&c->stage[i].copied, cudaEventDisableTiming));
@@ -730,6 +785,19 @@ int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits
 		return fail(rc);
 	*out = c;
 	return NTC_OK;
+}
+
+int ntc_create(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigned rBits, unsigned sBits, int device, void* d_counters,
+    void* cuda_stream)
+{
+	return create_ctx(out, kList, nK, rBits, sBits, device, d_counters, cuda_stream, 0, nullptr);
+}
+
+int ntc_hll_create(ntc_ctx** out, unsigned k, unsigned nBits, int device, void* d_regs, void* cuda_stream)
+{
+	if (nBits < 1 || nBits > 30)
+		return set_err(NTC_EINVAL, "ntc_hll_create: nBits=%u out of range (1..30)", nBits);
+	return create_ctx(out, &k, 1, 1, 1, device, nullptr, cuda_stream, nBits, d_regs);
 }
 
 void ntc_destroy(ntc_ctx* c)
@@ -785,6 +853,7 @@ void ntc_destroy(ntc_ctx* c)
 	}
 	if (c->d_tile_info) cudaFree(c->d_tile_info);
 	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
+	if (c->own_hll && c->d_hll) cudaFree(c->d_hll);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -797,6 +866,13 @@ int ntc_reset(ntc_ctx* c)
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
+	if (c->hll_bits) { // nthll mode: fresh registers (nthll.cpp:200-201)
+		CK(cudaMemsetAsync(c->d_hll, 0, c->hll_bytes, c->stream));
+		CK(cudaMemsetAsync(c->d_f1, 0, NTC_MAX_K * sizeof(unsigned long long), c->stream));
+		c->totals_overridden = false;
+		c->pending = false;
+		return NTC_OK;
+	}
 	// The counters are NOT cleared here: the first flush after a reset writes zeros slice by slice right before it
 	// applies the slice's increments (apply_kernel, state 0), which saves one full pass over the 1 GiB/k sketch.
 	CK(cudaMemsetAsync(c->d_pool_ctl_region, 0, c->pool_ctl_bytes, c->stream)); // empty log, state = not materialised
@@ -819,6 +895,7 @@ int ntc_set_gap(ntc_ctx* c, unsigned gap)
 {
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
+	SKETCH_ONLY(c, "ntc_set_gap");
 	if (gap != 0) {
 		if (c->nK != 1)
 			return set_err(NTC_EINVAL, "ntc_set_gap: gap seeds support one k only (ntcard.cpp:397)");
@@ -981,6 +1058,7 @@ int ntc_log_info(ntc_ctx* c, uint32_t* n_slices, uint64_t* counters_per_slice, u
 {
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
+	SKETCH_ONLY(c, "ntc_log_info");
 	if (n_slices) *n_slices = c->pool.n_slices;
 	if (counters_per_slice) *counters_per_slice = (uint64_t)1 << c->pool.bin_shift;
 	if (entries_per_block) *entries_per_block = ntc::pl::kBlkEntries;
@@ -991,6 +1069,7 @@ int ntc_log_counts(ntc_ctx* c, uint32_t* nblk, int* exportable, uint32_t* pool_i
 {
 	if (!c || !nblk || !exportable)
 		return set_err(NTC_EINVAL, "ntc_log_counts: bad argument");
+	SKETCH_ONLY(c, "ntc_log_counts");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
@@ -1036,6 +1115,7 @@ int ntc_log_export(ntc_ctx* c, const uint32_t* slices, uint32_t n, void* d_block
 {
 	if (!c || (n && !slices) || c->h_nblk.size() != c->pool.n_slices)
 		return set_err(NTC_EINVAL, "ntc_log_export: bad argument (call ntc_log_counts first)");
+	SKETCH_ONLY(c, "ntc_log_export");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
@@ -1066,6 +1146,7 @@ int ntc_log_import(ntc_ctx* c, const void* d_blocks, uint32_t n_blocks, const ui
 {
 	if (!c || (n_blocks && (!d_blocks || !runs_in)) || c->h_nblk.size() != c->pool.n_slices)
 		return set_err(NTC_EINVAL, "ntc_log_import: bad argument (call ntc_log_counts first)");
+	SKETCH_ONLY(c, "ntc_log_import");
 	if (n_blocks == 0)
 		return NTC_OK;
 	int rc;
@@ -1119,6 +1200,7 @@ int ntc_flush_slices(ntc_ctx* c, const uint8_t* owned)
 {
 	if (!c || !owned)
 		return set_err(NTC_EINVAL, "ntc_flush_slices: bad argument");
+	SKETCH_ONLY(c, "ntc_flush_slices");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
@@ -1152,6 +1234,7 @@ int ntc_hist_slices(ntc_ctx* c, const uint8_t* owned, uint32_t* p_hist, void* d_
 {
 	if (!c || !owned || (!p_hist && !d_p_hist))
 		return set_err(NTC_EINVAL, "ntc_hist_slices: bad argument");
+	SKETCH_ONLY(c, "ntc_hist_slices");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
@@ -1192,6 +1275,7 @@ int ntc_counters_device(ntc_ctx* c, void** d_counters, size_t* n_counters)
 {
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
+	SKETCH_ONLY(c, "ntc_counters_device");
 	int rc;
 	if (c->partial)
 		return set_err(NTC_ESTATE, "ntc_counters_device: after ntc_flush_slices only ntc_hist_slices / ntc_totals / ntc_reset are valid");
@@ -1248,6 +1332,7 @@ int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_h
 {
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
+	SKETCH_ONLY(c, "ntc_finish");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
@@ -1293,10 +1378,39 @@ int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_h
 	return NTC_OK;
 }
 
+// ---- nthll mode --------------------------------------------------------------------------------------------
+int ntc_hll_registers_device(ntc_ctx* c, void** d_regs, size_t* n_regs)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	HLL_ONLY(c, "ntc_hll_registers_device");
+	if (d_regs) *d_regs = c->d_hll;
+	if (n_regs) *n_regs = (size_t)1 << c->hll_bits;
+	return NTC_OK;
+}
+
+int ntc_hll_finish(ntc_ctx* c, uint8_t* regs, uint64_t* totKmer)
+{
+	if (!c)
+		return set_err(NTC_EINVAL, "null context");
+	HLL_ONLY(c, "ntc_hll_finish");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	if (regs)
+		CK(cudaMemcpyAsync(regs, c->d_hll, (size_t)1 << c->hll_bits, cudaMemcpyDeviceToHost, c->stream));
+	if ((rc = ntc_sync(c)))
+		return rc;
+	if (totKmer && (rc = ntc_totals(c, totKmer)))
+		return rc;
+	return NTC_OK;
+}
+
 int ntc_hist_range(ntc_ctx* c, const void* d_counters, uint64_t first, uint64_t n, uint32_t* p_hist)
 {
 	if (!c || !d_counters || !p_hist || first + n > c->n_counters)
 		return set_err(NTC_EINVAL, "ntc_hist_range: bad argument");
+	SKETCH_ONLY(c, "ntc_hist_range");
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;

@@ -178,3 +178,14 @@ def _buffer(device, name, n_words):
         buf = torch.empty(max(int(n_words * 1.25), 1024), dtype=torch.int32, device=device)
         _BUFFERS[key] = buf
     return buf
+
+
+def all_reduce_hll(registers: torch.Tensor) -> torch.Tensor:
+    """nthll's only reduction (nthll.cpp:234-239: tVec[j] = max over threads of mVec[j]), across ranks: an in-place MAX
+    all-reduce of the uint8 HyperLogLog registers (the tensor HllSketch was created on, or a CPU tensor with gloo).
+    64 KiB at the default 2^16 registers: one latency-bound collective; NCCL and gloo both reduce uint8."""
+    if registers.dtype != torch.uint8:
+        raise TypeError("HyperLogLog registers are uint8")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(registers, op=dist.ReduceOp.MAX)
+    return registers

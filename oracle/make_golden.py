@@ -20,7 +20,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.pyoracle import Oracle, Reference, REF_CLI, build  # noqa: E402
+from oracle.pyoracle import HLL_REF_CLI, HllReference, Oracle, Reference, REF_CLI, build  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -85,9 +85,68 @@ def gap_golden():
     print("gap_cases.json", os.path.getsize(os.path.join(GOLD, "gap_cases.json")))
 
 
+def fnv_bytes(a):
+    """FNV-1a-64 over a uint8 array (offset 0xcbf29ce484222325, prime 0x100000001b3)."""
+    h = 0xcbf29ce484222325
+    for v in bytes(a):
+        h = ((h ^ v) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def hll_golden():
+    """tests/golden/hll_cases.json: nthll, the HyperLogLog estimator beside ntcard (nthll.cpp:92-104 ntComp / ntRead,
+    :243-254 the estimate) -- register digests from the reference's own ntRead, and the unmodified CLI's output line."""
+    build(ref=True)
+    orc, ref = Oracle(), HllReference()
+
+    def gen(S, n, L, mode=0, U=0):
+        a = orc.gen_reads(S, 0, n, L, mode, U)
+        return [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+
+    out = {"source": "ntRead / ntComp of the unmodified reference nthll.cpp via oracle/_ref/libnthll_ref.so; the estimate is computed "
+                     "by oracle/_ref/nthll_ref (the unmodified CLI) for the cli cases; reads from the SURVEY 8d generator "
+                     "(S, n, L, mode, U)", "registers": [], "cli": {}}
+    for name, g, k, nBits in (("rep_k32_b16", [21, 6000, 150, 1, 750], 32, 16), ("uni_k64_b16", [22, 6000, 150, 0, 0], 64, 16),
+                              ("nmode_k31_b12", [4, 2000, 400, 2, 0], 31, 12), ("rep_k12_b4", [23, 3000, 150, 1, 300], 12, 4),
+                              ("uni_k96_b18", [24, 4000, 150, 0, 0], 96, 18), ("uni_k150_b10", [25, 3000, 150, 0, 0], 150, 10),
+                              ("long_k20_b17", [26, 40, 20000, 2, 0], 20, 17), ("uni_k1_b1", [27, 50, 40, 0, 0], 1, 1)):
+        reads = gen(*g)
+        regs = ref.hll_registers(reads, k, nBits, nthreads=4)
+        case = {"name": name, "gen": g, "k": k, "nBits": nBits, "digest": f"{fnv_bytes(regs):#018x}", "max": int(regs.max()),
+                "nonzero": int(np.count_nonzero(regs)), "sum": int(regs.astype(np.uint64).sum())}
+        if nBits <= 4:
+            case["regs"] = [int(x) for x in regs]
+        out["registers"].append(case)
+    with tempfile.TemporaryDirectory() as td:
+        g = [1, 20000, 150, 1, 2500]
+        reads = gen(*g)
+        fq, fa, sam = (os.path.join(td, n) for n in ("a.fq", "a.fa", "a.sam"))
+        with open(fq, "w") as f:
+            for i, r in enumerate(reads):
+                f.write(f"@r{i}\n{r.decode()}\n+\n{'I' * len(r)}\n")
+        with open(fa, "w") as f:
+            for i, r in enumerate(reads):
+                s_ = r.decode()
+                f.write(f">r{i}\n" + "\n".join(s_[j:j + 60] for j in range(0, len(s_), 60)) + "\n")
+        with open(sam, "w") as f:
+            f.write("@HD\tVN:1.6\n@SQ\tSN:x\tLN:1000\n")
+            for i, r in enumerate(reads):
+                f.write(f"r{i}\t4\t*\t0\t0\t*\t*\t0\t0\t{r.decode()}\t{'I' * len(r)}\n")
+        for tag, args, files in (("fq_k32", ["-k32"], [fq]), ("fq_default", [], [fq]), ("fa_k32", ["-k32"], [fa]), ("sam_k32", ["-k32"], [sam]),
+                                 ("fq_k12_b12_t2", ["-k12", "-b12", "-t2"], [fq, fa]), ("fq_k151", ["-k151"], [fq])):
+            r = subprocess.run([HLL_REF_CLI] + args + files, capture_output=True, text=True, check=True)
+            out["cli"][tag] = {"args": args, "files": [os.path.basename(x) for x in files], "stdout": r.stdout}
+        out["cli"]["gen_a"] = {"S": g[0], "n": g[1], "L": g[2], "mode": g[3], "U": g[4]}
+    with open(os.path.join(GOLD, "hll_cases.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("hll_cases.json", os.path.getsize(os.path.join(GOLD, "hll_cases.json")))
+
+
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "gap":
         return gap_golden()
+    if len(sys.argv) > 2 and sys.argv[1] == "--only" and sys.argv[2] == "hll":
+        return hll_golden()
     build(ref=True)
     os.makedirs(GOLD, exist_ok=True)
     ref = Reference()

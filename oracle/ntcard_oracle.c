@@ -338,6 +338,60 @@ void orc_stread_batch(const char* seqs, const uint64_t* off, size_t n, unsigned 
 	}
 }
 
+/* ---- nthll: the HyperLogLog F0 estimator that ships beside ntcard (nthll.cpp) -----------------------------------
+ * ntComp (nthll.cpp:92-97): with nBuck = 2^nBits registers, a canonical hash h whose bits above the low nBits are not
+ * all zero updates register h & (nBuck-1) with run0 = clz(h & ~(nBuck-1)) if that is larger.  ntRead (nthll.cpp:99-104)
+ * walks the sequence with the same ntHashIterator as ntcard; the readers skip sequences shorter than k
+ * (nthll.cpp:112,129,146).  Threads keep private registers merged by max (nthll.cpp:213-241). */
+static void orc_hll_read(const char* seq, size_t len, unsigned k, unsigned nBits, uint8_t* m)
+{
+	const uint64_t nBuck = (uint64_t)1 << nBits;
+	orc_iter it = { seq, len, k, 0, 0, 0 };
+	if (len < k)
+		return;
+	orc_iter_init(&it);
+	while (it.pos != SIZE_MAX) {
+		const uint64_t h = orc_iter_hash(&it), top = h & ~(nBuck - 1);
+		if (top) {
+			const uint8_t run0 = (uint8_t)__builtin_clzll(top);
+			if (run0 > m[h & (nBuck - 1)])
+				m[h & (nBuck - 1)] = run0;
+		}
+		orc_iter_next(&it);
+	}
+}
+
+void orc_hll_batch(const char* seqs, const uint64_t* off, size_t n, unsigned k, unsigned nBits, uint8_t* regs, int nthreads)
+{
+	const uint64_t nBuck = (uint64_t)1 << nBits;
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+	{
+		uint8_t* m = (uint8_t*)calloc(nBuck, 1);
+#pragma omp for schedule(dynamic, 1024)
+		for (size_t i = 0; i < n; i++)
+			orc_hll_read(seqs + off[i], off[i + 1] - off[i], k, nBits, m);
+#pragma omp critical(orc_hll_merge)
+		for (uint64_t j = 0; j < nBuck; j++)
+			if (regs[j] < m[j])
+				regs[j] = m[j];
+		free(m);
+	}
+}
+
+/* The estimate main() prints (nthll.cpp:243-254), canonical k-mers (alpha / 2, nthll.cpp:245). */
+double orc_hll_estimate(const uint8_t* regs, unsigned nBits)
+{
+	const unsigned nBuck = 1u << nBits;
+	double pEst = 0.0, zEst, eEst, alpha;
+	alpha = 1.4426 / (1 + 1.079 / nBuck);
+	alpha /= 2;
+	for (unsigned j = 0; j < nBuck; j++)
+		pEst += 1.0 / ((uint64_t)1 << regs[j]);
+	zEst = 1.0 / pEst;
+	eEst = alpha * nBuck * nBuck * zEst;
+	return eEst;
+}
+
 /* compEst: ntcard.cpp:237-275.  f must hold 65536 doubles.  imax (2..65535)
  * truncates the recurrence; f[i] for i <= imax is identical to the full run
  * because f[i] depends only on f[j], j < i (ntcard.cpp:266-272).

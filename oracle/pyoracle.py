@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libntcard_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libntcard_ref.so")
 REF_CLI = os.path.join(HERE, "_ref", "ntcard_ref")
+HLL_REF_SO = os.path.join(HERE, "_ref", "libnthll_ref.so")
+HLL_REF_CLI = os.path.join(HERE, "_ref", "nthll_ref")
 
 _u64p = C.POINTER(C.c_uint64)
 _u32p = C.POINTER(C.c_uint32)
@@ -94,6 +96,9 @@ class Oracle(_Lib):
         L.orc_table_digest.restype = C.c_uint64
         L.orc_table_digest.argtypes = [_u16p, C.c_uint64, _u64p, _u64p, _u32p, _u64p]
         L.orc_max_threads.restype = C.c_int
+        L.orc_hll_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_uint, C.c_uint, C.c_void_p, C.c_int]
+        L.orc_hll_estimate.restype = C.c_double
+        L.orc_hll_estimate.argtypes = [C.c_void_p, C.c_uint]
         L.orc_st_hash_seq.restype = C.c_size_t
         L.orc_st_hash_seq.argtypes = [C.c_char_p, C.c_size_t, C.c_uint, C.c_uint, _u64p, C.c_size_t]
         L.orc_stread_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, _u16p, _u64p, C.c_int]
@@ -134,6 +139,18 @@ class Oracle(_Lib):
         off = np.zeros(len(reads) + 1, dtype=np.uint64)
         np.cumsum(lens, out=off[1:])
         return np.frombuffer(b"".join(reads) + b"\0", dtype=np.uint8), off
+
+    def hll_registers(self, reads, k, nBits=16, nthreads=1):
+        """nthll's HyperLogLog registers (uint8 [2^nBits]) over reads (nthll.cpp:92-104, 213-241)."""
+        regs = np.zeros(1 << nBits, dtype=np.uint8)
+        buf, off = self._flat(reads)
+        self.lib.orc_hll_batch(buf.ctypes.data, _ptr(off, _u64p), len(off) - 1, k, nBits, regs.ctypes.data, nthreads)
+        return regs
+
+    def hll_estimate(self, regs, nBits=16):
+        """The estimate nthll prints (nthll.cpp:243-254)."""
+        regs = np.ascontiguousarray(regs, dtype=np.uint8)
+        return self.lib.orc_hll_estimate(regs.ctypes.data, nBits)
 
     def st_hash_seq(self, seq: bytes, k, gap):
         """Gap-seed hashes (stHashIterator + NTMSM64) of a sequence, iterator order."""
@@ -271,3 +288,26 @@ class Reference(_Lib):
 
     def max_threads(self):
         return self.lib.ref_max_threads()
+
+
+class HllReference:
+    """The unmodified reference nthll.cpp behind ctypes (oracle/_ref/libnthll_ref.so): its own ntRead / ntComp."""
+
+    def __init__(self, path=HLL_REF_SO):
+        self.lib = C.CDLL(path)
+        self.lib.ref_hll_set.argtypes = [C.c_uint, C.c_uint]
+        self.lib.ref_hll_batch.argtypes = [C.c_void_p, _u64p, C.c_size_t, C.c_void_p, C.c_int]
+
+    @staticmethod
+    def available():
+        return os.path.exists(HLL_REF_SO)
+
+    def hll_registers(self, reads, k, nBits=16, nthreads=1):
+        self.lib.ref_hll_set(k, nBits)
+        regs = np.zeros(1 << nBits, dtype=np.uint8)
+        lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=off[1:])
+        buf = np.frombuffer(b"".join(reads) + b"\0", dtype=np.uint8)
+        self.lib.ref_hll_batch(buf.ctypes.data, _ptr(off, _u64p), len(off) - 1, regs.ctypes.data, nthreads)
+        return regs
