@@ -8,8 +8,9 @@ CXXFLAGS = -O3 -std=c++17 -fPIC -Wall -Wextra -ffp-contract=off
 SRC = ntcard_b200/csrc
 BUILD = build
 
-# k mod 31 variants of the bit-sliced kernel to compile (each is one translation unit)
-BS_KMS ?= 0 1 2 3 4 12
+# k mod 31 variants of the bit-sliced scan kernel to compile (each is one translation unit, ~3 s and 0.45 MB): all of them, so that
+# every k < 288 takes the pipeline
+BS_KMS ?= 0 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 23 24 25 26 27 28 29 30
 BS_KM_LIST = $(foreach n,$(BS_KMS),X($(n)))
 CU_SRCS = $(SRC)/ntc_api.cu $(SRC)/sketch_kernels.cu $(SRC)/hit_kernels.cu $(SRC)/hll_kernels.cu $(SRC)/bitslice_dispatch.cu
 BS_OBJS = $(foreach n,$(BS_KMS),$(BUILD)/bitslice_km$(n).o)
@@ -26,7 +27,7 @@ $(BUILD)/bitslice_km%.o: $(SRC)/bitslice_inst.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -DBS_KM=$* -c $< -o $@ 2> $(BUILD)/bitslice_km$*.ptxas.log || (cat $(BUILD)/bitslice_km$*.ptxas.log; exit 1)
 	@grep -E "error|warning|spill|registers" $(BUILD)/bitslice_km$*.ptxas.log | grep -v "0 bytes spill" | head -8 || true
 
-$(BUILD)/bitslice_dispatch.o: $(SRC)/bitslice_dispatch.cu $(HDRS)
+$(BUILD)/bitslice_dispatch.o: $(SRC)/bitslice_dispatch.cu $(HDRS) Makefile
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) '-DBS_KM_LIST=$(BS_KM_LIST)' -c $< -o $@
 

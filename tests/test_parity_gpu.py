@@ -215,6 +215,27 @@ def test_bitslice_uniform_reads(oracle, L, kList, sBits):
     assert np.array_equal(t.reshape(-1), want)
 
 
+@pytest.mark.parametrize("L,sBits,n,kList", [(150, 7, 5000, list(range(13, 29))), (150, 7, 5000, list(range(29, 44))),
+                                            (150, 11, 40000, [21, 25, 41, 51, 55, 71, 77, 91, 101, 121, 127, 150]),
+                                            (250, 7, 5000, [21, 33, 45, 57, 69, 81, 111, 151, 171, 200, 222, 250]),
+                                            (300, 11, 40000, [35, 99, 160, 201, 255, 287, 288, 300])])
+def test_bitslice_every_k_class(oracle, L, sBits, n, kList):
+    """every k mod 31 variant of the scan kernel (Makefile BS_KMS = 0..30) against the oracle, forced: k = 13..43 covers the
+    31 classes once, the other lists are the usual assembly k values and k up to the record length (k >= 288: general kernel)"""
+    a = oracle.gen_reads(37, 0, n, L, 1, n // 4)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, kList, 18, sBits, nthreads=4)
+    stride = nt.stride_words(L)
+    words = nt.gen_packed(37, 0, n, L, 1, n // 4, stride)
+    with nt.Sketch(kList, rBits=18, sBits=sBits) as sk:
+        if max(kList) < 288:
+            sk.set_kernel(nt.KERNEL_BITSLICE)       # fails loudly if a class has no variant
+        sk.submit(words, None, n, stride)
+        t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1)
+    assert np.array_equal(t.reshape(-1), want)
+
+
 def test_bitslice_mixed_lengths_in_uniform_stride(oracle):
     """Records of different lengths inside a uniform-stride batch: tiles that are not uniform fall back
     to the 64-bit path inside the kernel; results stay exact."""

@@ -98,6 +98,20 @@ int main()
 	bad += check<4, 7>(128, 3000);
 	bad += check<1, 7>(63, 3000);
 	bad += check<5, 3>(5, 1000);
+	// every k mod 31 class the library compiles (Makefile BS_KMS = 0..30): k = 31 + KM at s = 7, and the usual assembly k values
+#define CLS(KM) bad += check<KM, 7>(31 + KM, 2000);
+	CLS(0) CLS(1) CLS(2) CLS(3) CLS(4) CLS(5) CLS(6) CLS(7) CLS(8) CLS(9) CLS(10) CLS(11) CLS(12) CLS(13) CLS(14) CLS(15)
+	CLS(16) CLS(17) CLS(18) CLS(19) CLS(20) CLS(21) CLS(22) CLS(23) CLS(24) CLS(25) CLS(26) CLS(27) CLS(28) CLS(29) CLS(30)
+#undef CLS
+	bad += check<21, 7>(21, 2000);
+	bad += check<25, 11>(25, 40000);
+	bad += check<10, 7>(41, 2000);
+	bad += check<20, 11>(51, 40000);
+	bad += check<9, 7>(71, 2000);
+	bad += check<8, 7>(101, 2000);
+	bad += check<28, 11>(121, 40000);
+	bad += check<27, 7>(151, 2000);
+	bad += check<14, 7>(200, 2000);
 	printf(bad ? "FAILED\n" : "ALL OK\n");
 	return bad != 0;
 }
