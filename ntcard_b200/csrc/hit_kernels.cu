@@ -285,7 +285,8 @@ __device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs
 				uint32_t rec, rl, p;
 				decode(a, U, sm.queue[i], rec, rl, p);
 				const uint32_t* rw = kStaged ? sm.tile + rl * c.stride + 1 : c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1;
-				const uint32_t idx = rec < a.n_rec ? hit_finish<kStaged>(c, h[u], rw, p, last) : kVoid;
+				// slots past the end of the batch, and positions past the end of a record of a mixed-length tile (scan_kernel.cuh)
+				const uint32_t idx = (rec < a.n_rec && p + a.k <= (kStaged ? rw[-1] : __ldg(rw - 1))) ? hit_finish<kStaged>(c, h[u], rw, p, last) : kVoid;
 				uint32_t after = 0;
 				if (idx != kVoid && !append(sm, a, idx)) {
 					after = idx | kPendingBit;

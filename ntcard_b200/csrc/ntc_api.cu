@@ -70,6 +70,7 @@ struct ntc_ctx {
 	struct KInit {                          // per-k constants of the scan / hit kernels
 		uint32_t F0[31], R0[31];            // initial bit-sliced state (bitslice_core.cuh init_state)
 		uint64_t rot_a, rot_b;              // byte m: (k%32 + 32m) % 31 and % 33 for block m of the full hash (k < 288)
+		bool polyA_sampled;                 // ntComp samples the all-A k-mer: zero padding must not be scanned (scan_kernel.cuh, mixed tiles)
 	} kinit[NTC_MAX_K];
 	bool totals_overridden = false;
 	uint64_t totals[NTC_MAX_K] = {};
@@ -382,6 +383,7 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	sa.L.nwarps = sh.nwarps;
 	sa.L.npos_max = sh.npos_max;
 	sa.L.start_limit = sh.start_limit;
+	sa.L.mixed_ok = c->kinit[ki].polyA_sampled ? 0u : 1u;
 	memcpy(sa.L.F0, c->kinit[ki].F0, sizeof sa.L.F0);
 	memcpy(sa.L.R0, c->kinit[ki].R0, sizeof sa.L.R0);
 	sa.masks = c->d_masks;
@@ -765,6 +767,14 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 			ntc_ctx::KInit& L = c->kinit[ki];
 			ntc::bs::init_state(c->k[ki], L.F0, L.R0);
 			L.rot_a = L.rot_b = 0;
+			{
+				uint64_t fh = 0, rh = 0; // A^k: NTF64 / NTR64 base forms, nthash.hpp:220-239
+				for (unsigned i = 0; i < c->k[ki]; i++) {
+					fh = ntc::srol(fh) ^ ntc::seed_of(0);
+					rh = ntc::srol(rh) ^ ntc::seed_of(3);
+				}
+				L.polyA_sampled = ntc::sample_table(rh < fh ? rh : fh, sBits) < 2;
+			}
 			for (unsigned m = 0; m < 8; m++) {
 				L.rot_a |= (uint64_t)(((c->k[ki] & 31u) + 32u * m) % 31u) << (8 * m);
 				L.rot_b |= (uint64_t)(((c->k[ki] & 31u) + 32u * m) % 33u) << (8 * m);

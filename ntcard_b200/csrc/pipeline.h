@@ -7,7 +7,8 @@
 //   A  apply_kernel        per slice: bring the slice into L2 (write zeros on the first flush after a reset, read
 //                          it otherwise), then RED.ADD the slice's log entries -- L2-resident atomics run ~8x
 //                          faster than random atomics into the 1 GiB sketch in HBM
-//   F  fallback_kernel     tiles whose records are not all of one length: 64-bit recurrence, direct RED
+//   F  fallback_kernel     tiles the scan kernel flagged (records of different lengths AND the all-A k-mer of the padding is sampled
+//                          for this k): 64-bit recurrence, direct RED
 //
 // Exactness never depends on capacities: when the pool is exhausted H increments the sketch directly, and the
 // conditional flush in front of H (apply_kernel with force = 0) guarantees the sketch is materialised (zeroed)
@@ -53,6 +54,7 @@ struct ScanLaunch {              // per-k constants of the scan kernel, passed b
 	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (k + 16 rounded up to a multiple of 16)
 	uint32_t npos_max;           // mask rows per tile
 	uint32_t start_limit;        // != 0: hash only the k-mers starting in the first start_limit positions of a record (re-tiled pieces)
+	uint32_t mixed_ok;           // != 0: tiles of records of different lengths may be scanned at the longest length (the all-A k-mer is not sampled)
 	uint32_t F0[31], R0[31];     // initial bit-sliced state (bitslice_core.cuh init_state)
 };
 

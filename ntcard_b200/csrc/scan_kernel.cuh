@@ -9,8 +9,9 @@
 // Output: one mask word per (tile, k-mer position, lane) -- bit s set = the k-mer of slot s ending here is
 // sampled by ntComp (ntcard.cpp:132-145) -- written straight to HBM with coalesced 128-byte stores; the hit
 // kernel (hit_kernels.cu) turns the set bits into sketch increments.  Also: F1 (ntcard.cpp:155), the candidate
-// count of the batch, and per-tile info (k-mer positions per record; tiles whose records differ in length are
-// flagged for the fallback kernel).
+// count of the batch, and per-tile info (k-mer positions per record).  Tiles whose records differ in length are scanned
+// at the longest length (the hit kernel drops what lies past a record's end), or flagged for the fallback kernel when
+// the all-A k-mer of the padding would itself be sampled.
 //
 // No tensor cores: there is no dense contraction; the kernel is bound by the 16-lane integer ALU pipe.
 #pragma once
@@ -124,24 +125,39 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 #pragma unroll
 		for (int s = 0; s < 32; s++)
 			same = same && (v[s].x == len0);
-		if (!__all_sync(0xFFFFFFFFu, same)) {
-			// records of different lengths: the fallback kernel hashes this tile with the 64-bit recurrence; its k-mers
-			// are counted here (F1, and as an upper bound of the tile's sketch increments)
+		const bool mixed = !__all_sync(0xFFFFFFFFu, same);
+		int n = (int)len0;
+		if (mixed) {
+			// records of different lengths: their k-mers are counted here, record by record (F1, and as an upper bound of
+			// the tile's sketch increments)
 			unsigned long long cnt = 0;
+			uint32_t mx = 0;
 #pragma unroll
 			for (int s = 0; s < 32; s++)
-				if ((vmask >> s) & 1u)
+				if ((vmask >> s) & 1u) {
 					cnt += v[s].x >= (uint32_t)k ? v[s].x - (uint32_t)k + 1u : 0u;
+					mx = max(mx, v[s].x);
+				}
 			f1_local += cnt;
-			cand_local += cnt;
-			if (lane == 0) {
-				tile_info[tile] = kTileFlag;
-				n_flag++;
+			if (!L.mixed_ok || L.start_limit) {
+				// the fallback kernel hashes this tile with the 64-bit recurrence
+				cand_local += cnt;
+				if (lane == 0) {
+					tile_info[tile] = kTileFlag;
+					n_flag++;
+				}
+				zero_rows(masks, tile, 0, L.npos_max, lane);
+				continue;
 			}
-			zero_rows(masks, tile, 0, L.npos_max, lane);
-			continue;
+			// Scan the tile as if every record had the longest length: positions past a shorter record's end run on its
+			// padding and may mark candidates, which the hit kernel drops (start + k > the record's length).  Only legal
+			// when the all-A k-mer of the zero padding is not itself sampled (mixed_ok, decided on the host per k).
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1)
+				mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+			n = (int)mx;
 		}
-		int n = (int)len0;
+		n = min(n, (int)(stride - 1u) * 16); // a length word beyond the record's capacity (corrupt input) must not leave the tile's mask rows
 		if (n >= k && L.start_limit) // re-tiled pieces: only the first start_limit windows belong to this record
 			n = min(n, (int)L.start_limit + k - 1);
 		if (n < k) {
@@ -151,8 +167,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			continue;
 		}
 		zero_rows(masks, tile, (uint32_t)(n - k + 1), L.npos_max, lane);
-		if (lane == 0)
+		if (lane == 0) {
 			tile_info[tile] = (uint32_t)(n - k + 1);
+			if (mixed) // counted record by record above: cancel the uniform formula at the end of the tile
+				f1_local -= (unsigned long long)nvalid * (unsigned long long)(n - k + 1);
+		}
 		const uint32_t nwords = (uint32_t)(n + 15) >> 4;
 		const uint32_t ngroups = (nwords + 1 + 3) / 4; // uint4 groups per record incl. the length word
 		// mask row of the block's first position: a running pointer (not recomputed from tile / lane per store)

@@ -260,6 +260,35 @@ def test_bitslice_mixed_lengths_in_uniform_stride(oracle):
         assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want)
 
 
+@pytest.mark.parametrize("sBits,kList", [(7, [32, 44, 64, 73]), (11, [21, 31, 55, 128]), (7, [12, 96, 150])])
+def test_bitslice_ragged_lengths_in_every_tile(oracle, sBits, kList):
+    """Trimmed reads: every record of every tile has its own length (same stride).  The scan kernel runs such tiles at the
+    tile's longest length and the hit kernel drops what lies past a record's end; for the k whose all-A k-mer is itself
+    sampled (k = 44, 73 at sBits 7: the zero padding would flood the hit queue) the tile goes to the fallback kernel.
+    Padding beyond a record's last base is zero in one half of the batch and random in the other."""
+    rng = random.Random(11)
+    n, stride = 7000, 12
+    lens = [rng.choice((0, 5, 31, 32, 33, 63, 64)) if rng.random() < 0.05 else rng.randint(90, 176) for _ in range(n)]
+    reads = [bytes(rng.choice(b"ACGT") for _ in range(L)) for L in lens]
+    words = np.zeros(n * stride, dtype=np.uint32)
+    for i, r in enumerate(reads):
+        w, _ = nt.pack_reads([r])
+        if i >= n // 2:   # garbage behind the record: whole words, and the unused bits of its last word
+            words[i * stride + 1:(i + 1) * stride] = np.frombuffer(rng.randbytes(4 * (stride - 1)), dtype=np.uint32)
+            if len(r) % 16 and len(w) > 1:
+                w = w.copy()
+                w[-1] |= np.uint32((rng.getrandbits(32) << (2 * (len(r) % 16))) & 0xFFFFFFFF)
+        words[i * stride:i * stride + len(w)] = w
+        words[i * stride] = len(r)
+    want, wf1 = oracle.sketch_reads(reads, kList, 18, sBits, nthreads=4)
+    with nt.Sketch(kList, rBits=18, sBits=sBits) as sk:
+        sk.set_kernel(nt.KERNEL_BITSLICE)
+        sk.submit(words, None, n, stride)
+        t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1)
+    assert np.array_equal(t.reshape(-1), want)
+
+
 def test_bitslice_low_complexity_queue_overflow(oracle):
     """Poly-A / dinucleotide reads: every k-mer of a read has the same hash, so either none or ALL of
     them are sampled -- the per-body hit queue overflows and the slow exact path must take over."""
