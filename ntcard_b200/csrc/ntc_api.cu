@@ -105,6 +105,7 @@ struct ntc_ctx {
 	size_t cap_tile_info = 0;
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
+	unsigned scan_prefetch = 2; // scan kernel: L2 prefetch of a warp's next tile one column before the end of the current one (NTC_SCAN_PREFETCH: 0 = none, 1 = half way: measured, thrashes L2)
 	bool partial = false;     // after ntc_flush_slices: only the owned slices of the sketch are defined (until ntc_reset)
 	std::vector<uint32_t> h_nblk; // block counts per slice as of the last ntc_log_counts
 	uint32_t log_used = 0;
@@ -384,6 +385,7 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	sa.L.npos_max = sh.npos_max;
 	sa.L.start_limit = sh.start_limit;
 	sa.L.mixed_ok = c->kinit[ki].polyA_sampled ? 0u : 1u;
+	sa.L.prefetch = c->scan_prefetch;
 	memcpy(sa.L.F0, c->kinit[ki].F0, sizeof sa.L.F0);
 	memcpy(sa.L.R0, c->kinit[ki].R0, sizeof sa.L.R0);
 	sa.masks = c->d_masks;
@@ -782,6 +784,8 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 		}
 	}
 	c->use_pipeline = !(getenv("NTC_PIPELINE") && atoi(getenv("NTC_PIPELINE")) == 0);
+	if (getenv("NTC_SCAN_PREFETCH"))
+		c->scan_prefetch = (unsigned)atoi(getenv("NTC_SCAN_PREFETCH"));
 	if (getenv("NTC_CHUNK_WAVES"))
 		c->chunk_waves = (unsigned)atoi(getenv("NTC_CHUNK_WAVES"));
 	if (!hll_bits && (rc = pool_create(c)))

@@ -54,6 +54,7 @@ struct ScanLaunch {              // per-k constants of the scan kernel, passed b
 	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (k + 16 rounded up to a multiple of 16)
 	uint32_t npos_max;           // mask rows per tile
 	uint32_t start_limit;        // != 0: hash only the k-mers starting in the first start_limit positions of a record (re-tiled pieces)
+	uint32_t prefetch;           // cp.async.bulk.prefetch.L2 of the warp's next tile: 0 = none, 1 = half way through the current one, 2 = one column before its end
 	uint32_t mixed_ok;           // != 0: tiles of records of different lengths may be scanned at the longest length (the all-A k-mer is not sampled)
 	uint32_t F0[31], R0[31];     // initial bit-sliced state (bitslice_core.cuh init_state)
 };

@@ -216,8 +216,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 				for (int s = 0; s < 32; s++)
 					v[s] = ldg_nc_v4(reinterpret_cast<const uint4*>(words + (uint64_t)min(rb + s * 32u + lane, last_rec) * stride) + (g + 1), keep);
 			}
-			if (w == nwords / 2) {
-				// half way through: warm L2 with this warp's next tile (bulk async prefetch)
+			if (L.prefetch && w == (L.prefetch == 1 ? nwords / 2 : nwords - 2)) {
+				// warm L2 with this warp's next tile (bulk async prefetch) -- late: one column before the end of this tile.  Half way
+				// through (mode 1) doubles the tiles resident in L2 (2 x 57 MB for 1184 warps) and the 32-byte sectors that a record's
+				// 16-byte groups share were evicted between their uses: 876 MB of DRAM reads per 10 M reads instead of 492 MB
+				// (profiles/r01_scan_l2_experiment.txt)
 				const uint64_t nrb = (uint64_t)(tile + gridDim.x * L.nwarps) * kTileRecs;
 				if (lane == 0 && nrb + kTileRecs <= n_rec) {
 					const uint32_t bytes = kTileRecs * stride * 4u;
