@@ -16,6 +16,7 @@ struct BatchView {          // a packed record stream resident in device memory
 	uint32_t n_rec;
 	uint64_t n_words;
 	uint32_t uniform_len;   // bases per record when the host knows all records are equal, else 0
+	uint32_t max_rec_words; // ragged batches: words of the longest record when the host knows it, else 0
 };
 
 size_t piece_scan_temp_bytes(uint32_t n_items);
@@ -30,6 +31,8 @@ cudaError_t launch_retile_fill(const BatchView& b, uint32_t Lp, uint32_t D, uint
     int n_sm, cudaStream_t st);
 cudaError_t launch_stride_offsets(uint32_t stride, uint32_t n_rec, uint32_t* d_off, cudaStream_t st);
 cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t stride_out, uint32_t n_rec, uint32_t* d_out, int n_sm, cudaStream_t st);
+cudaError_t launch_pad_ragged(const uint32_t* d_in, const uint32_t* d_off, uint32_t n_rec, uint32_t stride_out, uint32_t* d_out, int n_sm,
+    cudaStream_t st);
 cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
     const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t* d_counters, unsigned long long* d_f1, uint32_t kmask,
     int n_sm, cudaStream_t st);

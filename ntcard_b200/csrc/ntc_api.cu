@@ -95,6 +95,7 @@ struct ntc_ctx {
 	uint32_t* d_rt_off = nullptr;      // offsets made up for uniform-stride batches of long records
 	size_t cap_rt_off = 0;
 	uint64_t n_retiled = 0;
+	uint64_t n_padded = 0;             // ragged batches of short records padded to a uniform stride for the pipeline
 	// sketch pipeline (scan -> hit log -> apply), pipeline.h
 	ntc::pl::Pool pool{};
 	uint32_t* d_pool_ctl_region = nullptr; // ctl + slice_nblk + zero_done + apply_done + cand, one allocation (zeroed by reset)
@@ -544,7 +545,7 @@ int run_retiled(ntc_ctx* c, const ntc::BatchView& b_in, uint32_t* handled)
 	c->n_launches += 5;
 	c->n_retiled++;
 	if (n_full) {
-		ntc::BatchView u{ c->d_rt_uniform, nullptr, stride, n_full, (uint64_t)n_full * stride, Lp };
+		ntc::BatchView u{ c->d_rt_uniform, nullptr, stride, n_full, (uint64_t)n_full * stride, Lp, 0 };
 		PipeShape shape[NTC_MAX_K];
 		const uint32_t pm = pipeline_config(c, u, true, shape, /*min_rec=*/1);
 		for (unsigned ki = 0; ki < c->nK; ki++)
@@ -559,7 +560,7 @@ int run_retiled(ntc_ctx* c, const ntc::BatchView& b_in, uint32_t* handled)
 	if (n_tail) {
 		if ((rc = flush(c))) // the general kernel increments the counters in HBM directly
 			return rc;
-		ntc::BatchView t{ c->d_rt_tail_words, c->d_rt_tail_off, 0, n_tail, tail_words, 0 };
+		ntc::BatchView t{ c->d_rt_tail_words, c->d_rt_tail_off, 0, n_tail, tail_words, 0, 0 };
 		if ((rc = run_roll64(c, t, false, kmask)))
 			return rc;
 	}
@@ -602,6 +603,28 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 			b.words = c->d_rt_uniform;
 			b.stride = s4;
 			b.n_words = (uint64_t)b.n_rec * s4;
+		}
+	}
+	else if (b.off && b.max_rec_words >= 2 && b.max_rec_words <= 20 && b.n_rec >= 1024 && c->use_pipeline && !c->gap && c->kernel != NTC_KERNEL_ROLL64 &&
+	         record_is_piece && !getenv("NTC_NO_PAD")) {
+		// ragged batch of short records (what ntc_pack_seqs makes of reads: the documented drop-in for ntRead): zero-pad every record
+		// to the stride of the longest on the device; the pipeline takes tiles of mixed lengths (scan_kernel.cuh).  Not when the padding
+		// would be most of the batch (a few long records among many short fragments).
+		const uint32_t s4 = (b.max_rec_words + 3u) & ~3u;
+		const uint64_t padded = (uint64_t)b.n_rec * s4;
+		bool any = false;
+		for (unsigned ki = 0; ki < c->nK; ki++)
+			any = any || (c->k[ki] < 288 && ntc::pl::have_scan_kernel(c->k[ki], c->sBits));
+		if (any && padded <= 0xFFFFFFF0ull && padded <= 3 * b.n_words + 4096) {
+			if ((rc = grow(&c->d_rt_uniform, &c->cap_rt_uniform, (size_t)padded + 4, false)))
+				return rc;
+			CK(ntc::launch_pad_ragged(b.words, b.off, b.n_rec, s4, c->d_rt_uniform, c->n_sm, c->stream));
+			c->n_launches++;
+			c->n_padded++;
+			b.words = c->d_rt_uniform;
+			b.off = nullptr;
+			b.stride = s4;
+			b.n_words = padded;
 		}
 	}
 	uint32_t pmask = pipeline_config(c, b, record_is_piece, shape);
@@ -1000,7 +1023,7 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 		CK(cudaMemcpyAsync(s.d_off, src_off, (n_rec + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
 	CK(cudaEventRecord(s.copied, c->copy_stream));
 	CK(cudaStreamWaitEvent(c->stream, s.copied, 0));
-	ntc::BatchView b{ s.d_words, off ? s.d_off : nullptr, stride_words, (uint32_t)n_rec, n_words, 0 };
+	ntc::BatchView b{ s.d_words, off ? s.d_off : nullptr, stride_words, (uint32_t)n_rec, n_words, 0, off ? max_rec_words : 0u };
 	if ((rc = run_batch(c, b, single_piece_records(c, max_rec_words))))
 		return rc;
 	CK(cudaEventRecord(s.consumed, c->stream));
@@ -1024,7 +1047,7 @@ int ntc_submit_device(ntc_ctx* c, const uint32_t* d_words, size_t n_words, const
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
-	ntc::BatchView b{ d_words, d_off, stride_words, (uint32_t)n_rec, n_words, 0 };
+	ntc::BatchView b{ d_words, d_off, stride_words, (uint32_t)n_rec, n_words, 0, 0 };
 	return run_batch(c, b, d_off ? false : single_piece_records(c, stride_words));
 }
 

@@ -334,6 +334,28 @@ cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t s
 	return cudaGetLastError();
 }
 
+// ragged batch of short records -> the same records zero-padded to one stride (a multiple of 4 words), so that they can take the
+// pipeline as tiles of mixed lengths (scan_kernel.cuh)
+__global__ void __launch_bounds__(256) pad_ragged_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ off, uint32_t stride_out,
+    uint64_t n_out_words, uint32_t* __restrict__ out)
+{
+	for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_out_words; x += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t rec = (uint32_t)(x / stride_out), w = (uint32_t)(x - (uint64_t)rec * stride_out);
+		const uint32_t o = __ldg(off + rec), nw = __ldg(off + rec + 1) - o;
+		out[x] = w < nw ? __ldg(in + o + w) : 0u;
+	}
+}
+
+cudaError_t launch_pad_ragged(const uint32_t* d_in, const uint32_t* d_off, uint32_t n_rec, uint32_t stride_out, uint32_t* d_out, int n_sm,
+    cudaStream_t st)
+{
+	const uint64_t n = (uint64_t)n_rec * stride_out;
+	if (n == 0)
+		return cudaSuccess;
+	pad_ragged_kernel<<<grid_for(n, 256, (unsigned)n_sm * 32u), 256, 0, st>>>(d_in, d_off, stride_out, n, d_out);
+	return cudaGetLastError();
+}
+
 __global__ void stride_offsets_kernel(uint32_t stride, uint32_t n_rec, uint32_t* __restrict__ off /* [n_rec + 1] */)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

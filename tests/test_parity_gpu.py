@@ -289,6 +289,26 @@ def test_bitslice_ragged_lengths_in_every_tile(oracle, sBits, kList):
     assert np.array_equal(t.reshape(-1), want)
 
 
+@pytest.mark.parametrize("sBits,kList", [(7, [12, 32, 44, 64]), (11, [31, 96])])
+def test_ragged_short_records_are_padded_for_the_pipeline(oracle, sBits, kList):
+    """The documented drop-in path (ntc_pack_seqs -> ntc_submit with offsets): reads with N runs and reads of odd lengths make a
+    RAGGED batch; the library pads it to one stride on the device and the pipeline takes it as mixed-length tiles.  Forced
+    NTC_KERNEL_BITSLICE proves the pipeline took every k (it fails loudly otherwise)."""
+    rng = random.Random(23)
+    a = oracle.gen_reads(5, 0, 6000, 150, 2, 0)                       # N mode: reads split into segments
+    reads = [bytes(a[i * 150:(i + 1) * 150]) for i in range(6000)]
+    reads += [bytes(rng.choice(b"ACGTacgtu") for _ in range(rng.randint(40, 240))) for _ in range(3000)]   # odd lengths, no N
+    rng.shuffle(reads)
+    want, wf1 = oracle.sketch_reads(reads, kList, 18, sBits, nthreads=4)
+    with nt.Sketch(kList, rBits=18, sBits=sBits) as sk:
+        sk.set_kernel(nt.KERNEL_BITSLICE)
+        sk.submit_reads(reads[:4500])
+        sk.submit_reads(reads[4500:])
+        t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1)
+    assert np.array_equal(t.reshape(-1), want)
+
+
 def test_bitslice_low_complexity_queue_overflow(oracle):
     """Poly-A / dinucleotide reads: every k-mer of a read has the same hash, so either none or ALL of
     them are sampled -- the per-body hit queue overflows and the slow exact path must take over."""
