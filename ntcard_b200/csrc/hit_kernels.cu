@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 
 #include "nthash_device.cuh"
+#include <cstdlib>
+
 #include "pipeline.h"
 #include "sketch_common.cuh"
 
@@ -703,17 +705,25 @@ cudaError_t launch_hit(const HitArgs& a, bool staged, unsigned ctas)
 {
 	const size_t smem = hit_smem(staged, a.stride);
 	cudaError_t e;
+	// the opt-in shared-memory limit is a property of (function, device): set it when it has to grow, not on every launch
+	static size_t smem_set[2][64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	const bool known = dev >= 0 && dev < 64;
+	const bool raise = !known || smem > smem_set[staged ? 1 : 0][dev];
 	if (staged) {
 		auto kern = hit_kernel<true, kStagedGroups>;
-		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+		if (raise && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
 			return e;
 		kern<<<ctas, kStagedGroups * kGroupThreads, smem, a.stream>>>(a);
 	} else {
 		auto kern = hit_kernel<false, kPlainGroups>;
-		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+		if (raise && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
 			return e;
 		kern<<<ctas, kPlainGroups * kGroupThreads, smem, a.stream>>>(a);
 	}
+	if (raise && known)
+		smem_set[staged ? 1 : 0][dev] = smem;
 	return cudaGetLastError();
 }
 
@@ -739,6 +749,11 @@ cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32
 	// Cooperative launch: the stagers and appliers of different CTAs wait for each other through counters in global
 	// memory, so every CTA of the grid must be resident at once -- also when another context's kernels share the GPU.
 	Pool p = pool;
+	static const bool plain = getenv("NTC_APPLY_COOP") && atoi(getenv("NTC_APPLY_COOP")) == 0; // experiment: ordinary launch
+	if (plain) {
+		apply_kernel<<<grid, kApplyThreads, 0, st>>>(p, counters, force, reserve_blocks, d_order, n_order);
+		return cudaGetLastError();
+	}
 	void* args[] = { &p, &counters, &force, &reserve_blocks, &d_order, &n_order };
 	return cudaLaunchCooperativeKernel((const void*)apply_kernel, dim3(grid), dim3(kApplyThreads), args, 0, st);
 }

@@ -279,9 +279,17 @@ template <int KM, int S>
 cudaError_t launch_scan_one(const ScanArgs& a)
 {
 	auto kern = scan_kernel<KM, S>;
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes);
-	if (e != cudaSuccess)
-		return e;
+	// the opt-in shared-memory limit is a property of (function, device): set it when it has to grow, not on every launch
+	static size_t smem_set[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64 || a.smem_bytes > smem_set[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes);
+		if (e != cudaSuccess)
+			return e;
+		if (dev >= 0 && dev < 64)
+			smem_set[dev] = a.smem_bytes;
+	}
 	kern<<<a.grid, kScanThreads, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.masks, a.tile_info, a.f1_k, a.cand, a.ctl);
 	return cudaGetLastError();
 }
