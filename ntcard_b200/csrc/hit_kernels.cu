@@ -727,6 +727,23 @@ cudaError_t launch_hit(const HitArgs& a, bool staged, unsigned ctas)
 	return cudaGetLastError();
 }
 
+// Start of a batch: the candidate count and the flagged-tile count back to zero -- as one kernel instead of two cudaMemsetAsync.
+// Experiment only (NTC_CLEAR_MEMSET=0): it was meant to keep the tiny memsets out of the copy engine's queue, but measured far slower on the
+// host side (ntc_api.cu).
+__global__ void batch_clear_kernel(unsigned long long* cand, uint32_t* ctl)
+{
+	if (threadIdx.x == 0) {
+		*cand = 0ull;
+		ctl[CTL_NFLAG] = 0u;
+	}
+}
+
+cudaError_t launch_batch_clear(const Pool& pool, cudaStream_t st)
+{
+	batch_clear_kernel<<<1, 32, 0, st>>>(pool.cand, pool.ctl);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_fallback(const uint32_t* words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, const uint32_t* tile_info,
     const DevParams* d_params, uint32_t ki, uint32_t* ctr_k, const uint32_t* ctl, int n_sm, cudaStream_t st)
 {

@@ -106,6 +106,7 @@ struct ntc_ctx {
 	size_t cap_tile_info = 0;
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
+	bool clear_by_memset = true;
 	unsigned scan_prefetch = 2; // scan kernel: L2 prefetch of a warp's next tile one column before the end of the current one (NTC_SCAN_PREFETCH: 0 = none, 1 = half way: measured, thrashes L2)
 	bool partial = false;     // after ntc_flush_slices: only the owned slices of the sketch are defined (until ntc_reset)
 	std::vector<uint32_t> h_nblk; // block counts per slice as of the last ntc_log_counts
@@ -374,8 +375,12 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	    (rc = grow(&c->d_tile_info, &c->cap_tile_info, (size_t)n_tiles, false)))
 		return rc;
 	ntc::pl::Pool& P = c->pool;
-	CK(cudaMemsetAsync(P.cand, 0, sizeof(unsigned long long), c->stream));
-	CK(cudaMemsetAsync(P.ctl + ntc::pl::CTL_NFLAG, 0, sizeof(uint32_t), c->stream));
+	if (c->clear_by_memset) {
+		CK(cudaMemsetAsync(P.cand, 0, sizeof(unsigned long long), c->stream));
+		CK(cudaMemsetAsync(P.ctl + ntc::pl::CTL_NFLAG, 0, sizeof(uint32_t), c->stream));
+	} else {
+		CK(ntc::pl::launch_batch_clear(P, c->stream));
+	}
 	ntc::pl::ScanArgs sa;
 	sa.words = b.words;
 	sa.stride = b.stride;
@@ -807,6 +812,9 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 		}
 	}
 	c->use_pipeline = !(getenv("NTC_PIPELINE") && atoi(getenv("NTC_PIPELINE")) == 0);
+	// two 8-byte cudaMemsetAsync per batch (default) or one 1-thread kernel (NTC_CLEAR_MEMSET=0): measured, the kernel variant makes the host
+	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
+	c->clear_by_memset = !(getenv("NTC_CLEAR_MEMSET") && atoi(getenv("NTC_CLEAR_MEMSET")) == 0);
 	if (getenv("NTC_SCAN_PREFETCH"))
 		c->scan_prefetch = (unsigned)atoi(getenv("NTC_SCAN_PREFETCH"));
 	if (getenv("NTC_CHUNK_WAVES"))

@@ -95,6 +95,7 @@ cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a);
 bool hit_can_stage(uint32_t stride, uint32_t units_per_tile, uint32_t tiles_per_unit);
 unsigned hit_groups_per_sm(bool staged);
 cudaError_t launch_hit(const HitArgs& a, bool staged, unsigned ctas);
+cudaError_t launch_batch_clear(const Pool& pool, cudaStream_t st); // candidate count and flagged-tile count of the batch := 0
 cudaError_t launch_fallback(const uint32_t* words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, const uint32_t* tile_info,
     const DevParams* d_params, uint32_t ki, uint32_t* ctr_k, const uint32_t* ctl, int n_sm, cudaStream_t st);
 // force = 0: flush only if the batch about to be hashed could overflow the pool while the sketch is still
