@@ -24,8 +24,9 @@ def main():
     ap.add_argument("--reads", type=int, default=4_000_000)
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--per", type=int, default=500_000, help="reads per host batch")
     args = ap.parse_args()
-    n, L, k, per = args.reads, 150, args.k, 500_000
+    n, L, k, per = args.reads, 150, args.k, args.per
     batches = []
     n_rec = n_words = 0
     for lo in range(0, n, per):
