@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,18 @@ using ntc::set_err;
 		cudaError_t e_ = (call);                                                                         \
 		if (e_ != cudaSuccess)                                                                           \
 			return set_err(NTC_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+// HT(c, "label", statement): the statement, timed on the host when the context was created with NTC_HOST_TIMING=1
+#define HT(c, what, stmt)                                                                                  \
+	do {                                                                                                   \
+		if (!(c)->host_timing) {                                                                           \
+			stmt;                                                                                          \
+		} else {                                                                                           \
+			const auto ht0_ = std::chrono::steady_clock::now();                                            \
+			stmt;                                                                                          \
+			(c)->host_span(what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ht0_).count()); \
+		}                                                                                                  \
 	} while (0)
 
 constexpr int NBUF = 3; // device/pinned staging ring depth
@@ -107,6 +120,21 @@ struct ntc_ctx {
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
 	bool clear_by_memset = true;
+	// NTC_HOST_TIMING=1: host time spent in the calls of the submit path, per call site, printed by ntc_destroy (diagnosis only)
+	bool host_timing = false;
+	struct HostSpan { const char* what; double total_ms, max_ms; uint64_t n; };
+	std::vector<HostSpan> host_spans;
+	void host_span(const char* what, double ms)
+	{
+		for (auto& h : host_spans)
+			if (h.what == what) {
+				h.total_ms += ms;
+				h.max_ms = std::max(h.max_ms, ms);
+				h.n++;
+				return;
+			}
+		host_spans.push_back({ what, ms, ms, 1 });
+	}
 	unsigned scan_prefetch = 2; // scan kernel: L2 prefetch of a warp's next tile one column before the end of the current one (NTC_SCAN_PREFETCH: 0 = none, 1 = half way: measured, thrashes L2)
 	bool partial = false;     // after ntc_flush_slices: only the owned slices of the sketch are defined (until ntc_reset)
 	std::vector<uint32_t> h_nblk; // block counts per slice as of the last ntc_log_counts
@@ -371,15 +399,16 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 {
 	int rc;
 	const uint32_t n_tiles = (b.n_rec + 1023) / 1024;
-	if ((rc = grow(&c->d_masks, &c->cap_masks, (size_t)n_tiles * sh.npos_max * 32, false)) ||
-	    (rc = grow(&c->d_tile_info, &c->cap_tile_info, (size_t)n_tiles, false)))
+	HT(c, "chunk: grow masks / tile_info", rc = grow(&c->d_masks, &c->cap_masks, (size_t)n_tiles * sh.npos_max * 32, false);
+	   if (!rc) rc = grow(&c->d_tile_info, &c->cap_tile_info, (size_t)n_tiles, false));
+	if (rc)
 		return rc;
 	ntc::pl::Pool& P = c->pool;
 	if (c->clear_by_memset) {
-		CK(cudaMemsetAsync(P.cand, 0, sizeof(unsigned long long), c->stream));
-		CK(cudaMemsetAsync(P.ctl + ntc::pl::CTL_NFLAG, 0, sizeof(uint32_t), c->stream));
+		HT(c, "chunk: 2 x cudaMemsetAsync", CK(cudaMemsetAsync(P.cand, 0, sizeof(unsigned long long), c->stream));
+		   CK(cudaMemsetAsync(P.ctl + ntc::pl::CTL_NFLAG, 0, sizeof(uint32_t), c->stream)));
 	} else {
-		CK(ntc::pl::launch_batch_clear(P, c->stream));
+		HT(c, "chunk: launch_batch_clear", CK(ntc::pl::launch_batch_clear(P, c->stream)));
 	}
 	ntc::pl::ScanArgs sa;
 	sa.words = b.words;
@@ -404,7 +433,7 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	sa.stream = c->stream;
 	if ((rc = stage_begin(c, 0)))
 		return rc;
-	CK(ntc::pl::launch_scan(c->k[ki], c->sBits, sa));
+	HT(c, "chunk: launch_scan", CK(ntc::pl::launch_scan(c->k[ki], c->sBits, sa)));
 	if ((rc = stage_end(c)) || (rc = stage_begin(c, 1)))
 		return rc;
 	ntc::pl::HitArgs ha;
@@ -432,9 +461,9 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	const unsigned gpc = staged ? 3u : 2u; // groups per CTA
 	const unsigned hit_ctas = std::min<unsigned>((unsigned)c->n_sm * (staged ? 1u : 2u), (ha.n_units + gpc - 1) / gpc);
 	// conditional flush: only when this batch could exhaust the pool while the sketch is not materialised yet
-	CK(ntc::pl::launch_apply(P, c->d_counters, 0, 3 * P.max_groups * P.nbins + 8, c->apply_grid, c->stream));
-	CK(ntc::pl::launch_hit(ha, staged, hit_ctas));
-	CK(ntc::pl::launch_fallback(b.words, b.stride, b.n_rec, n_tiles, c->d_tile_info, c->d_params, ki, ha.ctr_k, P.ctl, c->n_sm, c->stream));
+	HT(c, "chunk: launch_apply (conditional)", CK(ntc::pl::launch_apply(P, c->d_counters, 0, 3 * P.max_groups * P.nbins + 8, c->apply_grid, c->stream)));
+	HT(c, "chunk: launch_hit", CK(ntc::pl::launch_hit(ha, staged, hit_ctas)));
+	HT(c, "chunk: launch_fallback", CK(ntc::pl::launch_fallback(b.words, b.stride, b.n_rec, n_tiles, c->d_tile_info, c->d_params, ki, ha.ctr_k, P.ctl, c->n_sm, c->stream)));
 	if ((rc = stage_end(c)))
 		return rc;
 	c->n_launches += 4;
@@ -470,8 +499,8 @@ int run_roll64(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, uint32
 	uint64_t bound = 0;
 	if (!record_is_piece && (rc = prepare_pieces(c, b, &bound)))
 		return rc;
-	CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters, c->d_f1, kmask, c->n_sm,
-	    c->stream));
+	HT(c, "batch: launch_roll64", CK(ntc::launch_roll64(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->d_counters,
+	    c->d_f1, kmask, c->n_sm, c->stream)));
 	c->n_launches += 1;
 	return NTC_OK;
 }
@@ -623,7 +652,7 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 		if (any && padded <= 0xFFFFFFF0ull && padded <= 3 * b.n_words + 4096) {
 			if ((rc = grow(&c->d_rt_uniform, &c->cap_rt_uniform, (size_t)padded + 4, false)))
 				return rc;
-			CK(ntc::launch_pad_ragged(b.words, b.off, b.n_rec, s4, c->d_rt_uniform, c->n_sm, c->stream));
+			HT(c, "batch: launch_pad_ragged", CK(ntc::launch_pad_ragged(b.words, b.off, b.n_rec, s4, c->d_rt_uniform, c->n_sm, c->stream)));
 			c->n_launches++;
 			c->n_padded++;
 			b.words = c->d_rt_uniform;
@@ -815,6 +844,7 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 	// two 8-byte cudaMemsetAsync per batch (default) or one 1-thread kernel (NTC_CLEAR_MEMSET=0): measured, the kernel variant makes the host
 	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
 	c->clear_by_memset = !(getenv("NTC_CLEAR_MEMSET") && atoi(getenv("NTC_CLEAR_MEMSET")) == 0);
+	c->host_timing = getenv("NTC_HOST_TIMING") && atoi(getenv("NTC_HOST_TIMING")) != 0;
 	if (getenv("NTC_SCAN_PREFETCH"))
 		c->scan_prefetch = (unsigned)atoi(getenv("NTC_SCAN_PREFETCH"));
 	if (getenv("NTC_CHUNK_WAVES"))
@@ -849,6 +879,11 @@ void ntc_destroy(ntc_ctx* c)
 {
 	if (!c)
 		return;
+	if (c->host_timing && !c->host_spans.empty()) {
+		fprintf(stderr, "[ntc host timing] %-34s %10s %10s %10s\n", "call site", "calls", "total ms", "max ms");
+		for (const auto& h : c->host_spans)
+			fprintf(stderr, "[ntc host timing] %-34s %10llu %10.3f %10.3f\n", h.what, (unsigned long long)h.n, h.total_ms, h.max_ms);
+	}
 	cudaSetDevice(c->device);
 	if (c->stream)
 		cudaStreamSynchronize(c->stream);
@@ -988,15 +1023,18 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 		max_rec_words = 0;
 		if (off[n_rec] > n_words)
 			return set_err(NTC_EINVAL, "ntc_submit: off[n_rec] exceeds n_words");
+		const auto v0 = std::chrono::steady_clock::now();
 		for (size_t i = 0; i < n_rec; i++) {
 			if (off[i + 1] < off[i] + 1)
 				return set_err(NTC_EINVAL, "ntc_submit: record %zu has no length word", i);
 			max_rec_words = std::max(max_rec_words, off[i + 1] - off[i]);
 		}
+		if (c->host_timing)
+			c->host_span("submit: offset validation loop", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - v0).count());
 	}
 	Stage& s = c->stage[c->next_ticket % NBUF];
 	// the slot's previous batch must have been consumed by its kernels before we overwrite it
-	CK(cudaEventSynchronize(s.consumed));
+	HT(c, "submit: wait for the slot (consumed)", CK(cudaEventSynchronize(s.consumed)));
 	if ((rc = grow(&s.d_words, &s.cap_words, n_words, false)))
 		return rc;
 	if (off && (rc = grow(&s.d_off, &s.cap_off, n_rec + 1, false)))
@@ -1026,13 +1064,13 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 			src_off = s.h_off;
 		}
 	}
-	CK(cudaMemcpyAsync(s.d_words, src_words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+	HT(c, "submit: cudaMemcpyAsync words", CK(cudaMemcpyAsync(s.d_words, src_words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream)));
 	if (off)
-		CK(cudaMemcpyAsync(s.d_off, src_off, (n_rec + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
-	CK(cudaEventRecord(s.copied, c->copy_stream));
-	CK(cudaStreamWaitEvent(c->stream, s.copied, 0));
+		HT(c, "submit: cudaMemcpyAsync offsets", CK(cudaMemcpyAsync(s.d_off, src_off, (n_rec + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream)));
+	HT(c, "submit: record copied + stream wait", CK(cudaEventRecord(s.copied, c->copy_stream)); CK(cudaStreamWaitEvent(c->stream, s.copied, 0)));
 	ntc::BatchView b{ s.d_words, off ? s.d_off : nullptr, stride_words, (uint32_t)n_rec, n_words, 0, off ? max_rec_words : 0u };
-	if ((rc = run_batch(c, b, single_piece_records(c, max_rec_words))))
+	HT(c, "submit: run_batch (all of it)", rc = run_batch(c, b, single_piece_records(c, max_rec_words)));
+	if (rc)
 		return rc;
 	CK(cudaEventRecord(s.consumed, c->stream));
 	s.ticket = c->next_ticket++;

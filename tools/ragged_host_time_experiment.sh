@@ -5,6 +5,7 @@
 show='import json,sys; d=json.loads(sys.stdin.readline()); print({k:(round(v["wall_ms_per_pass"],2), round(v["kernel_ms_per_pass"],2), round(v["host_in_submit_ms"],2)) for k,v in d.items() if isinstance(v,dict)})'
 run() { echo "== $*"; env "$@" python tools/bench_ragged.py --steps 5 $EXTRA | python -c "$show"; }
 run NTC_DUMMY=0
+NTC_HOST_TIMING=1 python tools/bench_ragged.py --steps 5 2>&1 >/dev/null | grep "host timing"   # per call site, both kernels (two contexts' worth in one table)
 run NTC_NO_PAD=1
 run NTC_APPLY_COOP=0
 run NTC_CLEAR_MEMSET=0
