@@ -205,6 +205,11 @@ size_t ntc_pack_bound(size_t n_seq, size_t total_bases);
 int ntc_pack_seqs(const char* chars, const uint64_t* seq_off, size_t n_seq, uint32_t min_len, uint32_t* words,
     size_t cap_words, size_t* n_words, uint32_t* off, size_t cap_rec, size_t* n_rec, size_t* consumed);
 
+/* The checks ntc_submit makes on the offsets of a ragged batch, for callers that build batches themselves: off[0..n_rec]
+ * ascend strictly (every record has at least its length word) and off[n_rec] <= n_words.  *max_rec_words (optional) = words
+ * of the longest record.  NTC_EINVAL names the first bad record.  No device needed. */
+int ntc_check_offsets(const uint32_t* off, size_t n_rec, size_t n_words, uint32_t* max_rec_words);
+
 /* Deterministic synthetic reads (mix64 generator).  mode 0:
  * uniform; mode 1: read i = gen(i mod U), reverse-complemented when (i/U) is
  * odd; mode 2: uniform with N runs (ASCII output only).

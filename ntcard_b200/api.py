@@ -24,7 +24,7 @@ SYMBOLS = [
     "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
     "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_stage_times", "ntc_device_count",
     "ntc_last_error", "ntc_version",
-    "ntc_hll_create", "ntc_hll_registers_device", "ntc_hll_finish", "ntc_hll_estimate",
+    "ntc_hll_create", "ntc_hll_registers_device", "ntc_hll_finish", "ntc_hll_estimate", "ntc_check_offsets",
 ]
 
 
@@ -86,6 +86,7 @@ def _load():
         "ntc_hll_registers_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
         "ntc_hll_finish": (C.c_int, [vp, vp, u64p]),
         "ntc_hll_estimate": (C.c_int, [vp, C.c_uint, C.c_int, dblp]),
+        "ntc_check_offsets": (C.c_int, [vp, C.c_size_t, C.c_size_t, u32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -140,6 +141,14 @@ def pack_chars(chars, seq_off, min_len=1):
     _check(lib.ntc_pack_seqs(chars.ctypes.data, seq_off.ctypes.data_as(C.POINTER(C.c_uint64)), n, min_len,
                              words.ctypes.data, cap_w, C.byref(nw), off.ctypes.data, cap_r, C.byref(nr), C.byref(cons)))
     return words[:nw.value].copy(), off[:nr.value + 1].copy()
+
+
+def check_offsets(off, n_words):
+    """ntc_submit's checks of a ragged batch's offsets (uint32[n_rec+1]); returns the word count of the longest record."""
+    off = np.ascontiguousarray(off, dtype=np.uint32)
+    mx = C.c_uint32()
+    _check(lib.ntc_check_offsets(off.ctypes.data, len(off) - 1, n_words, C.byref(mx)))
+    return mx.value
 
 
 def gen_ascii(seed, first, n, L, mode=0, U=0):

@@ -256,6 +256,31 @@ int ntc_estimate(const uint32_t* p_hist, const uint16_t* t_Counter, unsigned rBi
 	return NTC_OK;
 }
 
+// What ntc_submit checks of a ragged batch, as one branch-free pass the compiler vectorises (a batch has millions of records
+// and the loop runs on the submitting thread): offsets ascend strictly -- every record has at least its length word -- and end
+// inside the batch.
+int ntc_check_offsets(const uint32_t* off, size_t n_rec, size_t n_words, uint32_t* max_rec_words)
+{
+	if (!off)
+		return set_err(NTC_EINVAL, "ntc_check_offsets: bad argument");
+	uint32_t mx = 0, bad = 0;
+	for (size_t i = 0; i < n_rec; i++) {
+		const uint32_t a = off[i], b = off[i + 1];
+		bad |= (uint32_t)(b <= a);
+		const uint32_t d = b - a;
+		mx = d > mx ? d : mx;
+	}
+	if (bad)
+		for (size_t i = 0; i < n_rec; i++)
+			if (off[i + 1] <= off[i])
+				return set_err(NTC_EINVAL, "ntc_submit: record %zu has no length word", i);
+	if (off[n_rec] > n_words)
+		return set_err(NTC_EINVAL, "ntc_submit: off[n_rec] exceeds n_words");
+	if (max_rec_words)
+		*max_rec_words = mx;
+	return NTC_OK;
+}
+
 // The estimate nthll prints, nthll.cpp:243-254, in the reference's operation order: alpha = 1.4426 / (1 + 1.079 / nBuck),
 // halved for canonical k-mers (:245; the reference's opt::canon is always true), harmonic mean of 2^register.
 int ntc_hll_estimate(const uint8_t* regs, unsigned nBits, int canon, double* est)

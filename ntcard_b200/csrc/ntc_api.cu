@@ -1020,15 +1020,9 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 		return rc;
 	uint32_t max_rec_words = stride_words;
 	if (off) {
-		max_rec_words = 0;
-		if (off[n_rec] > n_words)
-			return set_err(NTC_EINVAL, "ntc_submit: off[n_rec] exceeds n_words");
 		const auto v0 = std::chrono::steady_clock::now();
-		for (size_t i = 0; i < n_rec; i++) {
-			if (off[i + 1] < off[i] + 1)
-				return set_err(NTC_EINVAL, "ntc_submit: record %zu has no length word", i);
-			max_rec_words = std::max(max_rec_words, off[i + 1] - off[i]);
-		}
+		if ((rc = ntc_check_offsets(off, n_rec, n_words, &max_rec_words)))
+			return rc;
 		if (c->host_timing)
 			c->host_span("submit: offset validation loop", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - v0).count());
 	}

@@ -115,6 +115,26 @@ def test_estimate_from_counters_matches_oracle(oracle):
     assert F0 == oF0 and np.array_equal(f[1:], of[1:201])
 
 
+def test_check_offsets():
+    """the offset checks of ntc_submit (host helper, no device): strictly ascending, inside the batch; longest record"""
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(1, 20, size=100_000).astype(np.uint32)
+    off = np.zeros(len(sizes) + 1, dtype=np.uint32)
+    np.cumsum(sizes, out=off[1:])
+    assert nt.check_offsets(off, int(off[-1])) == int(sizes.max())
+    assert nt.check_offsets(off[:1], 0) == 0                       # no record
+    with pytest.raises(nt.NtcError, match="off\\[n_rec\\] exceeds n_words"):
+        nt.check_offsets(off, int(off[-1]) - 1)
+    bad = off.copy()
+    bad[70_001] = bad[70_000]                                       # record 70000 without a length word
+    with pytest.raises(nt.NtcError, match="record 70000 has no length word"):
+        nt.check_offsets(bad, int(off[-1]))
+    bad = off.copy()
+    bad[5] = bad[4] - 1                                             # descending
+    with pytest.raises(nt.NtcError, match="record 4 has no length word"):
+        nt.check_offsets(bad, int(off[-1]))
+
+
 def test_sbits_rule():
     # ntcard.cpp:427-431
     assert nt.apply_sbits_rule(49_999_999_999) == 7 and nt.apply_sbits_rule(50_000_000_000) == 11
