@@ -120,6 +120,7 @@ struct ntc_ctx {
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
 	bool clear_by_memset = true;
+	bool pad_ragged = false;   // NTC_PAD=1: NTC_KERNEL_AUTO pads short ragged batches for the pipeline too
 	// NTC_HOST_TIMING=1: host time spent in the calls of the submit path, per call site, printed by ntc_destroy (diagnosis only)
 	bool host_timing = false;
 	struct HostSpan { const char* what; double total_ms, max_ms; uint64_t n; };
@@ -639,11 +640,13 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 			b.n_words = (uint64_t)b.n_rec * s4;
 		}
 	}
-	else if (b.off && b.max_rec_words >= 2 && b.max_rec_words <= 20 && b.n_rec >= 1024 && c->use_pipeline && !c->gap && c->kernel != NTC_KERNEL_ROLL64 &&
-	         record_is_piece && !getenv("NTC_NO_PAD")) {
+	else if (b.off && b.max_rec_words >= 2 && b.max_rec_words <= 20 && b.n_rec >= 1024 && c->use_pipeline && !c->gap &&
+	         (c->kernel == NTC_KERNEL_BITSLICE || (c->kernel == NTC_KERNEL_AUTO && c->pad_ragged)) && record_is_piece) {
 		// ragged batch of short records (what ntc_pack_seqs makes of reads: the documented drop-in for ntRead): zero-pad every record
 		// to the stride of the longest on the device; the pipeline takes tiles of mixed lengths (scan_kernel.cuh).  Not when the padding
-		// would be most of the batch (a few long records among many short fragments).
+		// would be most of the batch (a few long records among many short fragments).  Halves the device time of such batches, but
+		// the host currently spends longer inside ntc_submit on this route than it saves, so NTC_KERNEL_AUTO takes
+		// it only with NTC_PAD=1; NTC_KERNEL_BITSLICE (forced pipeline) always does.
 		const uint32_t s4 = (b.max_rec_words + 3u) & ~3u;
 		const uint64_t padded = (uint64_t)b.n_rec * s4;
 		bool any = false;
@@ -845,6 +848,7 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
 	c->clear_by_memset = !(getenv("NTC_CLEAR_MEMSET") && atoi(getenv("NTC_CLEAR_MEMSET")) == 0);
 	c->host_timing = getenv("NTC_HOST_TIMING") && atoi(getenv("NTC_HOST_TIMING")) != 0;
+	c->pad_ragged = getenv("NTC_PAD") && atoi(getenv("NTC_PAD")) != 0;
 	if (getenv("NTC_SCAN_PREFETCH"))
 		c->scan_prefetch = (unsigned)atoi(getenv("NTC_SCAN_PREFETCH"));
 	if (getenv("NTC_CHUNK_WAVES"))

@@ -43,7 +43,7 @@ def main():
     out = {"workload": f"{n} reads x {L} bp with N runs -> {n_rec} ragged records, {n_words * 4 / 1e6:.0f} MB packed, k={k}, s=7, r=27"}
     hists = {}
     with nt.Sketch([k], rBits=27, sBits=7) as sk:
-        for name, kern in (("pipeline", nt.KERNEL_AUTO), ("roll64", nt.KERNEL_ROLL64)):
+        for name, kern in (("pipeline", nt.KERNEL_BITSLICE), ("roll64", nt.KERNEL_ROLL64)):
             sk.set_kernel(kern)
 
             host = {"submit_ms": 0.0, "finish_ms": 0.0}

@@ -6,7 +6,6 @@ show='import json,sys; d=json.loads(sys.stdin.readline()); print({k:(round(v["wa
 run() { echo "== $*"; env "$@" python tools/bench_ragged.py --steps 5 $EXTRA | python -c "$show"; }
 run NTC_DUMMY=0
 NTC_HOST_TIMING=1 python tools/bench_ragged.py --steps 5 2>&1 >/dev/null | grep "host timing"   # per call site, both kernels (two contexts' worth in one table)
-run NTC_NO_PAD=1
 run NTC_APPLY_COOP=0
 run NTC_CLEAR_MEMSET=0
 run CUDA_DEVICE_MAX_CONNECTIONS=32
