@@ -12,3 +12,4 @@ run CUDA_DEVICE_MAX_CONNECTIONS=32
 run CUDA_MODULE_LOADING=EAGER
 EXTRA="--per 2000000" run NTC_DUMMY=0
 EXTRA="--per 125000" run NTC_DUMMY=0
+EXTRA="--roll64-first" run NTC_DUMMY=0
