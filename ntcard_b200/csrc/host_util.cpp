@@ -8,6 +8,10 @@
 #include <sys/types.h>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include "../../include/ntcard_b200.h"
 #include "internal.h"
 #include "nthash_device.cuh"
@@ -44,6 +48,40 @@ static const struct CodeTab {
 		t[(unsigned char)'U'] = t[(unsigned char)'u'] = 3;
 	}
 } g_code;
+
+// ---- 16 characters at a time (SSSE3; the packer runs on the submitting / reader threads and bounds the command line) ----
+// valid16: bit q set = character q is one of ACGTUacgtu.  pack16: the 2-bit codes of 16 valid characters, base q in bits 2q..2q+1.
+// The code comes straight from the ASCII bits: (c >> 1) & 3 is A=0 C=1 T/U=2 G=3 in either case; x ^ (x >> 1) swaps 2 and 3.
+#if defined(__x86_64__)
+#define NTC_HAVE_SIMD_PACK 1
+__attribute__((target("ssse3"))) static inline unsigned valid16(const unsigned char* p)
+{
+	const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+	const __m128i up = _mm_and_si128(v, _mm_set1_epi8((char)0xDF)); // fold case
+	__m128i ok = _mm_cmpeq_epi8(up, _mm_set1_epi8('A'));
+	ok = _mm_or_si128(ok, _mm_cmpeq_epi8(up, _mm_set1_epi8('C')));
+	ok = _mm_or_si128(ok, _mm_cmpeq_epi8(up, _mm_set1_epi8('G')));
+	ok = _mm_or_si128(ok, _mm_cmpeq_epi8(up, _mm_set1_epi8('T')));
+	ok = _mm_or_si128(ok, _mm_cmpeq_epi8(up, _mm_set1_epi8('U')));
+	return (unsigned)_mm_movemask_epi8(ok);
+}
+
+__attribute__((target("ssse3"))) static inline uint32_t pack16(const unsigned char* p)
+{
+	const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+	__m128i c = _mm_and_si128(_mm_srli_epi16(v, 1), _mm_set1_epi8(3));
+	c = _mm_xor_si128(c, _mm_and_si128(_mm_srli_epi16(c, 1), _mm_set1_epi8(1)));
+	const __m128i t = _mm_maddubs_epi16(c, _mm_set1_epi16(0x0401));  // byte pairs  -> 4-bit values in 16-bit lanes
+	const __m128i u = _mm_madd_epi16(t, _mm_set1_epi32(0x00100001)); // lane pairs  -> 8-bit values in 32-bit lanes
+	const __m128i b = _mm_shuffle_epi8(u, _mm_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1));
+	return (uint32_t)_mm_cvtsi128_si32(b);
+}
+
+static const bool g_simd_pack = __builtin_cpu_supports("ssse3");
+#else
+#define NTC_HAVE_SIMD_PACK 0
+static const bool g_simd_pack = false;
+#endif
 
 static inline uint64_t mix64(uint64_t x)
 {
@@ -117,8 +155,22 @@ int ntc_pack_seqs(const char* chars, const uint64_t* seq_off, size_t n_seq, uint
 			while (i < L && ntc::g_code.t[p[i]] > 3)
 				i++;
 			uint64_t j = i;
+#if NTC_HAVE_SIMD_PACK
+			if (ntc::g_simd_pack)
+				while (j + 16 <= L) { // whole blocks of valid characters
+					const unsigned m = ntc::valid16(p + j);
+					if (m != 0xFFFFu) {
+						j += (unsigned)__builtin_ctz(~m); // first invalid character of the block ends the run
+						goto run_end;
+					}
+					j += 16;
+				}
+#endif
 			while (j < L && ntc::g_code.t[p[j]] <= 3)
 				j++;
+#if NTC_HAVE_SIMD_PACK
+		run_end:;
+#endif
 			const uint64_t len = j - i;
 			if (len >= min_len) {
 				if (len > 0xFFFFFFFFull)
@@ -132,6 +184,11 @@ int ntc_pack_seqs(const char* chars, const uint64_t* seq_off, size_t n_seq, uint
 					off[nr] = (uint32_t)nw;
 				words[nw++] = (uint32_t)len;
 				uint64_t b = i;
+#if NTC_HAVE_SIMD_PACK
+				if (ntc::g_simd_pack)
+					for (; b + 16 <= j; b += 16)
+						words[nw++] = ntc::pack16(p + b);
+#endif
 				for (; b + 16 <= j; b += 16) {
 					uint32_t w = 0;
 					for (unsigned q = 0; q < 16; q++)
@@ -140,8 +197,13 @@ int ntc_pack_seqs(const char* chars, const uint64_t* seq_off, size_t n_seq, uint
 				}
 				if (b < j) {
 					uint32_t w = 0;
-					for (unsigned q = 0; b + q < j; q++)
-						w |= (uint32_t)ntc::g_code.t[p[b + q]] << (2 * q);
+#if NTC_HAVE_SIMD_PACK
+					if (ntc::g_simd_pack && b + 16 <= L) // the 16 characters exist: pack them all, keep the run's
+						w = ntc::pack16(p + b) & ((1u << (2 * (unsigned)(j - b))) - 1u);
+					else
+#endif
+						for (unsigned q = 0; b + q < j; q++)
+							w |= (uint32_t)ntc::g_code.t[p[b + q]] << (2 * q);
 					words[nw++] = w;
 				}
 				nr++;

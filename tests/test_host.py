@@ -73,6 +73,31 @@ def test_pack_splits_at_invalid(oracle):
         assert np.array_equal(np.sort(a), np.sort(b))
 
 
+def test_pack_random_bytes_against_plain_python():
+    """the packer's 16-characters-at-a-time path (validity mask, 2-bit codes from the ASCII bits, partial last word) against a
+    plain restatement: every byte value occurs, segment boundaries fall on every offset inside a block, record words are exact
+    (unused high bits of the last word are zero)"""
+    import re
+    rng = np.random.default_rng(12)
+    alphabet = np.frombuffer(b"ACGTUacgtu" * 40 + bytes(range(256)), dtype=np.uint8)      # ~14 % of the bytes are invalid
+    clean = np.frombuffer(b"ACGTUacgtu", dtype=np.uint8)
+    reads = []
+    for L in list(range(0, 70)) + [150, 151, 255, 256, 257, 1000]:
+        for rep in range(4):
+            reads.append(bytes(rng.choice(alphabet if rep < 2 else clean, size=L)))
+    tr = bytes.maketrans(b"acgtuU", b"ACGTTT")
+    for min_len in (1, 12, 32):
+        words, off = nt.pack_reads(reads, min_len=min_len)
+        want = [seg.translate(tr) for r in reads for seg in re.split(rb"[^ACGTUacgtu]+", r) if len(seg) >= max(min_len, 1)]
+        assert unpack(words, off) == want
+        assert int(off[-1]) == len(words) and nt.check_offsets(off, len(words)) >= 1
+        for i in range(len(off) - 1):                                  # exact words: nothing above the last base
+            L = int(words[off[i]])
+            assert off[i + 1] - off[i] == 1 + (L + 15) // 16
+            if L % 16:
+                assert int(words[off[i + 1] - 1]) >> (2 * (L % 16)) == 0
+
+
 def test_pack_overflow_reports():
     chars = np.frombuffer(b"ACGTACGTACGTACGTACGT" * 3 + b"\0", dtype=np.uint8)
     soff = np.array([0, 20, 40, 60], dtype=np.uint64)
