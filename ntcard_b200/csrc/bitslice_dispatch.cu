@@ -10,7 +10,7 @@
 namespace ntc {
 namespace pl {
 
-#define X(n) cudaError_t launch_scan_km_##n(unsigned sBits, const ScanArgs& a);
+#define X(n) cudaError_t launch_scan_km_##n(unsigned sBits, const ScanArgs& a); cudaError_t launch_fused_km_##n(unsigned sBits, const FusedArgs& a);
 BS_KM_LIST
 #undef X
 
@@ -34,6 +34,23 @@ cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a)
 #undef X
 	default: return cudaErrorInvalidValue;
 	}
+}
+
+cudaError_t launch_fused(unsigned k, unsigned sBits, const FusedArgs& a)
+{
+	switch (k % 31) {
+#define X(n) case n: return launch_fused_km_##n(sBits, a);
+		BS_KM_LIST
+#undef X
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+// shared memory of the fused kernel: byte tables + per warp (plane ring + 3 mirror slots, candidate queue, log state); fused_kernel.cuh
+size_t fused_smem_bytes(uint32_t ring, uint32_t nwarps, uint32_t qlane, uint32_t nbins)
+{
+	const size_t queue = (((size_t)qlane * 64) + 15) & ~(size_t)15;
+	return 8 * 256 * 16 + (size_t)nwarps * ((size_t)(ring + 3u) * 256u + queue + 7 * (size_t)nbins * 4u);
 }
 
 // Per byte position j (4 bases) of a 32-base block: FB = XOR_u srol^(31-i) seed[c_i], RB = XOR_u srol^i seed[3-c_i], i = 4j+u

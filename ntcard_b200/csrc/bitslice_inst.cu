@@ -1,6 +1,7 @@
 // bitslice_inst.cu -- one translation unit per k mod 31 (compiled with -DBS_KM=<0..30>), so the unrolled variants
-// of the scan kernel build in parallel.  Each instantiates the kernel for sBits = 7 and 11, the two values the
+// of the scan kernel and of the fused sketch kernel build in parallel.  Each instantiates the kernel for sBits = 7 and 11, the two values the
 // reference can reach without its hidden -s flag (ntcard.cpp:58, 430-431).
+#include "fused_kernel.cuh"
 #include "scan_kernel.cuh"
 
 #ifndef BS_KM
@@ -19,6 +20,15 @@ cudaError_t BS_CAT(launch_scan_km_, BS_KM)(unsigned sBits, const ScanArgs& a)
 		return launch_scan_one<BS_KM, 7>(a);
 	if (sBits == 11)
 		return launch_scan_one<BS_KM, 11>(a);
+	return cudaErrorInvalidValue;
+}
+
+cudaError_t BS_CAT(launch_fused_km_, BS_KM)(unsigned sBits, const FusedArgs& a)
+{
+	if (sBits == 7)
+		return launch_fused_one<BS_KM, 7>(a);
+	if (sBits == 11)
+		return launch_fused_one<BS_KM, 11>(a);
 	return cudaErrorInvalidValue;
 }
 

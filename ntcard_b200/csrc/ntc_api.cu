@@ -119,6 +119,9 @@ struct ntc_ctx {
 	size_t cap_tile_info = 0;
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
+	bool use_fused = true;     // the fused sketch kernel (fused_kernel.cuh); NTC_FUSED=0: scan + hit kernels (round-1 pipeline, kept for comparison)
+	bool no_stage = false;     // NTC_NO_STAGE=1 (stand-alone hit kernel: gather with __ldg instead of a TMA-staged tile)
+	bool no_retile = false;    // NTC_NO_RETILE=1
 	bool clear_by_memset = true;
 	bool pad_ragged = false;   // NTC_PAD=1: NTC_KERNEL_AUTO pads short ragged batches for the pipeline too
 	// NTC_HOST_TIMING=1: host time spent in the calls of the submit path, per call site, printed by ntc_destroy (diagnosis only)
@@ -252,7 +255,9 @@ int pool_create(ntc_ctx* c)
 	}
 	P.nbins = 1u << (idx_bits - P.bin_shift);
 	P.n_slices = c->nK * P.nbins;
-	P.slice_cap = std::max(16u, P.n_blocks / 4);
+	// every slice's block list can hold the whole pool: a list can then never fill up before the pool does, so the only
+	// "out of space" event is pool exhaustion, which both hit paths handle exactly (deferred tiles / conditional flush)
+	P.slice_cap = P.n_blocks;
 	CK(cudaMalloc((void**)&P.entries, (size_t)P.n_blocks * ntc::pl::kBlkEntries * sizeof(uint32_t)));
 	CK(cudaMalloc((void**)&P.slice_blocks, (size_t)P.n_slices * P.slice_cap * sizeof(uint32_t)));
 	// control region: [ctl CTL_WORDS][slice_nblk n_slices][zero_done n_slices][apply_done n_slices][pad][cand 2 words]
@@ -266,7 +271,7 @@ int pool_create(ntc_ctx* c)
 	P.cand = reinterpret_cast<unsigned long long*>(P.apply_done + P.n_slices + ((ntc::pl::CTL_WORDS + 3 * P.n_slices) & 1u));
 	c->apply_grid = (unsigned)ntc::pl::apply_max_grid(c->n_sm);
 	c->hit_grid_max = (unsigned)c->n_sm * 2u;
-	P.max_groups = (unsigned)c->n_sm * 4u;
+	P.max_groups = (unsigned)c->n_sm * 8u; // fused kernel: one saved state per warp (8 per SM); hit kernel: per group (<= 4 per SM)
 	P.epoch = 1;
 	{
 		const size_t gwords = (size_t)c->nK * P.max_groups * (1 + 5 * (size_t)P.nbins);
@@ -320,7 +325,45 @@ int flush(ntc_ctx* c)
 struct PipeShape {
 	uint32_t ring = 0, nwarps = 0, npos_max = 0, rows_per_unit = 64, units_per_tile = 1, tiles_per_unit = 1, start_limit = 0;
 	size_t smem = 0;
+	uint32_t qlane = 0; // fused kernel: candidate slots per lane
 };
+
+// Shared-memory shape of the fused kernel for one k: as many warps as fit (<= 8) with a candidate queue that holds a tile's
+// expected candidates per lane (npos * 32 / 2^(sBits-1)) with a wide margin; the index buffer of the append phase aliases the
+// plane ring, hence qlane <= 2 * (ring + 3), and the ring may be chosen larger than k + 16 to make room.
+bool fused_shape(uint32_t k, uint32_t sBits, uint32_t npos_max, uint32_t nbins, PipeShape* s)
+{
+	if (npos_max > ntc::pl::kFusedMaxPos)
+		return false;
+	const uint32_t ring_min = (k + 16 + 15) & ~15u;
+	const double expect = (double)npos_max * 32.0 / (double)(1u << (sBits - 1));
+	const uint32_t target = std::max(32u, ((uint32_t)(expect * 1.5) + 24u + 7u) & ~7u);
+	const uint32_t qmin = std::max(32u, (uint32_t)(expect * 1.2) + 16u);
+	for (uint32_t nw = ntc::pl::kFusedWarps; nw >= 1; nw--) {
+		uint32_t best_q = 0, best_ring = 0;
+		for (uint32_t ring = ring_min; ring <= ring_min + 256; ring += 16) {
+			const size_t fixed = ntc::pl::fused_smem_bytes(ring, nw, 0, nbins);
+			if (fixed > ntc::pl::kSmemMax)
+				break;
+			const uint32_t q_mem = (uint32_t)((ntc::pl::kSmemMax - fixed) / nw / 64);
+			const uint32_t q = std::min(std::min(target, 2u * (ring + 3u)), q_mem);
+			if (q > best_q) {
+				best_q = q;
+				best_ring = ring;
+			}
+			if (q >= target)
+				break;
+		}
+		if (best_q >= qmin || (nw == 1 && best_q >= 32)) {
+			s->ring = best_ring;
+			s->nwarps = nw;
+			s->qlane = best_q;
+			s->smem = ntc::pl::fused_smem_bytes(best_ring, nw, best_q, nbins);
+			return s->smem <= ntc::pl::kSmemMax;
+		}
+	}
+	return false;
+}
 
 // Which k indices the scan -> hit -> apply pipeline can take for this batch.
 uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, PipeShape* shape, uint32_t min_rec = 1024)
@@ -343,6 +386,12 @@ uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 		s.npos_max = max_len - k + 1;
 		if (s.npos_max > 65535)
 			continue;
+		if (c->use_fused) {
+			if (!fused_shape(k, c->sBits, s.npos_max, c->pool.nbins, &s))
+				continue;
+			kmask |= 1u << ki;
+			continue;
+		}
 		const uint32_t r = (k + 16 + 15) & ~15u; // plane ring: k + 16 positions, rounded up to whole columns
 		const size_t per_warp = (size_t)(r + 3) * 256; // ring + 3 mirror slots (scan_kernel.cuh)
 		const uint32_t nw = (uint32_t)std::min<size_t>(8, ntc::pl::kSmemMax / per_warp);
@@ -396,8 +445,65 @@ int run_pipeline_k(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeS
 	return NTC_OK;
 }
 
+// One k over one batch with the fused kernel: pass 0 -> conditional flush -> pass 1 (deferred tiles) -> fallback (flagged tiles).
+int run_fused_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh)
+{
+	int rc;
+	const uint32_t n_tiles = (b.n_rec + 1023) / 1024;
+	if ((rc = grow(&c->d_tile_info, &c->cap_tile_info, (size_t)n_tiles, false)))
+		return rc;
+	ntc::pl::Pool& P = c->pool;
+	CK(cudaMemsetAsync(P.ctl + ntc::pl::CTL_NFLAG, 0, 2 * sizeof(uint32_t), c->stream)); // NFLAG and NDEFER
+	ntc::pl::FusedArgs fa;
+	fa.words = b.words;
+	fa.stride = b.stride;
+	fa.n_rec = b.n_rec;
+	fa.n_tiles = n_tiles;
+	fa.L.k = c->k[ki];
+	fa.L.ring = sh.ring;
+	fa.L.nwarps = sh.nwarps;
+	fa.L.npos_max = sh.npos_max;
+	fa.L.start_limit = sh.start_limit;
+	fa.L.mixed_ok = c->kinit[ki].polyA_sampled ? 0u : 1u;
+	fa.L.prefetch = c->scan_prefetch;
+	memcpy(fa.L.F0, c->kinit[ki].F0, sizeof fa.L.F0);
+	memcpy(fa.L.R0, c->kinit[ki].R0, sizeof fa.L.R0);
+	fa.ki = ki;
+	fa.pass = 0;
+	fa.qlane = sh.qlane;
+	fa.d_tab = c->d_bs_tab;
+	fa.rot_a = c->kinit[ki].rot_a;
+	fa.rot_b = c->kinit[ki].rot_b;
+	fa.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
+	fa.pool = P;
+	fa.tile_info = c->d_tile_info;
+	fa.f1_k = c->d_f1 + ki;
+	fa.grid = std::min<unsigned>((unsigned)c->n_sm, n_tiles);
+	fa.smem_bytes = sh.smem;
+	fa.stream = c->stream;
+	if ((rc = stage_begin(c, 0)))
+		return rc;
+	CK(ntc::pl::launch_fused(c->k[ki], c->sBits, fa));
+	if ((rc = stage_end(c)) || (rc = stage_begin(c, 1)))
+		return rc;
+	// Normally the next three launches find nothing to do and leave at once: the flush runs only when pass 0 deferred tiles (pool
+	// exhausted before the sketch was materialised) or flagged tiles (mixed lengths whose padding k-mer is sampled), pass 1 and the
+	// fallback kernel only over those tiles.
+	CK(ntc::pl::launch_apply(P, c->d_counters, 2, 0, c->apply_grid, c->stream));
+	fa.pass = 1;
+	CK(ntc::pl::launch_fused(c->k[ki], c->sBits, fa));
+	CK(ntc::pl::launch_fallback(b.words, b.stride, b.n_rec, n_tiles, c->d_tile_info, c->d_params, ki, fa.ctr_k, P.ctl, c->n_sm, c->stream));
+	if ((rc = stage_end(c)))
+		return rc;
+	c->n_launches += 4;
+	c->pending = true;
+	return NTC_OK;
+}
+
 int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh)
 {
+	if (c->use_fused)
+		return run_fused_chunk(c, b, ki, sh);
 	int rc;
 	const uint32_t n_tiles = (b.n_rec + 1023) / 1024;
 	HT(c, "chunk: grow masks / tile_info", rc = grow(&c->d_masks, &c->cap_masks, (size_t)n_tiles * sh.npos_max * 32, false);
@@ -458,7 +564,7 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	ha.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 	ha.pool = P;
 	ha.stream = c->stream;
-	const bool staged = ntc::pl::hit_can_stage(b.stride, sh.units_per_tile, sh.tiles_per_unit) && !(getenv("NTC_NO_STAGE"));
+	const bool staged = ntc::pl::hit_can_stage(b.stride, sh.units_per_tile, sh.tiles_per_unit) && !c->no_stage;
 	const unsigned gpc = staged ? 3u : 2u; // groups per CTA
 	const unsigned hit_ctas = std::min<unsigned>((unsigned)c->n_sm * (staged ? 1u : 2u), (ha.n_units + gpc - 1) / gpc);
 	// conditional flush: only when this batch could exhaust the pool while the sketch is not materialised yet
@@ -524,7 +630,7 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 int run_retiled(ntc_ctx* c, const ntc::BatchView& b_in, uint32_t* handled)
 {
 	*handled = 0;
-	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || b_in.n_rec == 0 || getenv("NTC_NO_RETILE"))
+	if (!c->use_pipeline || c->gap || c->kernel == NTC_KERNEL_ROLL64 || b_in.n_rec == 0 || c->no_retile)
 		return NTC_OK;
 	if (b_in.n_words / b_in.n_rec < 40) // average record below ~600 bases: pieces would mostly be tails
 		return NTC_OK;
@@ -844,6 +950,9 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 		}
 	}
 	c->use_pipeline = !(getenv("NTC_PIPELINE") && atoi(getenv("NTC_PIPELINE")) == 0);
+	c->use_fused = !(getenv("NTC_FUSED") && atoi(getenv("NTC_FUSED")) == 0);
+	c->no_stage = getenv("NTC_NO_STAGE") != nullptr;
+	c->no_retile = getenv("NTC_NO_RETILE") != nullptr;
 	// two 8-byte cudaMemsetAsync per batch (default) or one 1-thread kernel (NTC_CLEAR_MEMSET=0): measured, the kernel variant makes the host
 	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
 	c->clear_by_memset = !(getenv("NTC_CLEAR_MEMSET") && atoi(getenv("NTC_CLEAR_MEMSET")) == 0);

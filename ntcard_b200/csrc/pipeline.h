@@ -26,6 +26,10 @@ constexpr uint32_t kWireBlkWords = 260;        // a log block on the wire (multi
 constexpr uint32_t kBlkSlack = 96;            // a block with fewer free entries than this is closed at the end of a round
 constexpr uint32_t kVoid = 0xFFFFFFFFu;
 constexpr uint32_t kTileFlag = 0xFFFFFFFFu;   // tile_info value: not uniform -> fallback kernel
+constexpr uint32_t kTileDefer = 0x80000000u;  // fused kernel: tile_info = kTileDefer | first k-mer start still to be hashed (pool ran out
+                                              // while the sketch was not materialised: second pass after the conditional flush)
+constexpr uint32_t kFusedMaxPos = 2048;       // fused kernel: k-mer starts per record (11 bits of a 16-bit candidate word)
+constexpr uint32_t kFusedWarps = 8;
 constexpr uint32_t kTileRecs = 1024;
 constexpr uint32_t kMaxBins = 64;             // slices per k
 constexpr uint32_t kQueueCap = 4096;          // candidates per round of a hit group
@@ -34,7 +38,8 @@ constexpr uint32_t kApplyThreads = 512;
 constexpr size_t kSmemMax = 232448;           // 227 KB opt-in limit per CTA on sm_100
 
 // control words (device)
-enum { CTL_NEXT = 0, CTL_STATE = 1, CTL_NFLAG = 2, CTL_TICKET = 3, CTL_FLUSHES = 4, CTL_DIRECT = 5, CTL_WORDS = 8 };
+// NFLAG and NDEFER are adjacent: one 8-byte memset clears both at the start of a batch
+enum { CTL_NEXT = 0, CTL_STATE = 1, CTL_NFLAG = 2, CTL_NDEFER = 3, CTL_TICKET = 4, CTL_FLUSHES = 5, CTL_DIRECT = 6, CTL_WORDS = 8 };
 
 struct Pool {                    // device pointers + geometry, passed by value
 	uint32_t* entries;           // [n_blocks][kBlkEntries] counter indices inside one k's [2][2^rBits] sub-sketch
@@ -73,6 +78,23 @@ struct ScanArgs {
 	cudaStream_t stream;
 };
 
+struct FusedArgs {               // the fused sketch kernel (fused_kernel.cuh): scan + full hash + log append in one launch
+	const uint32_t* words;
+	uint32_t stride, n_rec, n_tiles;
+	ScanLaunch L;                // ring here also sizes the per-warp index buffer that aliases the planes
+	uint32_t ki, pass;           // pass 0: every tile (counts F1); pass 1: only the tiles pass 0 deferred
+	uint32_t qlane;              // candidate slots per lane of a warp's queue (<= 2 * (ring + 3))
+	const uint4* d_tab;          // [8][256] byte tables of the full hash
+	uint64_t rot_a, rot_b;
+	uint32_t* ctr_k;             // counters of this k (direct increments once the sketch is materialised and the pool is full)
+	Pool pool;
+	uint32_t* tile_info;         // [n_tiles]: 0 done, kTileFlag -> fallback kernel, kTileDefer | p -> second pass
+	unsigned long long* f1_k;
+	unsigned grid;
+	size_t smem_bytes;
+	cudaStream_t stream;
+};
+
 struct HitArgs {
 	const uint32_t* words;
 	uint32_t stride, n_rec, n_tiles;
@@ -92,6 +114,8 @@ bool have_scan_kernel(unsigned k, unsigned sBits);
 // Fill the byte tables of the full hash (host): tab[j*256+b] = {FB lo, FB hi, RB lo, RB hi}.
 void build_tables(uint32_t* tab /* 8*256*4 words */);
 cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a);
+cudaError_t launch_fused(unsigned k, unsigned sBits, const FusedArgs& a);
+size_t fused_smem_bytes(uint32_t ring, uint32_t nwarps, uint32_t qlane, uint32_t nbins);
 bool hit_can_stage(uint32_t stride, uint32_t units_per_tile, uint32_t tiles_per_unit);
 unsigned hit_groups_per_sm(bool staged);
 cudaError_t launch_hit(const HitArgs& a, bool staged, unsigned ctas);
@@ -100,6 +124,7 @@ cudaError_t launch_fallback(const uint32_t* words, uint32_t stride, uint32_t n_r
     const DevParams* d_params, uint32_t ki, uint32_t* ctr_k, const uint32_t* ctl, int n_sm, cudaStream_t st);
 // force = 0: flush only if the batch about to be hashed could overflow the pool while the sketch is still
 // unmaterialised (or has flagged tiles); force = 1: flush whatever is pending and materialise the sketch.
+// force = 2 (fused kernel): flush when tiles were deferred or flagged, or when a materialised sketch's pool is 3/4 full.
 cudaError_t launch_apply(const Pool& pool, uint32_t* counters, int force, uint32_t reserve_blocks, unsigned grid, cudaStream_t st,
     const uint32_t* d_order = nullptr, uint32_t n_order = 0);
 // Hit-log exchange between ranks: copy the blocks of runs of slices to contiguous buffers / register received blocks
