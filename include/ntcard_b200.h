@@ -139,6 +139,27 @@ int ntc_log_counts(ntc_ctx* ctx, uint32_t* nblk /* [n_slices] */, int* exportabl
 int ntc_log_export(ntc_ctx* ctx, const uint32_t* slices, uint32_t n, void* d_blocks);
 int ntc_log_import(ntc_ctx* ctx, const void* d_blocks, uint32_t n_blocks, const uint32_t* runs, uint32_t n_runs);
 int ntc_flush_slices(ntc_ctx* ctx, const uint8_t* owned /* [n_slices] */);
+/* ---- multi-GPU reduction over peer memory (NVLink) -----------------------------------------
+ * One process per GPU on one node.  Replaces, across GPUs, what the reference gets for free from its single
+ * shared sketch (ntcard.cpp:439, 142-143) and its F1 merge (ntcard.cpp:464-466).  Rank r owns the sketch slices
+ * s with s % world == r.  Set-up, once: every rank exports the IPC handles of its hit log (ntc_peer_export),
+ * the handles are all-gathered by the caller, every rank maps its peers' logs (ntc_peer_attach).  Per reduction,
+ * all on the context's stream and without a host synchronisation:
+ *   ntc_log_status_device(d_status)      d_status[0..nK) = F1 per k, d_status[nK] = 1 if this rank's log is no
+ *                                        longer complete (flushed / direct increments), as int64
+ *   <all-reduce (sum) of d_status>       F1 totals; also the barrier "every rank's log is complete"
+ *   ntc_reduce_owned(d_status, d_hist)   zero the owned slices, apply to them the log entries of ALL ranks (remote
+ *                                        logs are read through NVLink by the kernel itself), counter-value histogram
+ *                                        of the owned slices -> d_hist [nK][2][65536] uint32 (values >= 1 only).
+ *                                        Does nothing useful when d_status[nK] != 0: the caller then falls back to
+ *                                        a dense reduction (ntc_counters_device + all-reduce).
+ *   <all-reduce (sum) of d_hist>         the global histogram; also the barrier "nobody reads my log any more"
+ * Afterwards only ntc_totals / ntc_set_totals / ntc_reset are valid (as after ntc_flush_slices).              */
+#define NTC_PEER_HANDLE_BYTES 128
+int ntc_peer_export(ntc_ctx* ctx, void* handles /* NTC_PEER_HANDLE_BYTES */);
+int ntc_peer_attach(ntc_ctx* ctx, int world, int rank, const void* all_handles /* world x NTC_PEER_HANDLE_BYTES, by rank */);
+int ntc_log_status_device(ntc_ctx* ctx, void* d_status /* int64 [nK + 1], device */);
+int ntc_reduce_owned(ntc_ctx* ctx, const void* d_status, void* d_p_hist);
 int ntc_stream_sync(ntc_ctx* ctx); /* wait for the context's stream WITHOUT flushing (before handing exported buffers to a collective) */
 int ntc_hist_slices(ntc_ctx* ctx, const uint8_t* owned /* [n_slices] */, uint32_t* p_hist, void* d_p_hist);
 

@@ -36,7 +36,7 @@ namespace ntc {
 namespace pl {
 
 constexpr uint32_t kWarpStateArrays = 7; // cur, fill, curpos, wcnt, wbase, wat, wcursor: nbins words each
-constexpr int kFusedBatch = 4;                     // candidates per lane whose loads are in flight together
+constexpr int kFusedBatch = 8;                     // candidates per lane whose loads are in flight together
 
 __host__ __device__ constexpr size_t fused_queue_bytes(uint32_t qlane) { return (((size_t)qlane * 64) + 15) & ~(size_t)15; }
 __host__ __device__ constexpr size_t fused_warp_bytes(uint32_t ring, uint32_t qlane, uint32_t nbins)
@@ -102,36 +102,49 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane)
 
 // The hash + append phase of one round of one tile.  Returns false when the pool could not serve the round while the sketch is
 // not materialised (nothing was appended: the caller defers the tile).
-template <int S>
-__device__ __noinline__ bool fused_drain(const FusedArgs& a, const WarpSmem& sm, const uint4* __restrict__ tab, uint32_t tile, uint32_t cnt,
-    uint32_t p_end, bool mixed, uint32_t lane)
+// Not inlined, so that its registers do not add to the scan loop's; the shared-memory pointers are rebuilt from the kernel's
+// dynamic shared array here, which keeps them shared-space accesses (LDS / STS) instead of generic ones.
+// This phase is bound by the load/store unit (L1 wavefronts of the gathers and of the scattered log stores, the table
+// lookups), so it is written to need few of them: 128-bit gathers, and the slot of a hit inside its slice's block is
+// assigned with a warp match instead of shared-memory atomics.
+static __device__ __noinline__ bool fused_drain(const FusedArgs& a, uint32_t tile, uint32_t cnt, uint32_t p_end, bool mixed, uint32_t lane, uint32_t warp)
 {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const Pool& P = a.pool;
 	const uint32_t nb = P.nbins, k = a.L.k;
+	const uint4* tab = reinterpret_cast<const uint4*>(smem_raw);
+	const WarpSmem sm = warp_smem(smem_raw + kTabBytes + (size_t)warp * fused_warp_bytes(a.L.ring, a.qlane, nb), a.L.ring, a.qlane, nb);
 	uint32_t maxcnt = cnt;
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1)
 		maxcnt = max(maxcnt, __shfl_xor_sync(0xFFFFFFFFu, maxcnt, d));
 	if (maxcnt == 0)
 		return true;
-	for (uint32_t b = lane; b < nb; b += 32)
-		sm.wcnt[b] = 0;
+	// cursor of every slice: the fill of the warp's open block (a full block when there is none); wcnt keeps the start
+	for (uint32_t b = lane; b < nb; b += 32) {
+		const uint32_t f = sm.cur[b] != kVoid ? sm.fill[b] : kBlkEntries;
+		sm.wcursor[b] = f;
+		sm.wcnt[b] = f;
+	}
 	__syncwarp();
-	HashCtx c;
-	c.words = a.words;
-	c.stride = a.stride;
-	c.k = k;
-	c.rBits = P.rBits;
-	c.sBits = S;
-	c.tab = tab;
-	c.rot_a = a.rot_a;
-	c.rot_b = a.rot_b;
-	const uint32_t last = a.stride - 2u;
-	// ---- candidates -> counter indices (parked in hq), hits per slice ---------------------------------------------
+	HashK K;
+	K.k = a.hk_k;
+	K.tprime = a.hk_tprime;
+	K.nblk = a.hk_nblk;
+	K.head_ra = a.hk_head_ra;
+	K.head_rb = a.hk_head_rb;
+	K.head_c = a.hk_head_c;
+	K.head_d = a.hk_head_d;
+	K.rot_a = a.hk_rot_a;
+	K.rot_b = a.hk_rot_b;
+	const uint32_t rBits = P.rBits, S = a.sBits, bin_shift = P.bin_shift, n_rec = a.n_rec, ngroups = a.stride >> 2;
+	const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(a.words);
+	const uint32_t lt = (1u << lane) - 1u;
+	// ---- candidates -> counter index + slot in the slice's block (parked in hq / queue) ---------------------------
 	for (uint32_t i0 = 0; i0 < maxcnt; i0 += kFusedBatch) {
-		HitLoad h[kFusedBatch];
+		HitLoadV h[kFusedBatch];
 		uint32_t pp[kFusedBatch];
-		const uint32_t* rw[kFusedBatch];
+		const uint4* rp[kFusedBatch];
 		bool val[kFusedBatch];
 #pragma unroll
 		for (int u = 0; u < kFusedBatch; u++) {
@@ -139,22 +152,32 @@ __device__ __noinline__ bool fused_drain(const FusedArgs& a, const WarpSmem& sm,
 			const uint32_t e = i < cnt ? sm.queue[i * 32u + lane] : 0u;
 			const uint32_t p = e >> 5, rec = tile * kTileRecs + (e & 31u) * 32u + lane;
 			pp[u] = p;
-			val[u] = i < cnt && p < p_end && rec < a.n_rec; // past the round's end / slots past the end of the batch
-			rw[u] = a.words + (uint64_t)min(rec, a.n_rec - 1u) * a.stride + 1;
+			val[u] = i < cnt && p < p_end && rec < n_rec; // past the round's end / slots past the end of the batch
+			rp[u] = recs + (uint64_t)min(rec, n_rec - 1u) * ngroups;
 			if (val[u])
-				h[u] = hit_issue<false>(c, rw[u], p, last);
+				h[u] = hit_issue_v(rp[u], ngroups, 1u + (p >> 4));
 		}
 #pragma unroll
 		for (int u = 0; u < kFusedBatch; u++) {
 			const uint32_t i = i0 + u;
 			uint32_t idx = kVoid;
 			// positions past the end of a record of a mixed-length tile ran on its padding (scan_kernel.cuh)
-			if (val[u] && (!mixed || pp[u] + k <= __ldg(rw[u] - 1)))
-				idx = hit_finish<false>(c, h[u], rw[u], pp[u], last);
-			if (i < maxcnt)
-				sm.hq[i * 32u + lane] = idx;
+			if (val[u] && (!mixed || pp[u] + k <= __ldg(reinterpret_cast<const uint32_t*>(rp[u]))))
+				idx = hash_kmer_v(K, tab, rBits, S, h[u], rp[u], ngroups, pp[u]);
+			const uint32_t b = idx == kVoid ? 0xFFFFu : idx >> bin_shift;
+			const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b);
+			const uint32_t rank = (uint32_t)__popc(peers & lt);
+			uint32_t slot = 0;
 			if (idx != kVoid)
-				atomicAdd(&sm.wcnt[idx >> P.bin_shift], 1u);
+				slot = sm.wcursor[b] + rank;
+			__syncwarp();
+			if (idx != kVoid && rank == 0)
+				sm.wcursor[b] = slot + (uint32_t)__popc(peers);
+			__syncwarp();
+			if (i < maxcnt) {
+				sm.hq[i * 32u + lane] = idx;
+				sm.queue[i * 32u + lane] = (uint16_t)slot;
+			}
 		}
 	}
 	__syncwarp();
@@ -168,8 +191,8 @@ __device__ __noinline__ bool fused_drain(const FusedArgs& a, const WarpSmem& sm,
 		if (32u * j >= nb) // warp-uniform
 			continue;
 		const bool mine = b < nb;
-		const uint32_t need = mine ? sm.wcnt[b] : 0u;
-		const uint32_t f = (mine && sm.cur[b] != kVoid) ? sm.fill[b] : kBlkEntries;
+		const uint32_t f = mine ? sm.wcnt[b] : kBlkEntries;
+		const uint32_t need = mine ? sm.wcursor[b] - f : 0u;
 		const uint32_t room = kBlkEntries - f;
 		const uint32_t nbj = need > room ? (need - room + kBlkEntries - 1) / kBlkEntries : 0u;
 		const uint32_t incl = warp_incl_scan(nbj, lane);
@@ -211,7 +234,6 @@ __device__ __noinline__ bool fused_drain(const FusedArgs& a, const WarpSmem& sm,
 				at = atomicAdd(P.slice_nblk + (a.ki * nb + b), nb_[j]); // slice_cap == n_blocks: the list cannot overflow before the pool
 			sm.wbase[b] = base_[j];
 			sm.wat[b] = at;
-			sm.wcursor[b] = f_[j];
 		}
 	}
 	__syncwarp();
@@ -219,8 +241,8 @@ __device__ __noinline__ bool fused_drain(const FusedArgs& a, const WarpSmem& sm,
 	for (uint32_t i = 0; i < maxcnt; i++) {
 		const uint32_t idx = sm.hq[i * 32u + lane];
 		if (idx != kVoid) {
-			const uint32_t b = idx >> P.bin_shift;
-			const uint32_t slot = atomicAdd(&sm.wcursor[b], 1u);
+			const uint32_t b = idx >> bin_shift;
+			const uint32_t slot = sm.queue[i * 32u + lane];
 			uint32_t blk, off;
 			if (slot < kBlkEntries) {
 				blk = sm.cur[b];
@@ -453,7 +475,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) fused_kernel(const __grid_con
 					uint32_t m[kScanBlock];
 					FusedBlock<KM, S, 0>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, m);
 					scan_rotate_home(st);
-					if (qb + kScanBlock > qlo) { // warp-uniform: some window of the block belongs to this round
+					if (qb + kScanBlock > qlo && !(a.dbg & 2u)) { // warp-uniform: some window of the block belongs to this round
 #pragma unroll
 						for (int u = 0; u < kScanBlock; u++) {
 							const int q = qb + u;
@@ -483,7 +505,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) fused_kernel(const __grid_con
 #pragma unroll
 			for (int d = 16; d > 0; d >>= 1)
 				p_end = min(p_end, __shfl_xor_sync(0xFFFFFFFFu, p_end, d));
-			const bool served = fused_drain<S>(a, sm, tab, tile, cnt, p_end, mixed, lane);
+			const bool served = (a.dbg & 1u) ? true : fused_drain(a, tile, cnt, p_end, mixed, lane, warp);
 			if (!served) {
 				exhausted = true;
 				if (lane == 0) {

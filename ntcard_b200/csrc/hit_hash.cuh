@@ -125,5 +125,120 @@ __device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& 
 	return ((t1 ? 1u : 0u) << c.rBits) | (hl & ((1u << c.rBits) - 1u));
 }
 
+// ---- block-wise full hash with 128-bit gathers (fused kernel) ---------------------------------------------------------------
+// k = tprime + 32 (nblk - 1), 1 <= tprime <= 32: the first tprime bases form the HEAD block, put through the byte tables with the
+// other 32 - tprime codes masked to 0 ('A'); what those A's contribute is a constant per k (head_c / head_d), and the head's hash
+// sits 32 - tprime rotations too far left:
+//   fh = sror^(32-tprime)( FB(head) ^ head_c ),  rh = RB(head) ^ head_d;   then per full block m = 1 .. nblk-1:
+//   fh = srol^32(fh) ^ FB_m,                      rh ^= srol^(tprime + 32 (m-1)) RB_m
+// (NTF64 / NTR64 base forms, nthash.hpp:220-239, regrouped; checked against them for k = 1 .. 287 on the host.)
+struct HashK {
+	uint32_t k, tprime, nblk;
+	uint32_t head_ra, head_rb;   // srol amounts (mod 31, mod 33) equal to sror^(32 - tprime)
+	uint64_t head_c, head_d;
+	uint64_t rot_a, rot_b;       // byte m-1: (tprime + 32 (m-1)) % 31 and % 33
+};
+
+inline HashK make_hashk(uint32_t k)
+{
+	HashK K;
+	K.k = k;
+	K.nblk = (k + 31) / 32;
+	K.tprime = k - 32 * (K.nblk - 1);
+	K.head_ra = (31 - (32 - K.tprime) % 31) % 31;
+	K.head_rb = (33 - (32 - K.tprime) % 33) % 33;
+	K.head_c = K.head_d = 0;
+	for (uint32_t i = K.tprime; i < 32; i++) {
+		K.head_c ^= srol_n(seed_of(0), 31 - i);
+		K.head_d ^= srol_n(seed_of(3), i);
+	}
+	K.rot_a = K.rot_b = 0;
+	for (uint32_t m = 1; m < K.nblk && m <= 8; m++) {
+		K.rot_a |= (uint64_t)((K.tprime + 32 * (m - 1)) % 31) << (8 * (m - 1));
+		K.rot_b |= (uint64_t)((K.tprime + 32 * (m - 1)) % 33) << (8 * (m - 1));
+	}
+	return K;
+}
+
+#if defined(__CUDACC__)
+struct HitLoadV { // the one or two 16-byte groups of a record that hold three consecutive packed words, in flight
+	uint4 g0, g1;
+};
+
+// rec: the record (16-byte aligned, ngroups uint4 long); w: index of the first of the three words inside the record (>= 1:
+// word 0 is the length).  One 128-bit load when the three words lie in one group, two otherwise -- against three 32-bit
+// loads, each its own L1 wavefront per lane.
+__device__ __forceinline__ HitLoadV hit_issue_v(const uint4* __restrict__ rec, uint32_t ngroups, uint32_t w)
+{
+	HitLoadV h;
+	const uint32_t g = w >> 2;
+	h.g0 = __ldg(rec + min(g, ngroups - 1u));
+	h.g1 = make_uint4(0u, 0u, 0u, 0u);
+	if ((w & 3u) >= 2u && g + 1u < ngroups)
+		h.g1 = __ldg(rec + g + 1u);
+	return h;
+}
+
+__device__ __forceinline__ HitLoad hit_select(const HitLoadV& h, uint32_t w)
+{
+	const bool odd = (w & 1u) != 0, hi = (w & 2u) != 0;
+	const uint32_t a0 = odd ? h.g0.y : h.g0.x, a1 = odd ? h.g0.z : h.g0.y, a2 = odd ? h.g0.w : h.g0.z, a3 = odd ? h.g1.x : h.g0.w,
+	               a4 = odd ? h.g1.y : h.g1.x;
+	HitLoad r;
+	r.x0 = hi ? a2 : a0;
+	r.x1 = hi ? a3 : a1;
+	r.x2 = hi ? a4 : a2;
+	return r;
+}
+
+// Canonical hash of the k-mer starting at base p of the record and ntComp (ntcard.cpp:132-145): the counter index inside the
+// k's [2][2^rBits] sub-sketch, or kVoid when ntComp does not sample it.  h0: hit_issue_v(rec, ngroups, 1 + (p >> 4)).
+__device__ __forceinline__ uint32_t hash_kmer_v(const HashK& K, const uint4* __restrict__ tab, uint32_t rBits, uint32_t S, const HitLoadV& h0,
+    const uint4* __restrict__ rec, uint32_t ngroups, uint32_t p)
+{
+	uint32_t hh, hl;
+	const uint32_t sh = (p & 15u) * 2u;
+	const HitLoad x = hit_select(h0, 1u + (p >> 4));
+	uint32_t w0 = __funnelshift_r(x.x0, x.x1, sh), w1 = __funnelshift_r(x.x1, x.x2, sh);
+	uint32_t f0, f1, r0, r1;
+	if (K.nblk == 1 && K.tprime == 32) { // k = 32: pure 32-bit path
+		block_tables(tab, w0, w1, f0, f1, r0, r1);
+		const bool rlt = r1 < f1 || (r1 == f1 && r0 < f0);
+		hh = rlt ? r1 : f1;
+		hl = rlt ? r0 : f0;
+	} else {
+		const uint32_t t = K.tprime;
+		if (t <= 16) {
+			w0 &= t == 16 ? 0xFFFFFFFFu : ((1u << (2u * t)) - 1u);
+			w1 = 0;
+		} else if (t < 32) {
+			w1 &= (1u << (2u * (t - 16u))) - 1u;
+		}
+		block_tables(tab, w0, w1, f0, f1, r0, r1);
+		uint64_t fh = (((uint64_t)f1 << 32) | f0) ^ K.head_c, rh = (((uint64_t)r1 << 32) | r0) ^ K.head_d;
+		if (t < 32)
+			fh = srol_ab(fh, K.head_ra, K.head_rb);
+		for (uint32_t m = 1; m < K.nblk; m++) {
+			const uint32_t o = p + t + 32u * (m - 1u), wm = 1u + (o >> 4), shm = (o & 15u) * 2u;
+			const HitLoadV hv = hit_issue_v(rec, ngroups, wm);
+			const HitLoad y = hit_select(hv, wm);
+			block_tables(tab, __funnelshift_r(y.x0, y.x1, shm), __funnelshift_r(y.x1, y.x2, shm), f0, f1, r0, r1);
+			const uint64_t FB = ((uint64_t)f1 << 32) | f0, RB = ((uint64_t)r1 << 32) | r0;
+			fh = srol_ab(fh, 1, 32) ^ FB;
+			const uint32_t ra = (uint32_t)(K.rot_a >> (8u * (m - 1u))) & 0xFFu, rb = (uint32_t)(K.rot_b >> (8u * (m - 1u))) & 0xFFu;
+			rh ^= (ra | rb) ? srol_ab(RB, ra, rb) : RB;
+		}
+		const uint64_t hm = rh < fh ? rh : fh;
+		hh = (uint32_t)(hm >> 32);
+		hl = (uint32_t)hm;
+	}
+	const bool t0 = (hh >> (31 - S)) == 1u;
+	const bool t1 = (hh >> (32 - S)) == ((1u << (S - 1)) - 1u);
+	if (!(t0 || t1))
+		return kVoid;
+	return ((t1 ? 1u : 0u) << rBits) | (hl & ((1u << rBits) - 1u));
+}
+#endif
+
 } // namespace pl
 } // namespace ntc

@@ -576,6 +576,105 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 	}
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU reduction over peer memory (NVLink): apply_owned_kernel
+// ------------------------------------------------------------------------------------------------
+// Rank r owns the sketch slices s with s % world == r.  Every rank's hit log (block lists + pool) is mapped into every
+// other rank's address space (CUDA IPC, ntc_peer_attach); this kernel zeroes the OWNED slices of the local sketch and
+// RED.ADDs into them the log entries of those slices from ALL ranks' logs -- the remote ones are read straight through
+// NVLink with coalesced 1 KB block loads, two blocks per warp in flight.  The fused compute + collective step of the
+// reduction: no staging buffers, no host planning, no NCCL on the data path (NCCL only carries the small all-reduces
+// around it, which also are the barriers: the status all-reduce before -- every log is complete -- and the histogram
+// all-reduce after -- every rank has finished reading its peers' pools).
+// status[status_idx] != 0 (device memory, all-reduced): some rank's log is incomplete -- do nothing (the host falls
+// back to the dense reduction once it has read the flag).
+__global__ void __launch_bounds__(kApplyThreads) apply_owned_kernel(const Pool P, const PeerLogs G, uint32_t* __restrict__ counters,
+    const uint32_t* __restrict__ order, uint32_t n_order, const long long* __restrict__ status, uint32_t status_idx)
+{
+	if (status && status[status_idx] != 0)
+		return;
+	const uint32_t kApplyAhead = P.ahead;
+	const uint32_t role = threadIdx.x / (kApplyThreads / 2), rtid = threadIdx.x % (kApplyThreads / 2), nrt = kApplyThreads / 2;
+	const size_t slice_len = (size_t)1 << P.bin_shift;
+	const size_t per_k = (size_t)2 << P.rBits;
+	if (role == 0) {
+		const size_t n16 = slice_len / 4;
+		const size_t a0 = n16 * blockIdx.x / gridDim.x, a1 = n16 * (blockIdx.x + 1) / gridDim.x;
+		for (uint32_t si = 0; si < n_order; si++) {
+			const uint32_t s = order[si];
+			if (si >= kApplyAhead) {
+				if (rtid == 0)
+					while (ld_acquire(P.apply_done + si - kApplyAhead) < gridDim.x)
+						__nanosleep(20);
+				role_sync(role);
+			}
+			uint4* p = reinterpret_cast<uint4*>(counters + (size_t)(s / P.nbins) * per_k + (size_t)(s % P.nbins) * slice_len);
+			for (size_t i = a0 + rtid; i < a1; i += nrt)
+				p[i] = make_uint4(0u, 0u, 0u, 0u);
+			role_sync(role);
+			if (rtid == 0) {
+				__threadfence();
+				atomicAdd(P.zero_done + si, 1u);
+			}
+		}
+	} else {
+		const uint32_t lane = rtid & 31u, warp = rtid >> 5, nwarp = nrt / 32;
+		constexpr int kV = kBlkEntries / 32;
+		const uint32_t j0 = blockIdx.x * nwarp + warp, jstep = gridDim.x * nwarp;
+		for (uint32_t si = 0; si < n_order; si++) {
+			const uint32_t s = order[si];
+			if (rtid == 0)
+				while (ld_acquire(P.zero_done + si) < gridDim.x)
+					__nanosleep(20);
+			role_sync(role);
+			uint32_t* ctr = counters + (size_t)(s / P.nbins) * per_k;
+			for (uint32_t q = 0; q < G.n; q++) {
+				const uint32_t nbq = min(__ldcg(G.slice_nblk[q] + s), P.slice_cap);
+				const uint32_t* list = G.slice_blocks[q] + (size_t)s * P.slice_cap;
+				const uint32_t* ent = G.entries[q];
+				for (uint32_t j = j0; j < nbq; j += 2 * jstep) { // two blocks in flight per warp (remote latency)
+					const uint32_t ja = j, jb = j + jstep;
+					const uint32_t la = __ldcg(list + ja), lb = jb < nbq ? __ldcg(list + jb) : kVoid;
+					const uint32_t fa = la == kVoid ? 0u : min(la & 511u, kBlkEntries), fb = lb == kVoid ? 0u : min(lb & 511u, kBlkEntries);
+					const uint32_t* ea = ent + (size_t)(la >> 9) * kBlkEntries;
+					const uint32_t* eb = ent + (size_t)(lb >> 9) * kBlkEntries;
+					uint32_t va[kV], vb[kV];
+#pragma unroll
+					for (int u = 0; u < kV; u++)
+						va[u] = lane + 32u * u < fa ? __ldcg(ea + lane + 32u * u) : kVoid;
+#pragma unroll
+					for (int u = 0; u < kV; u++)
+						vb[u] = lane + 32u * u < fb ? __ldcg(eb + lane + 32u * u) : kVoid;
+#pragma unroll
+					for (int u = 0; u < kV; u++)
+						if (va[u] != kVoid)
+							atomicAdd(ctr + va[u], 1u);
+#pragma unroll
+					for (int u = 0; u < kV; u++)
+						if (vb[u] != kVoid)
+							atomicAdd(ctr + vb[u], 1u);
+				}
+			}
+			role_sync(role);
+			if (rtid == 0)
+				atomicAdd(P.apply_done + si, 1u);
+		}
+	}
+	// the pool is NOT reset here: peers may still be reading it (ntc_reset does, after the histogram all-reduce)
+}
+
+// F1 per k and "my log is not complete" as int64, ready for one all-reduce (sum)
+__global__ void log_status_kernel(const Pool P, const unsigned long long* __restrict__ f1, uint32_t nK, int host_ok, long long* __restrict__ out)
+{
+	if (threadIdx.x < nK)
+		out[threadIdx.x] = (long long)f1[threadIdx.x];
+	if (threadIdx.x == 0) {
+		const bool ok = host_ok && P.ctl[CTL_STATE] == 0 && P.ctl[CTL_DIRECT] == 0 && P.ctl[CTL_NEXT] <= P.n_blocks && P.ctl[CTL_NDEFER] == 0;
+		out[nK] = ok ? 0 : 1;
+	}
+}
+
 } // namespace
 
 constexpr int kStagedGroups = 3, kPlainGroups = 2;
@@ -798,6 +897,21 @@ cudaError_t launch_hist_slices(const Pool& pool, const uint32_t* counters, const
 	if (chunk > ((uint64_t)1 << pool.rBits))
 		return cudaErrorInvalidValue;
 	hist_slices_kernel<<<(unsigned)(n_order * (slice_len / chunk)), 256, 0, st>>>(counters, d_order, pool.bin_shift, pool.nbins, pool.rBits, d_phist);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_apply_owned(const Pool& pool, const PeerLogs& logs, uint32_t* counters, const uint32_t* d_order, uint32_t n_order,
+    const long long* d_status, uint32_t status_idx, unsigned grid, cudaStream_t st)
+{
+	Pool p = pool;
+	PeerLogs g = logs;
+	void* args[] = { &p, &g, &counters, &d_order, &n_order, &d_status, &status_idx };
+	return cudaLaunchCooperativeKernel((const void*)apply_owned_kernel, dim3(grid), dim3(kApplyThreads), args, 0, st);
+}
+
+cudaError_t launch_log_status(const Pool& pool, const unsigned long long* d_f1, uint32_t nK, int host_ok, long long* d_out, cudaStream_t st)
+{
+	log_status_kernel<<<1, 32, 0, st>>>(pool, d_f1, nK, host_ok, d_out);
 	return cudaGetLastError();
 }
 

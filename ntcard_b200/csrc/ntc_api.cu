@@ -13,6 +13,7 @@
 
 #include "../../include/ntcard_b200.h"
 #include "bitslice_core.cuh"
+#include "hit_hash.cuh"
 #include "internal.h"
 #include "launch.h"
 #include "pipeline.h"
@@ -111,15 +112,22 @@ struct ntc_ctx {
 	uint64_t n_padded = 0;             // ragged batches of short records padded to a uniform stride for the pipeline
 	// sketch pipeline (scan -> hit log -> apply), pipeline.h
 	ntc::pl::Pool pool{};
-	uint32_t* d_pool_ctl_region = nullptr; // ctl + slice_nblk + zero_done + apply_done + cand, one allocation (zeroed by reset)
+	uint32_t* d_pool_ctl_region = nullptr; // ctl + slice_nblk + zero_done + apply_done + cand (zeroed by reset); the head of d_log_slab
 	size_t pool_ctl_bytes = 0;
+	uint32_t* d_log_slab = nullptr;        // one allocation (one IPC handle): [control region, padded to 4 KB][slice_blocks]
+	size_t log_slab_ctl_words = 0;         // words of the padded control region = offset of slice_blocks in the slab
+	// multi-GPU reduction over peer memory (ntc_peer_attach): the logs of all ranks of the node
+	ntc::pl::PeerLogs peers{};
+	int peer_world = 0, peer_rank = 0;
+	void* peer_mapped[2 * ntc::pl::kMaxPeers] = {}; // cudaIpcOpenMemHandle results (to close)
 	uint32_t* d_masks = nullptr;
 	size_t cap_masks = 0;
 	uint32_t* d_tile_info = nullptr;
 	size_t cap_tile_info = 0;
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
-	bool use_fused = true;     // the fused sketch kernel (fused_kernel.cuh); NTC_FUSED=0: scan + hit kernels (round-1 pipeline, kept for comparison)
+	bool use_fused = false;    // NTC_FUSED=1: the fused sketch kernel (fused_kernel.cuh) instead of scan + hit; exact, but measured slower
+	unsigned fused_dbg = 0;    // NTC_FUSED_DBG: timing experiments (fused_kernel.cuh), results are wrong when set
 	bool no_stage = false;     // NTC_NO_STAGE=1 (stand-alone hit kernel: gather with __ldg instead of a TMA-staged tile)
 	bool no_retile = false;    // NTC_NO_RETILE=1
 	bool clear_by_memset = true;
@@ -259,11 +267,14 @@ int pool_create(ntc_ctx* c)
 	// "out of space" event is pool exhaustion, which both hit paths handle exactly (deferred tiles / conditional flush)
 	P.slice_cap = P.n_blocks;
 	CK(cudaMalloc((void**)&P.entries, (size_t)P.n_blocks * ntc::pl::kBlkEntries * sizeof(uint32_t)));
-	CK(cudaMalloc((void**)&P.slice_blocks, (size_t)P.n_slices * P.slice_cap * sizeof(uint32_t)));
-	// control region: [ctl CTL_WORDS][slice_nblk n_slices][zero_done n_slices][apply_done n_slices][pad][cand 2 words]
+	// control region: [ctl CTL_WORDS][slice_nblk n_slices][zero_done n_slices][apply_done n_slices][pad][cand 2 words], padded to
+	// 4 KB, then the block lists -- ONE allocation, so that one IPC handle maps everything a peer needs besides the pool
 	const size_t words = ntc::pl::CTL_WORDS + 3 * (size_t)P.n_slices + 4;
 	c->pool_ctl_bytes = words * sizeof(uint32_t);
-	CK(cudaMalloc((void**)&c->d_pool_ctl_region, c->pool_ctl_bytes));
+	c->log_slab_ctl_words = (words + 1023) & ~(size_t)1023;
+	CK(cudaMalloc((void**)&c->d_log_slab, (c->log_slab_ctl_words + (size_t)P.n_slices * P.slice_cap) * sizeof(uint32_t)));
+	c->d_pool_ctl_region = c->d_log_slab;
+	P.slice_blocks = c->d_log_slab + c->log_slab_ctl_words;
 	P.ctl = c->d_pool_ctl_region;
 	P.slice_nblk = P.ctl + ntc::pl::CTL_WORDS;
 	P.zero_done = P.slice_nblk + P.n_slices;
@@ -469,11 +480,23 @@ int run_fused_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const Pipe
 	memcpy(fa.L.F0, c->kinit[ki].F0, sizeof fa.L.F0);
 	memcpy(fa.L.R0, c->kinit[ki].R0, sizeof fa.L.R0);
 	fa.ki = ki;
+	fa.sBits = c->sBits;
 	fa.pass = 0;
 	fa.qlane = sh.qlane;
+	fa.dbg = c->fused_dbg;
 	fa.d_tab = c->d_bs_tab;
-	fa.rot_a = c->kinit[ki].rot_a;
-	fa.rot_b = c->kinit[ki].rot_b;
+	{
+		const ntc::pl::HashK hk = ntc::pl::make_hashk(c->k[ki]);
+		fa.hk_k = hk.k;
+		fa.hk_tprime = hk.tprime;
+		fa.hk_nblk = hk.nblk;
+		fa.hk_head_ra = hk.head_ra;
+		fa.hk_head_rb = hk.head_rb;
+		fa.hk_head_c = hk.head_c;
+		fa.hk_head_d = hk.head_d;
+		fa.hk_rot_a = hk.rot_a;
+		fa.hk_rot_b = hk.rot_b;
+	}
 	fa.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 	fa.pool = P;
 	fa.tile_info = c->d_tile_info;
@@ -950,8 +973,10 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 		}
 	}
 	c->use_pipeline = !(getenv("NTC_PIPELINE") && atoi(getenv("NTC_PIPELINE")) == 0);
-	c->use_fused = !(getenv("NTC_FUSED") && atoi(getenv("NTC_FUSED")) == 0);
+	c->use_fused = getenv("NTC_FUSED") && atoi(getenv("NTC_FUSED")) != 0;
 	c->no_stage = getenv("NTC_NO_STAGE") != nullptr;
+	if (getenv("NTC_FUSED_DBG"))
+		c->fused_dbg = (unsigned)atoi(getenv("NTC_FUSED_DBG"));
 	c->no_retile = getenv("NTC_NO_RETILE") != nullptr;
 	// two 8-byte cudaMemsetAsync per batch (default) or one 1-thread kernel (NTC_CLEAR_MEMSET=0): measured, the kernel variant makes the host
 	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
@@ -1035,9 +1060,10 @@ void ntc_destroy(ntc_ctx* c)
 	if (c->d_params) cudaFree(c->d_params);
 	if (c->d_bs_tab) cudaFree(c->d_bs_tab);
 	if (c->pool.entries) cudaFree(c->pool.entries);
-	if (c->pool.slice_blocks) cudaFree(c->pool.slice_blocks);
+	for (void* m : c->peer_mapped)
+		if (m) cudaIpcCloseMemHandle(m);
+	if (c->d_log_slab) cudaFree(c->d_log_slab);
 	if (c->pool.gstate) cudaFree(c->pool.gstate);
-	if (c->d_pool_ctl_region) cudaFree(c->d_pool_ctl_region);
 	if (c->d_masks) cudaFree(c->d_masks);
 	for (auto& rs : c->run_slot) {
 		if (rs.h) cudaFreeHost(rs.h);
@@ -1372,6 +1398,118 @@ int ntc_log_import(ntc_ctx* c, const void* d_blocks, uint32_t n_blocks, const ui
 	c->log_used += n_blocks;
 	c->n_launches++;
 	c->pending = true;
+	return NTC_OK;
+}
+
+/* ---- multi-GPU reduction over peer memory (one process per GPU, one node) ------------------------------------------ */
+int ntc_peer_export(ntc_ctx* c, void* handles)
+{
+	if (!c || !handles)
+		return set_err(NTC_EINVAL, "ntc_peer_export: bad argument");
+	SKETCH_ONLY(c, "ntc_peer_export");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	cudaIpcMemHandle_t h[2];
+	CK(cudaIpcGetMemHandle(&h[0], c->pool.entries));
+	CK(cudaIpcGetMemHandle(&h[1], c->d_log_slab));
+	static_assert(sizeof(cudaIpcMemHandle_t) == NTC_PEER_HANDLE_BYTES / 2, "CUDA IPC handle size");
+	memcpy(handles, h, sizeof h);
+	return NTC_OK;
+}
+
+int ntc_peer_attach(ntc_ctx* c, int world, int rank, const void* all_handles)
+{
+	if (!c || !all_handles || world < 1 || world > (int)ntc::pl::kMaxPeers || rank < 0 || rank >= world)
+		return set_err(NTC_EINVAL, "ntc_peer_attach: bad argument (world 1..%u)", ntc::pl::kMaxPeers);
+	SKETCH_ONLY(c, "ntc_peer_attach");
+	if (c->peer_world)
+		return set_err(NTC_ESTATE, "ntc_peer_attach: already attached");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	const ntc::pl::Pool& P = c->pool;
+	for (int q = 0; q < world; q++) {
+		const uint32_t *ent, *slab;
+		if (q == rank) {
+			ent = P.entries;
+			slab = c->d_log_slab;
+		} else {
+			cudaIpcMemHandle_t h[2];
+			memcpy(h, (const char*)all_handles + (size_t)q * NTC_PEER_HANDLE_BYTES, sizeof h);
+			void *m0 = nullptr, *m1 = nullptr;
+			CK(cudaIpcOpenMemHandle(&m0, h[0], cudaIpcMemLazyEnablePeerAccess));
+			c->peer_mapped[2 * q] = m0;
+			CK(cudaIpcOpenMemHandle(&m1, h[1], cudaIpcMemLazyEnablePeerAccess));
+			c->peer_mapped[2 * q + 1] = m1;
+			ent = (const uint32_t*)m0;
+			slab = (const uint32_t*)m1;
+		}
+		c->peers.entries[q] = ent;
+		c->peers.slice_blocks[q] = slab + c->log_slab_ctl_words;
+		c->peers.slice_nblk[q] = slab + ntc::pl::CTL_WORDS;
+	}
+	c->peers.n = (uint32_t)world;
+	c->peer_world = world;
+	c->peer_rank = rank;
+	return NTC_OK;
+}
+
+int ntc_log_status_device(ntc_ctx* c, void* d_status)
+{
+	if (!c || !d_status)
+		return set_err(NTC_EINVAL, "ntc_log_status_device: bad argument");
+	SKETCH_ONLY(c, "ntc_log_status_device");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	CK(ntc::pl::launch_log_status(c->pool, c->d_f1, c->nK, (c->pending && !c->partial) ? 1 : 0, (long long*)d_status, c->stream));
+	c->n_launches++;
+	return NTC_OK;
+}
+
+int ntc_reduce_owned(ntc_ctx* c, const void* d_status, void* d_p_hist)
+{
+	if (!c || !d_p_hist)
+		return set_err(NTC_EINVAL, "ntc_reduce_owned: bad argument");
+	SKETCH_ONLY(c, "ntc_reduce_owned");
+	if (!c->peer_world)
+		return set_err(NTC_ESTATE, "ntc_reduce_owned: ntc_peer_attach first");
+	if (c->partial)
+		return set_err(NTC_ESTATE, "ntc_reduce_owned: the sketch was already flushed partially; ntc_reset first");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	const ntc::pl::Pool& P = c->pool;
+	std::vector<uint32_t> order;
+	for (uint32_t s = 0; s < P.n_slices; s++)
+		if ((int)(s % (uint32_t)c->peer_world) == c->peer_rank)
+			order.push_back(s);
+	const uint32_t n = (uint32_t)order.size();
+	order.push_back(0);
+	const uint32_t* d_order = nullptr;
+	if ((rc = upload_runs(c, order, &d_order)))
+		return rc;
+	const size_t hist_bytes = (size_t)c->nK * NTC_NSAMP * 65536 * sizeof(uint32_t);
+	cudaEvent_t e0, e1;
+	if ((rc = get_event(c, &e0)) || (rc = get_event(c, &e1)))
+		return rc;
+	CK(cudaEventRecord(e0, c->stream));
+	if ((rc = stage_begin(c, 2)))
+		return rc;
+	CK(cudaMemsetAsync(d_p_hist, 0, hist_bytes, c->stream));
+	CK(ntc::pl::launch_apply_owned(P, c->peers, c->d_counters, d_order, n, (const long long*)d_status, c->nK, c->apply_grid, c->stream));
+	cudaError_t e = ntc::pl::launch_hist_slices(P, c->d_counters, d_order, n, (uint32_t*)d_p_hist, c->stream);
+	if (e == cudaErrorInvalidValue)
+		return set_err(NTC_EINVAL, "ntc_reduce_owned: rBits too small for the histogram chunk");
+	CK(e);
+	if ((rc = stage_end(c)))
+		return rc;
+	CK(cudaEventRecord(e1, c->stream));
+	c->timing.emplace_back(e0, e1);
+	c->n_launches += 2;
+	c->pending = false;
+	c->partial = true;
 	return NTC_OK;
 }
 

@@ -55,6 +55,14 @@ struct Pool {                    // device pointers + geometry, passed by value
 	uint32_t ahead;              // apply kernel: slices the stagers may run ahead of the appliers (L2 footprint)
 };
 
+constexpr uint32_t kMaxPeers = 8;
+struct PeerLogs {                // the hit logs of all ranks of one node, mapped through CUDA IPC (this rank's own included)
+	const uint32_t* entries[kMaxPeers];
+	const uint32_t* slice_blocks[kMaxPeers];
+	const uint32_t* slice_nblk[kMaxPeers];
+	uint32_t n;
+};
+
 struct ScanLaunch {              // per-k constants of the scan kernel, passed by value
 	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (k + 16 rounded up to a multiple of 16)
 	uint32_t npos_max;           // mask rows per tile
@@ -82,10 +90,12 @@ struct FusedArgs {               // the fused sketch kernel (fused_kernel.cuh): 
 	const uint32_t* words;
 	uint32_t stride, n_rec, n_tiles;
 	ScanLaunch L;                // ring here also sizes the per-warp index buffer that aliases the planes
-	uint32_t ki, pass;           // pass 0: every tile (counts F1); pass 1: only the tiles pass 0 deferred
+	uint32_t ki, sBits, pass;    // pass 0: every tile (counts F1); pass 1: only the tiles pass 0 deferred
 	uint32_t qlane;              // candidate slots per lane of a warp's queue (<= 2 * (ring + 3))
+	uint32_t dbg;                // timing experiments only (NTC_FUSED_DBG): 1 = skip the hash + append phase, 2 = skip the emission (results are wrong)
 	const uint4* d_tab;          // [8][256] byte tables of the full hash
-	uint64_t rot_a, rot_b;
+	uint32_t hk_k, hk_tprime, hk_nblk, hk_head_ra, hk_head_rb; // HashK of this k (hit_hash.cuh make_hashk), flattened
+	uint64_t hk_head_c, hk_head_d, hk_rot_a, hk_rot_b;
 	uint32_t* ctr_k;             // counters of this k (direct increments once the sketch is materialised and the pool is full)
 	Pool pool;
 	uint32_t* tile_info;         // [n_tiles]: 0 done, kTileFlag -> fallback kernel, kTileDefer | p -> second pass
@@ -134,6 +144,10 @@ cudaError_t launch_import(const Pool& pool, const uint32_t* d_runs, uint32_t n_r
     cudaStream_t st);
 cudaError_t launch_hist_slices(const Pool& pool, const uint32_t* counters, const uint32_t* d_order, uint32_t n_order, uint32_t* d_phist, cudaStream_t st);
 int apply_max_grid(int n_sm);
+// Multi-GPU reduction over peer memory: zero the owned slices and apply to them the log entries of ALL ranks (hit_kernels.cu).
+cudaError_t launch_apply_owned(const Pool& pool, const PeerLogs& logs, uint32_t* counters, const uint32_t* d_order, uint32_t n_order,
+    const long long* d_status, uint32_t status_idx, unsigned grid, cudaStream_t st);
+cudaError_t launch_log_status(const Pool& pool, const unsigned long long* d_f1, uint32_t nK, int host_ok, long long* d_out, cudaStream_t st);
 
 } // namespace pl
 } // namespace ntc
