@@ -42,6 +42,16 @@ METRIC = "k-mers hashed/sec at k=32 on 150bp reads"
 UNIT = "k-mers/s"
 
 
+def make_config(args, world, desc, n_reads, L, kList, sBits):
+    """The same dictionary in both arms (the driver compares them key by key)."""
+    return {"workload": desc, "reads_per_gpu": n_reads, "read_len": L, "k": kList, "sBits": sBits, "rBits": RBITS,
+            "kernel": args.kernel, "launches_per_step": max(1, args.batches),
+            "sharding": f"reads split over {world} GPU(s), no data-path collective; one reduction at the end over NVLink peer memory "
+                        "(each rank applies every rank's hit-log entries of the sketch slices it owns) + all-reduce of F1 and of the "
+                        "counter-value histogram; dense reduce-scatter fallback",
+            "l2": "no flush needed: per-step inputs (480 MB packed reads + 1 GiB sketch per k) exceed the 126 MB L2"}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -144,8 +154,8 @@ def reference_main(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": desc, "k": kList, "sBits": sBits, "rBits": RBITS, "read_len": L,
-                      "note": "CPU arm: rank 0 only, bounded sample per step"},
+           "config": make_config(args, world, desc, n_reads, L, kList, sBits),
+           "note": "CPU arm: rank 0 only, bounded sample of the workload per step (cpu_baseline.sample)",
            "cpu_baseline": dict(info, value=v, unit=UNIT),
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -154,7 +164,7 @@ def reference_main(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
@@ -177,7 +187,7 @@ def main():
     import torch.distributed as dist
 
     import ntcard_b200 as nt
-    from ntcard_b200.dist import all_reduce_sketch, exchange_hist, reduce_scatter_hist
+    from ntcard_b200.dist import PeerReducer, all_reduce_sketch, reduce_scatter_hist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
@@ -211,29 +221,35 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
-        reduce_kind = {"exchange": 0, "dense": 0}
+        reduce_kind = {"peer": 0, "dense": 0}
+        reducer = PeerReducer(sk, dev) if world > 1 else None
 
-        def reduce_sketch():
-            """N > 1: the one reduction at the end.  compEst needs only the counter-value histogram.  Cheap path
-            (ntcard_b200.dist.exchange_hist): the ranks swap the blocks of their hit logs so that every rank holds
-            all increments of the sketch slices it owns (74 MB of log per 10 M reads instead of 1 GiB of counters),
-            materialises + histograms only those slices, and the 512 KiB/k histograms are all-reduced.  Fallback
-            when a log is no longer complete: reduce-scatter of the uint32 counters + per-rank histogram.
-            F1 is all-reduced alongside.  Returns the global histogram (None at N = 1)."""
-            if world > 1:
-                tots = []
-                p = exchange_hist(sk, RBITS, dev, totals_out=tots)
-                reduce_kind["exchange" if p is not None else "dense"] += 1
-                if p is not None:
-                    sk.set_totals(tots[0])
-                else:
-                    tot = sk.totals()
-                    tt = torch.from_numpy(tot.astype(np.int64)).to(dev)
-                    dist.all_reduce(tt)
-                    sk.set_totals(tt.cpu().numpy().astype(np.uint64))
-                    p = reduce_scatter_hist(sk, counters, RBITS)
-                return p
-            return None
+        def dense_reduce():
+            """Fallback when some rank's hit log is no longer complete: reduce-scatter of the uint32 counters, histogram of
+            the summed slice, all-reduce of the histograms (and of F1)."""
+            tot = sk.totals()
+            tt = torch.from_numpy(tot.astype(np.int64)).to(dev)
+            dist.all_reduce(tt)
+            sk.set_totals(tt.cpu().numpy().astype(np.uint64))
+            return reduce_scatter_hist(sk, counters, RBITS)
+
+        def reduce_sketch(fetch):
+            """N > 1: the one reduction at the end (ntcard_b200.dist.PeerReducer): every rank owns 1/N of the sketch slices,
+            pulls the other ranks' hit-log blocks of those slices through NVLink peer memory inside the apply kernel,
+            histograms its slices; two small all-reduces (F1 + completeness flag before, the 512 KiB/k histogram after) are the
+            only collectives and the only barriers.  No host synchronisation unless fetch: then the global histogram and F1
+            are read back (and the dense fallback runs if a log was incomplete)."""
+            reducer.reduce()
+            if not fetch:
+                reduce_kind["peer"] += 1
+                return None
+            p, f1 = reducer.result(RBITS)
+            if p is None:
+                reduce_kind["dense"] += 1
+                return dense_reduce()
+            reduce_kind["peer"] += 1
+            sk.set_totals(f1)
+            return p
 
         nb = max(1, args.batches)
         per = (n_reads + nb - 1) // nb
@@ -247,7 +263,7 @@ def main():
             if world == 1:
                 sk.flush()  # apply the hit log to the counters in HBM: the step ends with a complete sketch
             else:
-                reduce_sketch()  # ends with the global counter-value histogram on every rank
+                reduce_sketch(False)  # ends with the global counter-value histogram (and F1) on every rank's device
 
         def timed(fn, steps):
             barrier()
@@ -294,8 +310,23 @@ def main():
             clk["window"] = "warm-up + timed steps + 1.2 s of untimed repeats of the same step (the timed region alone is shorter than nvidia-smi's 100 ms sampling period)"
         ms_per_step = ms_total / args.steps
         value = world * kmers_rank / (ms_per_step * 1e-3)
-        tot = sk.totals()
-        assert int(tot.sum()) == kmers_rank * (world if world > 1 else 1), (tot, kmers_rank)
+        parity_check = None
+        if world == 1:
+            tot = sk.totals()
+            assert int(tot.sum()) == kmers_rank, (tot, kmers_rank)
+        else:
+            # untimed: the peer-memory reduction of one more step against the dense path (all-reduce of the uint32 counters,
+            # histogram of the whole table) on the same reads -- the result must be identical, bin by bin
+            step_resident()
+            p_peer, f1 = reducer.result(RBITS)
+            assert int(f1.sum()) == kmers_rank * world, (f1, kmers_rank, world)
+            sk.reset()
+            sk.submit_device(d_words.data_ptr(), n_reads * stride, n_reads, stride)
+            p_dense = dense_reduce()
+            same = 1 if (p_peer is not None and np.array_equal(p_peer, p_dense)) else 0
+            flag = torch.tensor([same], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity_check = bool(flag.item())
 
         # ---- e2e leg: host buffers through the C-ABI ------------------------------------------------
         e2e = None
@@ -321,10 +352,10 @@ def main():
                     r0 = c * cper
                     r1 = min(n_reads, r0 + cper)
                     sk.submit(pinned.array[r0 * estride:r1 * estride], None, r1 - r0, estride)
-                p = reduce_sketch()
                 if world == 1:
                     _, f1, p = sk.finish(counters=False, hist=True)
                 else:
+                    p = reduce_sketch(True)
                     f1 = sk.totals()
                 if rank == 0:
                     result["F1"] = f1
@@ -333,7 +364,7 @@ def main():
 
             for _ in range(2):
                 step_e2e()
-            esteps = max(3, min(args.steps, 10))
+            esteps = max(3, min(args.steps, 30))
             ems, _, _ = timed(step_e2e, esteps)
             e2e = {"value": world * kmers_rank / (ems / esteps * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": int(e_words * 4), "d2h_bytes_per_step": int(nK * 2 * 65536 * 4 + 8 * nK),
@@ -392,14 +423,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": desc, "reads_per_gpu": n_reads, "read_len": L, "k": kList, "sBits": sBits, "rBits": RBITS,
-                       "kernel": args.kernel, "launches_per_step": nb, "sharding": f"reads split over {world} GPU(s), no data-path collective; one reduction at the end: all-to-all of hit-log blocks to slice owners + all-reduce of the counter-value histogram and F1 (dense reduce-scatter fallback); reductions taken: {reduce_kind}",
-                       "l2": "no flush needed: per-step inputs (480 MB packed reads + 1 GiB sketch per k) exceed the 126 MB L2"},
+            "config": make_config(args, world, desc, n_reads, L, kList, sBits),
+            "reductions": reduce_kind, "parity_check": parity_check,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "scan_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": per_launch_bytes,
                          "kernel_kmers_per_s": kmers_rank / (kernel_ms * 1e-3),
-                         "stages_ms": dict(zip(names, stage_ms)), "longest_stage": names[dom],
+                         "stages_ms": dict(zip(names, stage_ms)), "scan_ms": stage_ms[0], "hit_ms": stage_ms[1], "apply_ms": stage_ms[2],
+                         "longest_stage": names[dom],
                          "pipeline_ms": pipeline_ms, "pipeline_achieved": per_launch_bytes / (pipeline_ms * 1e-3) / 1e9,
                          "pipeline_frac": per_launch_bytes / (pipeline_ms * 1e-3) / 1e9 / peak, **extra,
                          "note": "algorithmic bytes = sum(4 + ceil(len/4)) per record, read once per step by the scan kernel "
@@ -407,7 +438,7 @@ def main():
                                  "bytes over scan + hit + apply (everything between reset and a complete sketch)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
-        if world == 1 and not args.no_cpu:
+        if not args.no_cpu:  # rank 0 only; at N > 1 the other ranks wait in the final barrier
             try:
                 step, info = cpu_arm(args, n_reads, L, kList, sBits, bounded_seconds=args.cpu_seconds)
                 km, dt = step()

@@ -158,6 +158,8 @@ int ntc_flush_slices(ntc_ctx* ctx, const uint8_t* owned /* [n_slices] */);
 #define NTC_PEER_HANDLE_BYTES 128
 int ntc_peer_export(ntc_ctx* ctx, void* handles /* NTC_PEER_HANDLE_BYTES */);
 int ntc_peer_attach(ntc_ctx* ctx, int world, int rank, const void* all_handles /* world x NTC_PEER_HANDLE_BYTES, by rank */);
+/* the same for contexts of ONE process (several GPUs driven by one host program, or tests): all[rank] == ctx */
+int ntc_peer_attach_contexts(ntc_ctx* ctx, int world, int rank, ntc_ctx* const* all);
 int ntc_log_status_device(ntc_ctx* ctx, void* d_status /* int64 [nK + 1], device */);
 int ntc_reduce_owned(ntc_ctx* ctx, const void* d_status, void* d_p_hist);
 int ntc_stream_sync(ntc_ctx* ctx); /* wait for the context's stream WITHOUT flushing (before handing exported buffers to a collective) */

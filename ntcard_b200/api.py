@@ -25,7 +25,9 @@ SYMBOLS = [
     "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_stage_times", "ntc_device_count",
     "ntc_last_error", "ntc_version",
     "ntc_hll_create", "ntc_hll_registers_device", "ntc_hll_finish", "ntc_hll_estimate", "ntc_check_offsets",
+    "ntc_peer_export", "ntc_peer_attach", "ntc_peer_attach_contexts", "ntc_log_status_device", "ntc_reduce_owned",
 ]
+PEER_HANDLE_BYTES = 128
 
 
 class NtcError(RuntimeError):
@@ -87,6 +89,11 @@ def _load():
         "ntc_hll_finish": (C.c_int, [vp, vp, u64p]),
         "ntc_hll_estimate": (C.c_int, [vp, C.c_uint, C.c_int, dblp]),
         "ntc_check_offsets": (C.c_int, [vp, C.c_size_t, C.c_size_t, u32p]),
+        "ntc_peer_export": (C.c_int, [vp, vp]),
+        "ntc_peer_attach": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "ntc_peer_attach_contexts": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "ntc_log_status_device": (C.c_int, [vp, vp]),
+        "ntc_reduce_owned": (C.c_int, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -319,6 +326,34 @@ class Sketch:
         p = np.zeros((self.nK, 2, 65536), dtype=np.uint32)
         _check(lib.ntc_hist_slices(self.h, o.ctypes.data, p.ctypes.data, None))
         return p
+
+    # ---- multi-GPU reduction over peer memory (include/ntcard_b200.h) ----
+    def peer_export(self):
+        """IPC handles of this context's hit log (bytes, PEER_HANDLE_BYTES long) for the other ranks of the node."""
+        buf = np.zeros(PEER_HANDLE_BYTES, dtype=np.uint8)
+        _check(lib.ntc_peer_export(self.h, buf.ctypes.data))
+        return buf
+
+    def peer_attach(self, world, rank, all_handles):
+        """Map the hit logs of all ranks (all_handles: uint8 [world, PEER_HANDLE_BYTES], row r = rank r's peer_export())."""
+        hs = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(world, PEER_HANDLE_BYTES)
+        _check(lib.ntc_peer_attach(self.h, world, rank, hs.ctypes.data))
+        self.peer_world, self.peer_rank = world, rank
+
+    def peer_attach_contexts(self, rank, sketches):
+        """The same for Sketch objects of this process (sketches[rank] is self)."""
+        arr = (C.c_void_p * len(sketches))(*[x.h for x in sketches])
+        _check(lib.ntc_peer_attach_contexts(self.h, len(sketches), rank, arr))
+        self.peer_world, self.peer_rank = len(sketches), rank
+
+    def log_status_device(self, d_status):
+        """d_status (device pointer, int64 [nK + 1]) := F1 per k, 1 if this rank's log is incomplete (stream ordered)."""
+        _check(lib.ntc_log_status_device(self.h, d_status))
+
+    def reduce_owned(self, d_status, d_p_hist):
+        """Apply every rank's log entries of the slices this rank owns, histogram them into d_p_hist (device, uint32
+        [nK, 2, 65536], values >= 1); stream ordered, no host synchronisation.  d_status: the all-reduced status."""
+        _check(lib.ntc_reduce_owned(self.h, d_status, d_p_hist))
 
     def counters_device(self):
         p, n = C.c_void_p(), C.c_size_t()

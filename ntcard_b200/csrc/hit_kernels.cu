@@ -746,9 +746,13 @@ cudaError_t launch_fallback(const uint32_t* words, uint32_t stride, uint32_t n_r
 
 int apply_max_grid(int n_sm)
 {
-	int occ = 0;
+	// one grid size for both cooperative kernels (every CTA must be resident: their roles wait for each other)
+	int occ = 0, occ2 = 0;
 	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel, (int)kApplyThreads, 0) != cudaSuccess || occ < 1)
 		occ = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, apply_owned_kernel, (int)kApplyThreads, 0) != cudaSuccess || occ2 < 1)
+		occ2 = 1;
+	occ = occ < occ2 ? occ : occ2;
 	return n_sm * (occ > 2 ? 2 : occ);
 }
 

@@ -1455,6 +1455,40 @@ int ntc_peer_attach(ntc_ctx* c, int world, int rank, const void* all_handles)
 	return NTC_OK;
 }
 
+int ntc_peer_attach_contexts(ntc_ctx* c, int world, int rank, ntc_ctx* const* all)
+{
+	if (!c || !all || world < 1 || world > (int)ntc::pl::kMaxPeers || rank < 0 || rank >= world || all[rank] != c)
+		return set_err(NTC_EINVAL, "ntc_peer_attach_contexts: bad argument (world 1..%u, all[rank] must be the context itself)", ntc::pl::kMaxPeers);
+	SKETCH_ONLY(c, "ntc_peer_attach_contexts");
+	if (c->peer_world)
+		return set_err(NTC_ESTATE, "ntc_peer_attach_contexts: already attached");
+	int rc;
+	if ((rc = use_device(c)))
+		return rc;
+	for (int q = 0; q < world; q++) {
+		const ntc_ctx* o = all[q];
+		if (!o || o->hll_bits || o->nK != c->nK || o->rBits != c->rBits || o->pool.n_blocks != c->pool.n_blocks || o->pool.nbins != c->pool.nbins)
+			return set_err(NTC_EINVAL, "ntc_peer_attach_contexts: context %d has a different geometry", q);
+		if (o->device != c->device) {
+			int can = 0;
+			CK(cudaDeviceCanAccessPeer(&can, c->device, o->device));
+			if (!can)
+				return set_err(NTC_ECUDA, "ntc_peer_attach_contexts: device %d cannot access device %d", c->device, o->device);
+			cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+				CK(e);
+			cudaGetLastError();
+		}
+		c->peers.entries[q] = o->pool.entries;
+		c->peers.slice_blocks[q] = o->pool.slice_blocks;
+		c->peers.slice_nblk[q] = o->pool.slice_nblk;
+	}
+	c->peers.n = (uint32_t)world;
+	c->peer_world = world;
+	c->peer_rank = rank;
+	return NTC_OK;
+}
+
 int ntc_log_status_device(ntc_ctx* c, void* d_status)
 {
 	if (!c || !d_status)

@@ -167,6 +167,54 @@ def exchange_hist(sketch, rBits: int, device, totals_out=None):
     return p
 
 
+# ---- reduction over peer memory: no host planning, no host synchronisation -----------------------------------------
+def peer_setup(sketch):
+    """Once per context: all-gather the IPC handles of the ranks' hit logs and map them (ntc_peer_attach).  All ranks must
+    be processes on ONE node (CUDA IPC + NVLink peer access)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = sketch.peer_export()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine.tobytes())
+    sketch.peer_attach(world, rank, np.frombuffer(b"".join(gathered), dtype=np.uint8))
+
+
+class PeerReducer:
+    """The one reduction at the end of a multi-GPU run (the reference has a single shared sketch, ntcard.cpp:439, and an F1
+    merge, ntcard.cpp:464-466), host-free: two small NCCL all-reduces around ONE kernel sequence that pulls the other
+    ranks' hit-log blocks through NVLink peer memory (ntc_reduce_owned):
+
+        status := [F1 per k, my log is incomplete]      (kernel)          all-reduce(status)   -- F1 totals + barrier
+        owned slices := zeros + every rank's entries     (apply_owned_kernel, peer loads)
+        hist := counter-value histogram of my slices    (kernel)          all-reduce(hist)     -- result + barrier
+
+    Everything is ordered on torch's current stream, which must be the sketch's stream.  reduce() returns device tensors;
+    result() is the only host synchronisation (and checks the fallback flag)."""
+
+    def __init__(self, sketch, device):
+        self.sk, self.device = sketch, device
+        self.nK = sketch.nK
+        self.status = torch.zeros(self.nK + 1, dtype=torch.int64, device=device)
+        self.hist = torch.zeros(self.nK * 2 * 65536, dtype=torch.int32, device=device)
+        peer_setup(sketch)
+
+    def reduce(self):
+        self.sk.log_status_device(self.status.data_ptr())
+        dist.all_reduce(self.status, op=dist.ReduceOp.SUM)
+        self.sk.reduce_owned(self.status.data_ptr(), self.hist.data_ptr())
+        dist.all_reduce(self.hist, op=dist.ReduceOp.SUM)
+        return self.status, self.hist
+
+    def result(self, rBits):
+        """(p_hist uint32 [nK, 2, 65536] or None when some rank's log was incomplete -> dense fallback, F1 uint64 [nK])"""
+        st = self.status.cpu().numpy()
+        f1 = st[:self.nK].astype(np.uint64)
+        if st[self.nK] != 0:
+            return None, f1
+        p = self.hist.cpu().numpy().view(np.uint32).reshape(self.nK, 2, 65536).copy()
+        p[:, :, 0] = (1 << rBits) - p[:, :, 1:].sum(axis=2, dtype=np.uint64).astype(np.uint32)
+        return p, f1
+
+
 _BUFFERS = {}
 
 

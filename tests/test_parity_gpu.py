@@ -552,6 +552,62 @@ def test_hit_log_exchange_between_two_contexts_on_one_gpu(oracle):
         assert np.array_equal(t.reshape(-1), want) and np.array_equal(f1b, wf1)
 
 
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_peer_memory_reduction_between_contexts_on_one_gpu(oracle, world):
+    """The multi-GPU reduction over peer memory (ntc_log_status_device / ntc_reduce_owned) exercised on ONE device: `world`
+    contexts play the ranks, each sketches its share of the reads; every rank then zeroes the slices it owns (s % world ==
+    rank), applies to them the hit-log entries of ALL ranks -- read straight out of the other contexts' logs -- and
+    histograms them.  The summed histograms must equal the histogram of one sketch of all reads (oracle), F1 likewise."""
+    import torch
+    n, L, kList, rBits, sBits = 30720, 150, [32, 64], 25, 7
+    stride = nt.stride_words(L)
+    words = nt.gen_packed(62, 0, n, L, 1, n // 4, stride)
+    a = oracle.gen_reads(62, 0, n, L, 1, n // 4)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+    rB = 1 << rBits
+    want_p = np.stack([np.bincount(want[t * rB:(t + 1) * rB], minlength=65536) for t in range(2 * len(kList))]).reshape(len(kList), 2, 65536)
+    nK = len(kList)
+    ranks = [nt.Sketch(kList, rBits=rBits, sBits=sBits) for _ in range(world)]
+    try:
+        for r, sk in enumerate(ranks):
+            sk.peer_attach_contexts(r, ranks)
+        for rep in range(2):                                   # twice: a context is usable again after reset
+            status = [torch.zeros(nK + 1, dtype=torch.int64, device="cuda") for _ in ranks]
+            hist = [torch.zeros(nK * 2 * 65536, dtype=torch.int32, device="cuda") for _ in ranks]
+            per = (n + world - 1) // world
+            for r, sk in enumerate(ranks):
+                sk.reset()
+                lo, hi = r * per, min(n, (r + 1) * per)
+                sk.submit(words[lo * stride:hi * stride], None, hi - lo, stride)
+                sk.log_status_device(status[r].data_ptr())
+            for sk in ranks:
+                sk.stream_sync()                               # stands in for the status all-reduce (sum + barrier)
+            tot = torch.stack(status).sum(dim=0)
+            assert int(tot[nK]) == 0
+            assert np.array_equal(tot[:nK].cpu().numpy().astype(np.uint64), wf1)
+            for r, sk in enumerate(ranks):
+                sk.reduce_owned(tot.data_ptr(), hist[r].data_ptr())
+            for sk in ranks:
+                sk.stream_sync()                               # stands in for the histogram all-reduce
+            p = torch.stack(hist).cpu().numpy().view(np.uint32).astype(np.uint64).sum(axis=0).reshape(nK, 2, 65536)
+            p[:, :, 0] = rB - p[:, :, 1:].sum(axis=2)
+            assert np.array_equal(p, want_p.astype(np.uint64))
+            with pytest.raises(nt.NtcError):
+                ranks[0].finish(counters=True)                 # only the owned slices are defined now
+        # an incomplete log (flushed) raises the flag and the kernels leave the histogram untouched
+        ranks[0].reset()
+        ranks[0].submit(words, None, n, stride)
+        ranks[0].flush()
+        st = torch.zeros(nK + 1, dtype=torch.int64, device="cuda")
+        ranks[0].log_status_device(st.data_ptr())
+        ranks[0].stream_sync()
+        assert int(st[nK]) == 1
+    finally:
+        for sk in ranks:
+            sk.close()
+
+
 def test_tightly_packed_uniform_batches_take_the_pipeline(oracle):
     """Uniform-stride batches whose stride is not a multiple of 4 words (44 bytes per 150 bp read) are padded on the
     device and hashed by the pipeline; forced NTC_KERNEL_BITSLICE must accept them and the result stays exact."""
