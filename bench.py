@@ -28,14 +28,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (reads per GPU, L, kList, sBits, description)
-    "config2": (10_000_000, 150, [32], 7, "config 2: 10M synthetic 150 bp reads per GPU, k=32, s=7, r=27"),
-    "config3": (100_000_000, 150, [32, 64, 96, 128], 7, "config 3: 100M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27"),
-    "config4": (125_000_000, 150, [64], 11, "config 4: 125M synthetic 150 bp reads per GPU, k=64, s=11, r=27"),
-    "small": (1_000_000, 150, [32], 7, "dev: 1M synthetic 150 bp reads, k=32, s=7, r=27"),
-    "multik": (10_000_000, 150, [32, 64, 96, 128], 7, "dev: 10M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27"),
-    "k64s11": (10_000_000, 150, [64], 11, "dev: 10M synthetic 150 bp reads, k=64, s=11, r=27"),
-    "long10k": (200_000, 10_000, [31], 11, "dev (config 5 shape): 200k synthetic 10 kbp reads without N, k=31, s=11, r=27"),
+    # name: (reads per GPU, L, kList, sBits, description, generator seed S, generator mode) -- SURVEY 8d: S = 1, 2, 3, 4 for configs 2..5;
+    # mode 0 = uniform reads, 2 = N mode (0-3 runs of 1-20 N per read: the host packer splits the reads there -> ragged records)
+    "config2": (10_000_000, 150, [32], 7, "config 2: 10M synthetic 150 bp reads per GPU, k=32, s=7, r=27", 1, 0),
+    "config3": (100_000_000, 150, [32, 64, 96, 128], 7, "config 3: 100M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27", 2, 0),
+    "config4": (125_000_000, 150, [64], 11, "config 4: 1B synthetic 150 bp reads over 8 GPUs = 125M per GPU, k=64, s=11, r=27, one reduction at the end", 3, 0),
+    "config5": (5_000_000, 10_000, [31], 11, "config 5 (10 % sample, device resident): 5M of the 50M synthetic 10 kbp reads with N runs, k=31, s=11, r=27; "
+                "20 ragged batches of 250k reads, split at N by the host packer", 4, 2),
+    "small": (1_000_000, 150, [32], 7, "dev: 1M synthetic 150 bp reads, k=32, s=7, r=27", 1, 0),
+    "multik": (10_000_000, 150, [32, 64, 96, 128], 7, "dev: 10M synthetic 150 bp reads, k=32,64,96,128 one pass, s=7, r=27", 2, 0),
+    "k64s11": (10_000_000, 150, [64], 11, "dev: 10M synthetic 150 bp reads, k=64, s=11, r=27", 3, 0),
+    "long10k": (200_000, 10_000, [31], 11, "dev (config 5 shape): 200k synthetic 10 kbp reads without N, k=31, s=11, r=27", 4, 0),
+    "long10kN": (250_000, 10_000, [31], 11, "dev (config 5 shape): 250k synthetic 10 kbp reads with N runs, k=31, s=11, r=27", 4, 2),
 }
 RBITS = 27
 METRIC = "k-mers hashed/sec at k=32 on 150bp reads"
@@ -107,7 +111,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
-def cpu_arm(args, n_reads_full, L, kList, sBits, bounded_seconds=15.0):
+def cpu_arm(args, n_reads_full, L, kList, sBits, bounded_seconds=15.0, seed=1, mode=0):
     """The reference's CPU hot loop (ntRead over reads held in RAM, OpenMP over reads on the shared
     sketch: ntcard.cpp:147-158, 445-467) on this box's host cores.  Uses oracle/_ref (the unmodified
     reference) when it was built, else the C restatement.  Returns a function step() -> (kmers, seconds)."""
@@ -119,7 +123,7 @@ def cpu_arm(args, n_reads_full, L, kList, sBits, bounded_seconds=15.0):
     ref = Reference() if kind == "reference" else None
     # calibrate on 100k reads, then size the sample for ~bounded_seconds of CPU work (max: the full workload)
     def run(n):
-        reads = orc.gen_reads(1, 0, n, L, 0, 0)
+        reads = orc.gen_reads(seed, 0, n, L, mode, 0)
         off = np.arange(n + 1, dtype=np.uint64) * L
         sk = np.zeros(len(kList) * 2 << RBITS, dtype=np.uint16)
         tot = np.zeros(len(kList), dtype=np.uint64)
@@ -130,19 +134,20 @@ def cpu_arm(args, n_reads_full, L, kList, sBits, bounded_seconds=15.0):
         else:
             orc.ntread_batch(reads, off, kList, RBITS, sBits, sk, tot, threads)
         return int(tot.sum()), time.perf_counter() - t0
-    km, dt = run(100_000)
+    n_cal = max(1000, min(100_000, 15_000_000 // L))
+    km, dt = run(n_cal)
     rate = km / dt
     per_read = sum(max(0, L - k + 1) for k in kList)
-    n = int(min(n_reads_full, max(100_000, rate * bounded_seconds / per_read)))
+    n = int(min(n_reads_full, max(n_cal, rate * bounded_seconds / per_read)))
     sample = f"{n} of the workload's {n_reads_full} reads per step ({per_read} k-mers/read), reads in RAM, sketch shared, OpenMP over reads"
     return (lambda: run(n)), {"kind": kind, "cores": threads, "sample": sample}
 
 
 def reference_main(args, rank, world):
-    n_reads, L, kList, sBits, desc = WORKLOADS[args.workload]
+    n_reads, L, kList, sBits, desc, gseed, gmode = WORKLOADS[args.workload]
     if rank != 0:
         return
-    step, info = cpu_arm(args, n_reads, L, kList, sBits, bounded_seconds=args.cpu_seconds)
+    step, info = cpu_arm(args, n_reads, L, kList, sBits, bounded_seconds=args.cpu_seconds, seed=gseed, mode=gmode)
     for _ in range(min(args.warmup, 1)):
         step()
     tot_k, tot_t = 0, 0.0
@@ -197,8 +202,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
-    n_reads, L, kList, sBits, desc = WORKLOADS[args.workload]
+    n_reads, L, kList, sBits, desc, gseed, gmode = WORKLOADS[args.workload]
     nK = len(kList)
+    ragged = gmode == 2  # reads with N runs: ragged records, built by the host packer, then resident in HBM
     stride = nt.stride_words(L)
     kmers_per_read = sum(max(0, L - k + 1) for k in kList)
     kmers_rank = n_reads * kmers_per_read
@@ -207,13 +213,30 @@ def main():
 
     st = torch.cuda.Stream(device=dev)
     counters = torch.zeros(nK * 2 << RBITS, dtype=torch.int32, device=dev)
-    n_words = n_reads * stride
-    d_words = torch.empty(n_words, dtype=torch.int32, device=dev)
+    first = rank * n_reads  # read i lives on GPU i // n_reads (SURVEY 8d config 4 sharding rule)
+    rag = []                # ragged workloads: [(d_words, d_off, n_rec, n_words)] per batch
+    if ragged:
+        per_batch = 250_000
+        kmers_rank, alg_bytes_rank = 0, 0
+        for b0 in range(0, n_reads, per_batch):
+            nb_ = min(per_batch, n_reads - b0)
+            chars = nt.gen_ascii(gseed, first + b0, nb_, L, mode=2)
+            w, off = nt.pack_chars(chars, np.arange(nb_ + 1, dtype=np.uint64) * L, min_len=min(kList))
+            del chars
+            lens = w[off[:-1]].astype(np.int64)
+            kmers_rank += int(sum(np.maximum(lens - k + 1, 0).sum() for k in kList))
+            alg_bytes_rank += int((4 + (lens + 3) // 4).sum())
+            rag.append((torch.from_numpy(w.view(np.int32)).to(dev), torch.from_numpy(off.view(np.int32)).to(dev), len(off) - 1, len(w)))
+        n_words = sum(r[3] for r in rag)
+        d_words = None
+    else:
+        n_words = n_reads * stride
+        d_words = torch.empty(n_words, dtype=torch.int32, device=dev)
     with torch.cuda.stream(st):
         sk = nt.Sketch(kList, rBits=RBITS, sBits=sBits, device=local_rank, d_counters=counters.data_ptr(), stream=st.cuda_stream)
         sk.set_kernel(kern)
-        first = rank * n_reads  # read i lives on GPU i // n_reads (SURVEY 8d config 4 sharding rule)
-        sk.gen_packed_device(1, first, n_reads, L, 0, 0, stride, d_words.data_ptr())
+        if not ragged:
+            sk.gen_packed_device(gseed, first, n_reads, L, 0, 0, stride, d_words.data_ptr())
         sk.sync()
 
         def barrier():
@@ -254,12 +277,19 @@ def main():
         nb = max(1, args.batches)
         per = (n_reads + nb - 1) // nb
 
-        def step_resident():
-            sk.reset()
+        def submit_resident():
+            if ragged:
+                for dw, do, nr, nw in rag:
+                    sk.submit_device(dw.data_ptr(), nw, nr, 0, d_off=do.data_ptr())
+                return
             for b in range(nb):
                 r0 = b * per
                 r1 = min(n_reads, r0 + per)
                 sk.submit_device(d_words.data_ptr() + r0 * stride * 4, (r1 - r0) * stride, r1 - r0, stride)
+
+        def step_resident():
+            sk.reset()
+            submit_resident()
             if world == 1:
                 sk.flush()  # apply the hit log to the counters in HBM: the step ends with a complete sketch
             else:
@@ -321,7 +351,7 @@ def main():
             p_peer, f1 = reducer.result(RBITS)
             assert int(f1.sum()) == kmers_rank * world, (f1, kmers_rank, world)
             sk.reset()
-            sk.submit_device(d_words.data_ptr(), n_reads * stride, n_reads, stride)
+            submit_resident()
             p_dense = dense_reduce()
             same = 1 if (p_peer is not None and np.array_equal(p_peer, p_dense)) else 0
             flag = torch.tensor([same], dtype=torch.int32, device=dev)
@@ -334,24 +364,43 @@ def main():
             # host buffers are packed tightly (1 length word + ceil(L/16) base words = 44 bytes per 150 bp read); the library
             # pads the records to 16 bytes on the device
             estride = nt.stride_words(L, False)
-            e_words = n_reads * estride
-            d_tight = torch.empty(e_words, dtype=torch.int32, device=dev)
-            sk.gen_packed_device(1, first, n_reads, L, 0, 0, estride, d_tight.data_ptr())
-            pinned = nt.PinnedBuffer(e_words)
-            torch.cuda.synchronize(dev)
-            host_view = torch.from_numpy(pinned.array.view(np.int32))
-            host_view.copy_(d_tight)  # the same reads as the device-resident leg, now in pinned HOST memory
-            del d_tight
-            nchunk = max(1, args.e2e_chunks)
+            if ragged:
+                # the ragged batches as the host packer made them, in pinned host memory: words + offsets per batch
+                host_b = []
+                e_words = 0
+                for dw, do, nr, nw in rag:
+                    pw, po = nt.PinnedBuffer(nw), nt.PinnedBuffer(nr + 1)
+                    torch.from_numpy(pw.array.view(np.int32)).copy_(dw)
+                    torch.from_numpy(po.array.view(np.int32)).copy_(do)
+                    host_b.append((pw, po, nr))
+                    e_words += nw + nr + 1
+                torch.cuda.synchronize(dev)
+            else:
+                e_words = n_reads * estride
+                d_tight = torch.empty(e_words, dtype=torch.int32, device=dev)
+                sk.gen_packed_device(gseed, first, n_reads, L, 0, 0, estride, d_tight.data_ptr())
+                pinned = nt.PinnedBuffer(e_words)
+                torch.cuda.synchronize(dev)
+                host_view = torch.from_numpy(pinned.array.view(np.int32))
+                host_view.copy_(d_tight)  # the same reads as the device-resident leg, now in pinned HOST memory
+                del d_tight
+            nchunk = max(1, args.e2e_chunks) if not ragged else len(rag)
             cper = (n_reads + nchunk - 1) // nchunk
             result = {}
 
-            def step_e2e():
-                sk.reset()
+            def submit_host():
+                if ragged:
+                    for pw, po, nr in host_b:
+                        sk.submit(pw.array, po.array, nr)
+                    return
                 for c in range(nchunk):
                     r0 = c * cper
                     r1 = min(n_reads, r0 + cper)
                     sk.submit(pinned.array[r0 * estride:r1 * estride], None, r1 - r0, estride)
+
+            def step_e2e():
+                sk.reset()
+                submit_host()
                 if world == 1:
                     _, f1, p = sk.finish(counters=False, hist=True)
                 else:
@@ -371,7 +420,7 @@ def main():
                    "ms_per_step": ems / esteps, "chunks": nchunk}
             if rank == 0:
                 F0, f = result["est"][0]
-                distinct = world * n_reads * (L - kList[0] + 1)
+                distinct = world * (kmers_rank if ragged else n_reads * (L - kList[0] + 1))
                 e2e["F1"] = [int(x) for x in result["F1"]]
                 e2e["F0"] = F0
                 e2e["F0_rel_err_vs_distinct"] = abs(F0 - distinct) / distinct
@@ -379,7 +428,12 @@ def main():
                     e2e["sketch_increments"] = int((np.asarray(result["p"])[:, :, 1:].astype(np.uint64) * np.arange(1, 65536, dtype=np.uint64)).sum())
                 except Exception:  # reporting only
                     e2e["sketch_increments"] = None
-            pinned.free()
+            if ragged:
+                for pw, po, _ in host_b:
+                    pw.free()
+                    po.free()
+            else:
+                pinned.free()
         sk.close()
 
     if rank == 0:
@@ -440,7 +494,7 @@ def main():
         }
         if not args.no_cpu:  # rank 0 only; at N > 1 the other ranks wait in the final barrier
             try:
-                step, info = cpu_arm(args, n_reads, L, kList, sBits, bounded_seconds=args.cpu_seconds)
+                step, info = cpu_arm(args, n_reads, L, kList, sBits, bounded_seconds=args.cpu_seconds, seed=gseed, mode=gmode)
                 km, dt = step()
                 out["cpu_baseline"] = dict(info, value=km / dt, unit=UNIT)
             except Exception as e:  # the baseline is reporting, never the product path

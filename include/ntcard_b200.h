@@ -90,7 +90,9 @@ int ntc_set_gap(ntc_ctx* ctx, unsigned gap);
  * ntcard.cpp:182/203/230).  Pageable memory is copied to internal pinned
  * staging before the call returns.  Memory from ntc_host_alloc() is copied by
  * DMA directly and must stay untouched until ntc_wait(ticket) / ntc_sync().
- * Asynchronous; thread-compatible (one submitting thread per context).
+ * Asynchronous and THREAD-SAFE: like ntRead, which the reference calls concurrently on one shared
+ * sketch (one OpenMP thread per file, ntcard.cpp:445), every entry point that takes a context may be
+ * called from several host threads; the context serialises them internally.
  * *ticket (optional) identifies the batch for ntc_wait(). */
 int ntc_submit(ntc_ctx* ctx, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec,
     uint32_t stride_words, uint64_t* ticket);
@@ -218,7 +220,8 @@ void ntc_host_free(void* p);
 
 /* Upper bound of words produced by ntc_pack_seqs for `n_seq` sequences holding
  * `total_bases` characters in total. */
-size_t ntc_pack_bound(size_t n_seq, size_t total_bases);
+size_t ntc_pack_bound(size_t n_seq, size_t total_bases);                       /* safe for any min_len (about one word per character) */
+size_t ntc_pack_bound_k(size_t n_seq, size_t total_bases, uint32_t min_len); /* tighter: records shorter than min_len are dropped */
 /* Split each sequence seq[i] = chars[seq_off[i] .. seq_off[i+1]) at characters
  * outside ACGTUacgtu, drop segments shorter than min_len, 2-bit pack the rest
  * as records.  Appends to words[*n_words..] / off[*n_rec..] (off gets

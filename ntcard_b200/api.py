@@ -21,7 +21,7 @@ SYMBOLS = [
     "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_set_gap", "ntc_submit", "ntc_submit_device", "ntc_wait",
     "ntc_sync", "ntc_flush", "ntc_log_info", "ntc_log_counts", "ntc_log_export", "ntc_log_import", "ntc_flush_slices",
     "ntc_hist_slices", "ntc_stream_sync", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_totals_nosync", "ntc_set_totals", "ntc_finish", "ntc_estimate",
-    "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
+    "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_bound_k", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
     "ntc_gen_packed_device", "ntc_stride_words", "ntc_stats", "ntc_kernel_time", "ntc_stage_times", "ntc_device_count",
     "ntc_last_error", "ntc_version",
     "ntc_hll_create", "ntc_hll_registers_device", "ntc_hll_finish", "ntc_hll_estimate", "ntc_check_offsets",
@@ -71,6 +71,7 @@ def _load():
         "ntc_host_alloc": (vp, [C.c_size_t]),
         "ntc_host_free": (None, [vp]),
         "ntc_pack_bound": (C.c_size_t, [C.c_size_t, C.c_size_t]),
+        "ntc_pack_bound_k": (C.c_size_t, [C.c_size_t, C.c_size_t, C.c_uint32]),
         "ntc_pack_seqs": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t), vp,
                                     C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
         "ntc_gen_ascii": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_uint64, vp]),
@@ -140,8 +141,8 @@ def pack_chars(chars, seq_off, min_len=1):
     seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
     n = len(seq_off) - 1
     total = int(seq_off[-1])
-    cap_w = lib.ntc_pack_bound(n, total)
-    cap_r = n + total // 2 + 2
+    cap_w = lib.ntc_pack_bound_k(n, total, max(1, min_len))
+    cap_r = n + total // (max(1, min_len) + 1) + 2
     words = np.empty(cap_w, dtype=np.uint32)
     off = np.empty(cap_r + 1, dtype=np.uint32)
     nw, nr, cons = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) fused_kernel(const __grid_con
 
 	// the warp's open blocks: carried over from the previous launch unless a flush or a reset came between
 	const uint32_t wg = blockIdx.x * kFusedWarps + warp;
-	uint32_t* gs = P.gstate + ((size_t)a.ki * P.max_groups + wg) * (1 + 5 * (size_t)nb);
+	uint32_t* gs = P.gstate + ((size_t)a.ki * P.max_groups + wg) * gstate_row(nb);
 	const uint32_t gen_f = P.ctl[CTL_FLUSHES] + 1u;
 	const bool keep = wg < P.max_groups;
 	{
@@ -365,8 +365,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) fused_kernel(const __grid_con
 #pragma unroll
 					for (int s = 0; s < 32; s++)
 						if ((vmask >> s) & 1u) {
-							c1 += v[s].x >= (uint32_t)k ? v[s].x - (uint32_t)k + 1u : 0u;
-							mx = max(mx, v[s].x);
+							const uint32_t ls = min(v[s].x, (stride - 1u) * 16u); // a corrupt length word counts as the record's capacity
+							c1 += ls >= (uint32_t)k ? ls - (uint32_t)k + 1u : 0u;
+							mx = max(mx, ls);
 						}
 					if (a.pass == 0)
 						f1_local += c1;

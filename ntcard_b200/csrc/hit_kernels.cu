@@ -240,10 +240,10 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_
 	// open / spare blocks of this group: carried over from the previous launch unless a flush or a reset came between
 	const uint32_t group_id = blockIdx.x * kGroups + g;
 	const uint32_t nb = a.pool.nbins;
-	uint32_t* gs = a.pool.gstate + ((size_t)a.ki * a.pool.max_groups + group_id) * (1 + 5 * (size_t)nb);
-	const uint32_t gen = (a.pool.epoch << 16) | (a.pool.ctl[CTL_FLUSHES] & 0xFFFFu);
+	uint32_t* gs = a.pool.gstate + ((size_t)a.ki * a.pool.max_groups + group_id) * gstate_row(nb) + 1; // gs[-1] = epoch, gs[0] = flushes + 1
+	const uint32_t gen = a.pool.ctl[CTL_FLUSHES] + 1u; // the full counters: no wrap can make a stale state look current
 	const bool active = group_id < a.n_units && group_id < a.pool.max_groups;
-	const bool resume = active && gs[0] == gen;
+	const bool resume = active && gs[-1] == a.pool.epoch && gs[0] == gen;
 	Spare sp;
 	sp.have = false;
 	sp.blk = sp.at = 0;
@@ -383,8 +383,10 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_
 			gs[1 + 3 * nb + gtid] = sp.blk;
 			gs[1 + 4 * nb + gtid] = sp.at;
 		}
-		if (gtid == 0)
+		if (gtid == 0) {
+			gs[-1] = a.pool.epoch;
 			gs[0] = sp.have ? gen : 0u;
+		}
 	}
 }
 
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(256) fallback_kernel(const uint32_t* __restric
 			const uint32_t rec = tile * kTileRecs + r;
 			if (rec < n_rec) {
 				const uint32_t* p = words + (uint64_t)rec * stride;
-				process_piece_k(p + 1, __ldg(p), 0, k, T, ctr_k, rBits, sBits); // F1 was counted by the scan kernel
+				process_piece_k(p + 1, min(__ldg(p), (stride - 1u) * 16u), 0, k, T, ctr_k, rBits, sBits); // F1 was counted by the scan kernel
 			}
 		}
 	}

@@ -126,8 +126,11 @@ __global__ void __launch_bounds__(HLL_BLOCK) hll_kernel(const uint32_t* __restri
 				rec = piece_rec[piece];
 				a = (piece - piece_first[rec]) * PIECE_STARTS;
 			}
-			const uint32_t* r = words + (off ? (uint64_t)__ldg(off + rec) : (uint64_t)rec * stride);
-			mine += hll_piece(r + 1, __ldg(r), a, k, tab, regs, low_mask);
+			const uint64_t ro = off ? (uint64_t)__ldg(off + rec) : (uint64_t)rec * stride;
+			const uint32_t* r = words + ro;
+			const uint64_t cap = off ? (uint64_t)__ldg(off + rec + 1) - ro : stride; // a corrupt length word must not leave the record
+			const uint32_t len = (uint32_t)min((uint64_t)__ldg(r), cap ? (cap - 1) * 16 : 0);
+			mine += hll_piece(r + 1, len, a, k, tab, regs, low_mask);
 		}
 		const bool last = base + gridDim.x * blockDim.x >= n_pieces || base + gridDim.x * blockDim.x < base;
 		if (kShared && (last || ((round + 1) & round) == 0)) {

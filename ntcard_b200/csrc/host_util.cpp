@@ -127,13 +127,16 @@ uint32_t ntc_stride_words(uint32_t L, int align4)
 	return w;
 }
 
-size_t ntc_pack_bound(size_t n_seq, size_t total_bases)
+size_t ntc_pack_bound_k(size_t n_seq, size_t total_bases, uint32_t min_len)
 {
-	// every record costs 1 length word + ceil(len/16); a sequence with m invalid characters yields
-	// at most m+1 records, and each invalid character removes one base, so n_seq + total/16 + total/2 is safe;
-	// the common case (few Ns) is far below this.
-	return n_seq + total_bases / 16 + total_bases / 2 + 2;
+	// A record of len >= min_len bases costs 1 length word + ceil(len/16) <= 2 + len/16 words.  Every record but the last of a
+	// sequence is followed by at least one invalid character, so a sequence of c characters yields at most c/(min_len+1) + 1
+	// records: words <= total/16 + 2 * (n_seq + total/(min_len+1)).  min_len = 1 ("ANAN..."): about one word per character.
+	const size_t m = min_len ? min_len : 1;
+	return total_bases / 16 + 2 * (n_seq + total_bases / (m + 1)) + 2;
 }
+
+size_t ntc_pack_bound(size_t n_seq, size_t total_bases) { return ntc_pack_bound_k(n_seq, total_bases, 1); }
 
 int ntc_pack_seqs(const char* chars, const uint64_t* seq_off, size_t n_seq, uint32_t min_len, uint32_t* words, size_t cap_words,
     size_t* n_words, uint32_t* off, size_t cap_rec, size_t* n_rec, size_t* consumed)

@@ -29,6 +29,7 @@ cudaError_t launch_retile_count(const BatchView& b, uint32_t Lp, uint32_t D, uin
 cudaError_t launch_retile_fill(const BatchView& b, uint32_t Lp, uint32_t D, uint32_t stride, const uint32_t* d_full_first,
     const uint32_t* d_tail_idx, const uint32_t* d_tail_first, uint32_t* d_out_uniform, uint32_t* d_out_tail_words, uint32_t* d_out_tail_off,
     int n_sm, cudaStream_t st);
+cudaError_t launch_check_offsets(const uint32_t* d_off, uint32_t n_rec, uint64_t n_words, uint32_t* d_out /* [2], zeroed */, int n_sm, cudaStream_t st);
 cudaError_t launch_stride_offsets(uint32_t stride, uint32_t n_rec, uint32_t* d_off, cudaStream_t st);
 cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t stride_out, uint32_t n_rec, uint32_t* d_out, int n_sm, cudaStream_t st);
 cudaError_t launch_pad_ragged(const uint32_t* d_in, const uint32_t* d_off, uint32_t n_rec, uint32_t stride_out, uint32_t* d_out, int n_sm,

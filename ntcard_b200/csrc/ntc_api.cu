@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "../../include/ntcard_b200.h"
@@ -61,6 +62,9 @@ struct Stage {
 } // namespace
 
 struct ntc_ctx {
+	// Every entry point locks the context: ntRead is called concurrently on one shared sketch (one OpenMP thread per file,
+	// ntcard.cpp:445), so ntc_submit must be callable from several threads.  Recursive because entry points call each other.
+	std::recursive_mutex mu;
 	int device = 0;
 	int n_sm = 148;
 	cudaStream_t stream = nullptr; // compute stream (own or caller's)
@@ -124,6 +128,7 @@ struct ntc_ctx {
 	size_t cap_masks = 0;
 	uint32_t* d_tile_info = nullptr;
 	size_t cap_tile_info = 0;
+	uint32_t* d_offchk = nullptr; // ntc_submit_device: {longest record, bad offsets} of a ragged batch
 	bool pending = false;     // the hit log may hold entries, or the sketch is not materialised yet: flush before reading it
 	bool use_pipeline = true;
 	bool use_fused = false;    // NTC_FUSED=1: the fused sketch kernel (fused_kernel.cuh) instead of scan + hit; exact, but measured slower
@@ -131,7 +136,7 @@ struct ntc_ctx {
 	bool no_stage = false;     // NTC_NO_STAGE=1 (stand-alone hit kernel: gather with __ldg instead of a TMA-staged tile)
 	bool no_retile = false;    // NTC_NO_RETILE=1
 	bool clear_by_memset = true;
-	bool pad_ragged = false;   // NTC_PAD=1: NTC_KERNEL_AUTO pads short ragged batches for the pipeline too
+	bool pad_ragged = true;    // NTC_PAD=0: NTC_KERNEL_AUTO leaves short ragged batches to the general kernel instead of padding them for the pipeline
 	// NTC_HOST_TIMING=1: host time spent in the calls of the submit path, per call site, printed by ntc_destroy (diagnosis only)
 	bool host_timing = false;
 	struct HostSpan { const char* what; double total_ms, max_ms; uint64_t n; };
@@ -159,7 +164,8 @@ struct ntc_ctx {
 	} run_slot[kRunSlots];
 	unsigned next_run_slot = 0;
 	unsigned apply_grid = 0, hit_grid_max = 0;
-	unsigned chunk_waves = 0; // scan waves per pipeline chunk (0 = whole batch; chunking measured slower, kept for experiments)
+	unsigned chunk_waves = 0; // NTC_CHUNK_WAVES: scan waves per pipeline chunk (0 = as large as the hit-log pool allows)
+	unsigned multik_chunk_mb = 0; // NTC_MULTIK_CHUNK_MB: with several k, cap the chunks at this many MB of packed reads (L2 reuse across k)
 	uint64_t n_flush_launches = 0;
 	// finish buffers
 	uint16_t* d_narrow = nullptr;
@@ -251,7 +257,12 @@ int pool_create(ntc_ctx* c)
 {
 	ntc::pl::Pool& P = c->pool;
 	const char* env = getenv("NTC_POOL_BLOCKS");
-	P.n_blocks = env ? (uint32_t)strtoul(env, nullptr, 10) : (512u << 10); // x 256 entries x 4 B = 512 MiB
+	// default: 768 Ki blocks (x 256 entries x 4 B = 768 MiB) per k -- a flush walks the whole sketch (1 GiB per k), so the more
+	// hits fit between two flushes the better, and HBM is plentiful (100 M reads x 4 k: 48.5 ms per pass with 512 MiB, 33.6 ms
+	// with 4 GiB); capped so that the block lists (n_slices x n_blocks words) stay below 4 GiB
+	P.n_blocks = env ? (uint32_t)strtoul(env, nullptr, 10) : (768u << 10) * std::min(c->nK, 8u);
+	if (!env) // no more log entries than twice the counters (small sketches in tests: a small pool)
+		P.n_blocks = (uint32_t)std::min<uint64_t>(P.n_blocks, std::max<uint64_t>(4096, (((uint64_t)c->nK * NTC_NSAMP) << c->rBits) / 128));
 	P.n_blocks = std::min(std::max(P.n_blocks, 64u), (1u << 23) - 1u); // a block id has 23 bits in the slice lists
 	P.rBits = c->rBits;
 	P.nK = c->nK;
@@ -263,6 +274,8 @@ int pool_create(ntc_ctx* c)
 	}
 	P.nbins = 1u << (idx_bits - P.bin_shift);
 	P.n_slices = c->nK * P.nbins;
+	if (!env)
+		P.n_blocks = std::max(64u, std::min(P.n_blocks, (1u << 30) / P.n_slices));
 	// every slice's block list can hold the whole pool: a list can then never fill up before the pool does, so the only
 	// "out of space" event is pool exhaustion, which both hit paths handle exactly (deferred tiles / conditional flush)
 	P.slice_cap = P.n_blocks;
@@ -285,7 +298,7 @@ int pool_create(ntc_ctx* c)
 	P.max_groups = (unsigned)c->n_sm * 8u; // fused kernel: one saved state per warp (8 per SM); hit kernel: per group (<= 4 per SM)
 	P.epoch = 1;
 	{
-		const size_t gwords = (size_t)c->nK * P.max_groups * (1 + 5 * (size_t)P.nbins);
+		const size_t gwords = (size_t)c->nK * P.max_groups * ntc::pl::gstate_row(P.nbins);
 		CK(cudaMalloc((void**)&P.gstate, gwords * sizeof(uint32_t)));
 		CK(cudaMemset(P.gstate, 0, gwords * sizeof(uint32_t)));
 	}
@@ -313,6 +326,7 @@ int stage_end(ntc_ctx* c)
 // Apply everything that is pending to the counters in HBM (and materialise them after a reset).
 int flush(ntc_ctx* c)
 {
+	c->h_nblk.clear(); // (ntc_log_export / ntc_log_import refuse to work from a stale snapshot)
 	if (!c->pending)
 		return NTC_OK;
 	cudaEvent_t e0, e1;
@@ -430,28 +444,45 @@ uint32_t pipeline_config(const ntc_ctx* c, const ntc::BatchView& b, bool record_
 
 int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh);
 
-// One k over one batch.  The batch is cut into chunks of about one wave of scan tiles (8 per SM): the hit kernel then
-// finds the packed reads and the mask words its scan kernel just touched still in L2, not in HBM.
-int run_pipeline_k(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const PipeShape& sh)
+// All pipeline k (kmask) over one batch, chunk by chunk.  A chunk is a whole number of tiles and is kept small enough that the
+// hits it is expected to produce for any one k (tile k-mers / 2^(sBits-1)) fill at most ~40 % of the hit-log pool: a batch whose
+// hits exceed the pool would otherwise run the second half of its hit kernel on direct increments into HBM (~8x slower;
+// 100 M reads x k=32 in ONE batch: 186 M hits against 134 M pool entries).  The k loop is INSIDE the chunk loop -- with
+// NTC_MULTIK_CHUNK_MB=<n> the chunks are additionally capped at n MB of packed reads, so that the second and later k find them
+// in L2 and the reads cross DRAM once for all k (ntRead re-walks the read per k, ntcard.cpp:150; measured: DESIGN section 8).
+int run_pipeline_all(ntc_ctx* c, const ntc::BatchView& b, uint32_t kmask, const PipeShape* shape)
 {
-	if (sh.npos_max == 0)
-		return NTC_OK;
 	const uint32_t n_tiles = (b.n_rec + 1023) / 1024;
-	uint32_t chunk_tiles = (uint32_t)c->n_sm * std::max(1u, sh.nwarps) * c->chunk_waves;
-	if (c->chunk_waves == 0 || chunk_tiles >= n_tiles)
-		return run_pipeline_chunk(c, b, ki, sh);
-	// equal chunks, each a whole number of tiles
-	const uint32_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
+	const double pool_entries = (double)c->pool.n_blocks * ntc::pl::kBlkEntries;
+	uint64_t chunk_tiles = n_tiles;
+	unsigned nk = 0;
+	for (unsigned ki = 0; ki < c->nK; ki++)
+		if (((kmask >> ki) & 1u) && shape[ki].npos_max) {
+			nk++;
+			const double per_tile = 1024.0 * shape[ki].npos_max / (double)(1u << (c->sBits - 1));
+			chunk_tiles = std::min<uint64_t>(chunk_tiles, std::max<uint64_t>(1, (uint64_t)(0.4 * pool_entries / per_tile)));
+			if (c->chunk_waves)
+				chunk_tiles = std::min<uint64_t>(chunk_tiles, (uint64_t)c->n_sm * std::max(1u, shape[ki].nwarps) * c->chunk_waves);
+		}
+	if (nk == 0)
+		return NTC_OK;
+	if (c->multik_chunk_mb && nk > 1)
+		chunk_tiles = std::min<uint64_t>(chunk_tiles, std::max<uint64_t>(1, ((uint64_t)c->multik_chunk_mb << 20) / (1024ull * b.stride * 4)));
+	// equal chunks
+	const uint64_t n_chunks = (n_tiles + chunk_tiles - 1) / chunk_tiles;
 	chunk_tiles = (n_tiles + n_chunks - 1) / n_chunks;
-	for (uint32_t t0 = 0; t0 < n_tiles; t0 += chunk_tiles) {
+	for (uint64_t t0 = 0; t0 < n_tiles; t0 += chunk_tiles) {
 		ntc::BatchView sub = b;
-		const uint64_t r0 = (uint64_t)t0 * 1024;
+		const uint64_t r0 = t0 * 1024;
 		sub.words = b.words + r0 * b.stride;
-		sub.n_rec = (uint32_t)std::min<uint64_t>((uint64_t)chunk_tiles * 1024, b.n_rec - r0);
+		sub.n_rec = (uint32_t)std::min<uint64_t>(chunk_tiles * 1024, b.n_rec - r0);
 		sub.n_words = (uint64_t)sub.n_rec * b.stride;
-		int rc = run_pipeline_chunk(c, sub, ki, sh);
-		if (rc)
-			return rc;
+		for (unsigned ki = 0; ki < c->nK; ki++)
+			if (((kmask >> ki) & 1u) && shape[ki].npos_max) {
+				int rc = run_pipeline_chunk(c, sub, ki, shape[ki]);
+				if (rc)
+					return rc;
+			}
 	}
 	return NTC_OK;
 }
@@ -717,9 +748,9 @@ int run_retiled(ntc_ctx* c, const ntc::BatchView& b_in, uint32_t* handled)
 				if (!((pm >> ki) & 1u))
 					return set_err(NTC_ECUDA, "internal: re-tiled batch not accepted by the pipeline (k index %u)", ki);
 				shape[ki].start_limit = D;
-				if ((rc = run_pipeline_k(c, u, ki, shape[ki])))
-					return rc;
 			}
+		if ((rc = run_pipeline_all(c, u, kmask, shape)))
+			return rc;
 	}
 	if (n_tail) {
 		if ((rc = flush(c))) // the general kernel increments the counters in HBM directly
@@ -801,10 +832,8 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 	const uint32_t roll_mask = all & ~(pmask | retiled);
 	if (c->kernel == NTC_KERNEL_BITSLICE && roll_mask)
 		return set_err(NTC_EINVAL, "NTC_KERNEL_BITSLICE forced, but this batch / k / sBits has no bit-sliced variant (kmask %x)", pmask | retiled);
-	for (unsigned ki = 0; ki < c->nK; ki++)
-		if ((pmask >> ki) & 1u)
-			if ((rc = run_pipeline_k(c, b, ki, shape[ki])))
-				return rc;
+	if (pmask && (rc = run_pipeline_all(c, b, pmask, shape)))
+		return rc;
 	if (roll_mask && (rc = flush(c))) // the general kernel increments the counters in HBM directly
 		return rc;
 	if (roll_mask && (rc = run_roll64(c, b, record_is_piece, roll_mask)))
@@ -982,11 +1011,13 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
 	c->clear_by_memset = !(getenv("NTC_CLEAR_MEMSET") && atoi(getenv("NTC_CLEAR_MEMSET")) == 0);
 	c->host_timing = getenv("NTC_HOST_TIMING") && atoi(getenv("NTC_HOST_TIMING")) != 0;
-	c->pad_ragged = getenv("NTC_PAD") && atoi(getenv("NTC_PAD")) != 0;
+	c->pad_ragged = !(getenv("NTC_PAD") && atoi(getenv("NTC_PAD")) == 0);
 	if (getenv("NTC_SCAN_PREFETCH"))
 		c->scan_prefetch = (unsigned)atoi(getenv("NTC_SCAN_PREFETCH"));
 	if (getenv("NTC_CHUNK_WAVES"))
 		c->chunk_waves = (unsigned)atoi(getenv("NTC_CHUNK_WAVES"));
+	if (getenv("NTC_MULTIK_CHUNK_MB"))
+		c->multik_chunk_mb = (unsigned)atoi(getenv("NTC_MULTIK_CHUNK_MB"));
 	if (!hll_bits && (rc = pool_create(c)))
 		return fail(rc);
 	for (int i = 0; i < NBUF; i++) {
@@ -1071,6 +1102,7 @@ void ntc_destroy(ntc_ctx* c)
 		if (rs.done) cudaEventDestroy(rs.done);
 	}
 	if (c->d_tile_info) cudaFree(c->d_tile_info);
+	if (c->d_offchk) cudaFree(c->d_offchk);
 	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
 	if (c->own_hll && c->d_hll) cudaFree(c->d_hll);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1080,6 +1112,9 @@ void ntc_destroy(ntc_ctx* c)
 
 int ntc_reset(ntc_ctx* c)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	int rc;
@@ -1098,20 +1133,24 @@ int ntc_reset(ntc_ctx* c)
 	CK(cudaMemsetAsync(c->d_f1, 0, NTC_MAX_K * sizeof(unsigned long long), c->stream));
 	{ // the hit groups' saved open / spare blocks belong to the old log: invalidate their generation words
 		const ntc::pl::Pool& P = c->pool;
-		const size_t pitch = (1 + 5 * (size_t)P.nbins) * sizeof(uint32_t);
-		CK(cudaMemset2DAsync(P.gstate, pitch, 0, sizeof(uint32_t), (size_t)c->nK * P.max_groups, c->stream));
+		const size_t pitch = ntc::pl::gstate_row(P.nbins) * sizeof(uint32_t);
+		CK(cudaMemset2DAsync(P.gstate, pitch, 0, 2 * sizeof(uint32_t), (size_t)c->nK * P.max_groups, c->stream));
 	}
-	c->pool.epoch = (c->pool.epoch + 1) & 0xFFFFu; // (and date the new ones differently)
+	c->pool.epoch++; // (and date the new ones differently)
 	if (c->pool.epoch == 0)
 		c->pool.epoch = 1;
 	c->totals_overridden = false;
 	c->pending = true;
 	c->partial = false;
+	c->h_nblk.clear();
 	return NTC_OK;
 }
 
 int ntc_set_gap(ntc_ctx* c, unsigned gap)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	SKETCH_ONLY(c, "ntc_set_gap");
@@ -1135,6 +1174,9 @@ int ntc_set_gap(ntc_ctx* c, unsigned gap)
 
 int ntc_set_kernel(ntc_ctx* c, int kernel)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || kernel < NTC_KERNEL_AUTO || kernel > NTC_KERNEL_BITSLICE)
 		return set_err(NTC_EINVAL, "ntc_set_kernel: bad argument");
 	c->kernel = kernel;
@@ -1144,6 +1186,9 @@ int ntc_set_kernel(ntc_ctx* c, int kernel)
 int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec, uint32_t stride_words,
     uint64_t* ticket)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || (!words && n_words) || n_rec > 0xFFFFFFF0ull || n_words > 0xFFFFFFF0ull)
 		return set_err(NTC_EINVAL, "ntc_submit: bad argument");
 	if (!off && n_rec && (stride_words == 0 || (uint64_t)stride_words * n_rec > n_words))
@@ -1165,6 +1210,7 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 		if (c->host_timing)
 			c->host_span("submit: offset validation loop", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - v0).count());
 	}
+	c->h_nblk.clear(); // a snapshot taken by ntc_log_counts is stale once anything more is logged
 	Stage& s = c->stage[c->next_ticket % NBUF];
 	// the slot's previous batch must have been consumed by its kernels before we overwrite it
 	HT(c, "submit: wait for the slot (consumed)", CK(cudaEventSynchronize(s.consumed)));
@@ -1215,6 +1261,9 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 int ntc_submit_device(ntc_ctx* c, const uint32_t* d_words, size_t n_words, const uint32_t* d_off, size_t n_rec,
     uint32_t stride_words)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || (!d_words && n_words) || n_rec > 0xFFFFFFF0ull || n_words > 0xFFFFFFF0ull)
 		return set_err(NTC_EINVAL, "ntc_submit_device: bad argument");
 	if (!d_off && n_rec && (stride_words == 0 || (uint64_t)stride_words * n_rec > n_words))
@@ -1226,12 +1275,32 @@ int ntc_submit_device(ntc_ctx* c, const uint32_t* d_words, size_t n_words, const
 	int rc;
 	if ((rc = use_device(c)))
 		return rc;
-	ntc::BatchView b{ d_words, d_off, stride_words, (uint32_t)n_rec, n_words, 0, 0 };
-	return run_batch(c, b, d_off ? false : single_piece_records(c, stride_words));
+	c->h_nblk.clear(); // a snapshot taken by ntc_log_counts is stale once anything more is logged
+	uint32_t max_rec_words = 0;
+	if (d_off) {
+		// what ntc_check_offsets does for host batches, on the device: validity of the offsets and the longest record (the
+		// host needs it to choose the kernels: short records are padded for the pipeline, long ones re-tiled)
+		if (!c->d_offchk)
+			CK(cudaMalloc((void**)&c->d_offchk, 2 * sizeof(uint32_t)));
+		uint32_t h[2] = { 0, 0 };
+		CK(cudaMemsetAsync(c->d_offchk, 0, sizeof h, c->stream));
+		CK(ntc::launch_check_offsets(d_off, (uint32_t)n_rec, n_words, c->d_offchk, c->n_sm, c->stream));
+		CK(cudaMemcpyAsync(h, c->d_offchk, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		c->n_launches++;
+		if (h[1])
+			return set_err(NTC_EINVAL, "ntc_submit_device: offsets must start at 0, be non-decreasing and end within n_words");
+		max_rec_words = h[0];
+	}
+	ntc::BatchView b{ d_words, d_off, stride_words, (uint32_t)n_rec, n_words, 0, max_rec_words };
+	return run_batch(c, b, d_off ? single_piece_records(c, max_rec_words) : single_piece_records(c, stride_words));
 }
 
 int ntc_wait(ntc_ctx* c, uint64_t ticket)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	if (ticket == 0)
@@ -1246,6 +1315,9 @@ int ntc_wait(ntc_ctx* c, uint64_t ticket)
 
 int ntc_sync(ntc_ctx* c)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	int rc;
@@ -1260,6 +1332,9 @@ int ntc_sync(ntc_ctx* c)
 
 int ntc_flush(ntc_ctx* c)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	int rc;
@@ -1272,6 +1347,9 @@ int ntc_flush(ntc_ctx* c)
 /* ---- hit-log exchange (multi-GPU sparse reduction) ------------------------------------------------------ */
 int ntc_log_info(ntc_ctx* c, uint32_t* n_slices, uint64_t* counters_per_slice, uint32_t* entries_per_block)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	SKETCH_ONLY(c, "ntc_log_info");
@@ -1283,6 +1361,9 @@ int ntc_log_info(ntc_ctx* c, uint32_t* n_slices, uint64_t* counters_per_slice, u
 
 int ntc_log_counts(ntc_ctx* c, uint32_t* nblk, int* exportable, uint32_t* pool_info)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !nblk || !exportable)
 		return set_err(NTC_EINVAL, "ntc_log_counts: bad argument");
 	SKETCH_ONLY(c, "ntc_log_counts");
@@ -1329,8 +1410,11 @@ static int upload_runs(ntc_ctx* c, const std::vector<uint32_t>& runs, const uint
 
 int ntc_log_export(ntc_ctx* c, const uint32_t* slices, uint32_t n, void* d_blocks)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || (n && !slices) || c->h_nblk.size() != c->pool.n_slices)
-		return set_err(NTC_EINVAL, "ntc_log_export: bad argument (call ntc_log_counts first)");
+		return set_err(c && c->h_nblk.empty() ? NTC_ESTATE : NTC_EINVAL, "ntc_log_export: bad argument, or no current ntc_log_counts snapshot (a batch, flush or reset since invalidates it)");
 	SKETCH_ONLY(c, "ntc_log_export");
 	int rc;
 	if ((rc = use_device(c)))
@@ -1360,8 +1444,11 @@ int ntc_log_export(ntc_ctx* c, const uint32_t* slices, uint32_t n, void* d_block
 
 int ntc_log_import(ntc_ctx* c, const void* d_blocks, uint32_t n_blocks, const uint32_t* runs_in, uint32_t n_runs)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || (n_blocks && (!d_blocks || !runs_in)) || c->h_nblk.size() != c->pool.n_slices)
-		return set_err(NTC_EINVAL, "ntc_log_import: bad argument (call ntc_log_counts first)");
+		return set_err(c && c->h_nblk.empty() ? NTC_ESTATE : NTC_EINVAL, "ntc_log_import: bad argument, or no current ntc_log_counts snapshot (a batch, flush or reset since invalidates it)");
 	SKETCH_ONLY(c, "ntc_log_import");
 	if (n_blocks == 0)
 		return NTC_OK;
@@ -1404,6 +1491,9 @@ int ntc_log_import(ntc_ctx* c, const void* d_blocks, uint32_t n_blocks, const ui
 /* ---- multi-GPU reduction over peer memory (one process per GPU, one node) ------------------------------------------ */
 int ntc_peer_export(ntc_ctx* c, void* handles)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !handles)
 		return set_err(NTC_EINVAL, "ntc_peer_export: bad argument");
 	SKETCH_ONLY(c, "ntc_peer_export");
@@ -1420,6 +1510,9 @@ int ntc_peer_export(ntc_ctx* c, void* handles)
 
 int ntc_peer_attach(ntc_ctx* c, int world, int rank, const void* all_handles)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !all_handles || world < 1 || world > (int)ntc::pl::kMaxPeers || rank < 0 || rank >= world)
 		return set_err(NTC_EINVAL, "ntc_peer_attach: bad argument (world 1..%u)", ntc::pl::kMaxPeers);
 	SKETCH_ONLY(c, "ntc_peer_attach");
@@ -1457,6 +1550,9 @@ int ntc_peer_attach(ntc_ctx* c, int world, int rank, const void* all_handles)
 
 int ntc_peer_attach_contexts(ntc_ctx* c, int world, int rank, ntc_ctx* const* all)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !all || world < 1 || world > (int)ntc::pl::kMaxPeers || rank < 0 || rank >= world || all[rank] != c)
 		return set_err(NTC_EINVAL, "ntc_peer_attach_contexts: bad argument (world 1..%u, all[rank] must be the context itself)", ntc::pl::kMaxPeers);
 	SKETCH_ONLY(c, "ntc_peer_attach_contexts");
@@ -1491,6 +1587,9 @@ int ntc_peer_attach_contexts(ntc_ctx* c, int world, int rank, ntc_ctx* const* al
 
 int ntc_log_status_device(ntc_ctx* c, void* d_status)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !d_status)
 		return set_err(NTC_EINVAL, "ntc_log_status_device: bad argument");
 	SKETCH_ONLY(c, "ntc_log_status_device");
@@ -1504,6 +1603,9 @@ int ntc_log_status_device(ntc_ctx* c, void* d_status)
 
 int ntc_reduce_owned(ntc_ctx* c, const void* d_status, void* d_p_hist)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !d_p_hist)
 		return set_err(NTC_EINVAL, "ntc_reduce_owned: bad argument");
 	SKETCH_ONLY(c, "ntc_reduce_owned");
@@ -1549,6 +1651,9 @@ int ntc_reduce_owned(ntc_ctx* c, const void* d_status, void* d_p_hist)
 
 int ntc_stream_sync(ntc_ctx* c)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	int rc;
@@ -1560,6 +1665,9 @@ int ntc_stream_sync(ntc_ctx* c)
 
 int ntc_flush_slices(ntc_ctx* c, const uint8_t* owned)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !owned)
 		return set_err(NTC_EINVAL, "ntc_flush_slices: bad argument");
 	SKETCH_ONLY(c, "ntc_flush_slices");
@@ -1594,6 +1702,9 @@ int ntc_flush_slices(ntc_ctx* c, const uint8_t* owned)
 
 int ntc_hist_slices(ntc_ctx* c, const uint8_t* owned, uint32_t* p_hist, void* d_p_hist)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !owned || (!p_hist && !d_p_hist))
 		return set_err(NTC_EINVAL, "ntc_hist_slices: bad argument");
 	SKETCH_ONLY(c, "ntc_hist_slices");
@@ -1635,6 +1746,9 @@ int ntc_hist_slices(ntc_ctx* c, const uint8_t* owned, uint32_t* p_hist, void* d_
 
 int ntc_counters_device(ntc_ctx* c, void** d_counters, size_t* n_counters)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	SKETCH_ONLY(c, "ntc_counters_device");
@@ -1650,6 +1764,9 @@ int ntc_counters_device(ntc_ctx* c, void** d_counters, size_t* n_counters)
 
 int ntc_totals(ntc_ctx* c, uint64_t* totKmer)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !totKmer)
 		return set_err(NTC_EINVAL, "ntc_totals: bad argument");
 	if (c->totals_overridden) {
@@ -1668,6 +1785,9 @@ int ntc_totals(ntc_ctx* c, uint64_t* totKmer)
 
 int ntc_totals_nosync(ntc_ctx* c, uint64_t* totKmer)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !totKmer)
 		return set_err(NTC_EINVAL, "ntc_totals_nosync: bad argument");
 	int rc;
@@ -1683,6 +1803,9 @@ int ntc_totals_nosync(ntc_ctx* c, uint64_t* totKmer)
 
 int ntc_set_totals(ntc_ctx* c, const uint64_t* totKmer)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !totKmer)
 		return set_err(NTC_EINVAL, "ntc_set_totals: bad argument");
 	memcpy(c->totals, totKmer, c->nK * sizeof(uint64_t));
@@ -1692,6 +1815,9 @@ int ntc_set_totals(ntc_ctx* c, const uint64_t* totKmer)
 
 int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_hist)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	SKETCH_ONLY(c, "ntc_finish");
@@ -1743,6 +1869,9 @@ int ntc_finish(ntc_ctx* c, uint16_t* t_Counter, uint64_t* totKmer, uint32_t* p_h
 // ---- nthll mode --------------------------------------------------------------------------------------------
 int ntc_hll_registers_device(ntc_ctx* c, void** d_regs, size_t* n_regs)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	HLL_ONLY(c, "ntc_hll_registers_device");
@@ -1753,6 +1882,9 @@ int ntc_hll_registers_device(ntc_ctx* c, void** d_regs, size_t* n_regs)
 
 int ntc_hll_finish(ntc_ctx* c, uint8_t* regs, uint64_t* totKmer)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	HLL_ONLY(c, "ntc_hll_finish");
@@ -1770,6 +1902,9 @@ int ntc_hll_finish(ntc_ctx* c, uint8_t* regs, uint64_t* totKmer)
 
 int ntc_hist_range(ntc_ctx* c, const void* d_counters, uint64_t first, uint64_t n, uint32_t* p_hist)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !d_counters || !p_hist || first + n > c->n_counters)
 		return set_err(NTC_EINVAL, "ntc_hist_range: bad argument");
 	SKETCH_ONLY(c, "ntc_hist_range");
@@ -1812,6 +1947,9 @@ void ntc_host_free(void* p)
 int ntc_gen_packed_device(ntc_ctx* c, uint64_t seed, uint64_t first, uint64_t n, uint32_t L, int mode, uint64_t U,
     uint32_t stride_words, uint32_t* d_words)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !d_words || stride_words < 1 + (L + 15) / 16 || mode < 0 || mode > 1)
 		return set_err(NTC_EINVAL, "ntc_gen_packed_device: bad argument");
 	int rc;
@@ -1824,6 +1962,9 @@ int ntc_gen_packed_device(ntc_ctx* c, uint64_t seed, uint64_t first, uint64_t n,
 
 int ntc_stats(ntc_ctx* c, uint64_t* n_launches, uint64_t* n_batches)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	if (n_launches) *n_launches = c->n_launches;
@@ -1833,6 +1974,9 @@ int ntc_stats(ntc_ctx* c, uint64_t* n_launches, uint64_t* n_batches)
 
 int ntc_stage_times(ntc_ctx* c, double* ms3)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c || !ms3)
 		return set_err(NTC_EINVAL, "ntc_stage_times: bad argument");
 	for (int i = 0; i < 3; i++) {
@@ -1844,6 +1988,9 @@ int ntc_stage_times(ntc_ctx* c, double* ms3)
 
 int ntc_kernel_time(ntc_ctx* c, double* ms_total, uint64_t* n_timed)
 {
+	std::unique_lock<std::recursive_mutex> lk_;
+	if (c)
+		lk_ = std::unique_lock<std::recursive_mutex>(c->mu);
 	if (!c)
 		return set_err(NTC_EINVAL, "null context");
 	if (ms_total) *ms_total = c->kernel_ms;

@@ -30,6 +30,8 @@ constexpr uint32_t kTileDefer = 0x80000000u;  // fused kernel: tile_info = kTile
                                               // while the sketch was not materialised: second pass after the conditional flush)
 constexpr uint32_t kFusedMaxPos = 2048;       // fused kernel: k-mer starts per record (11 bits of a 16-bit candidate word)
 constexpr uint32_t kFusedWarps = 8;
+// words per saved state of a hit group / fused-kernel warp: [epoch][flush count + 1][5 x nbins]
+__host__ __device__ constexpr size_t gstate_row(uint32_t nbins) { return 2 + 5 * (size_t)nbins; }
 constexpr uint32_t kTileRecs = 1024;
 constexpr uint32_t kMaxBins = 64;             // slices per k
 constexpr uint32_t kQueueCap = 4096;          // candidates per round of a hit group
@@ -50,8 +52,8 @@ struct Pool {                    // device pointers + geometry, passed by value
 	uint32_t* ctl;               // [CTL_WORDS]
 	unsigned long long* cand;    // candidate k-mers of the batch being processed (upper bound of its log entries)
 	uint32_t n_blocks, slice_cap, n_slices, nbins, bin_shift, rBits, nK;
-	uint32_t* gstate;            // [nK][max_groups][1 + 5 * nbins]: open / spare blocks of every hit group, kept over launches
-	uint32_t max_groups, epoch;  // epoch: bumped by ntc_reset (host); with CTL_FLUSHES it dates gstate
+	uint32_t* gstate;            // [nK][max_groups][gstate_row(nbins)]: open / spare blocks of every hit group, kept over launches
+	uint32_t max_groups, epoch;  // epoch: bumped by ntc_reset (host); with the full 32-bit CTL_FLUSHES it dates gstate
 	uint32_t ahead;              // apply kernel: slices the stagers may run ahead of the appliers (L2 footprint)
 };
 

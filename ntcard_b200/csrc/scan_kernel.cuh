@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 #pragma unroll
 			for (int s = 0; s < 32; s++)
 				if ((vmask >> s) & 1u) {
-					cnt += v[s].x >= (uint32_t)k ? v[s].x - (uint32_t)k + 1u : 0u;
-					mx = max(mx, v[s].x);
+					const uint32_t ls = min(v[s].x, (stride - 1u) * 16u); // a corrupt length word counts as the record's capacity
+					cnt += ls >= (uint32_t)k ? ls - (uint32_t)k + 1u : 0u;
+					mx = max(mx, ls);
 				}
 			f1_local += cnt;
 			if (!L.mixed_ok || L.start_limit) {

@@ -19,6 +19,17 @@ __device__ __forceinline__ uint64_t rec_offset(const uint32_t* __restrict__ off,
 	return off ? (uint64_t)__ldg(off + rec) : (uint64_t)rec * stride;
 }
 
+// The record's length word, clamped to what its words can hold: a corrupt length (larger than 16 x (record words - 1)) must not
+// send a kernel past the record -- the scan kernel clamps the same way (scan_kernel.cuh), so all paths agree on malformed input.
+__device__ __forceinline__ uint32_t rec_len(const uint32_t* __restrict__ words, const uint32_t* __restrict__ off, uint32_t stride, uint32_t rec)
+{
+	const uint64_t o = rec_offset(off, stride, rec);
+	const uint64_t cap = off ? (uint64_t)__ldg(off + rec + 1) - o : stride;
+	const uint64_t room = cap ? (cap - 1) * 16 : 0;
+	const uint32_t len = __ldg(words + o);
+	return (uint64_t)len > room ? (uint32_t)room : len;
+}
+
 __global__ void piece_count_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ off, uint32_t stride,
     uint32_t n_rec, uint32_t kmin, uint32_t* __restrict__ n_pieces /* [n_rec + 1] */)
 {
@@ -27,7 +38,7 @@ __global__ void piece_count_kernel(const uint32_t* __restrict__ words, const uin
 		return;
 	uint32_t np = 0;
 	if (i < n_rec) {
-		uint32_t len = __ldg(words + rec_offset(off, stride, i));
+		uint32_t len = rec_len(words, off, stride, i);
 		if (len >= kmin)
 			np = (len - kmin + 1 + PIECE_STARTS - 1) / PIECE_STARTS;
 	}
@@ -60,7 +71,7 @@ __global__ void retile_count_kernel(const uint32_t* __restrict__ words, const ui
 		return;
 	uint32_t nf = 0, ht = 0, tw = 0;
 	if (i < n_rec) {
-		const uint32_t len = __ldg(words + __ldg(off + i));
+		const uint32_t len = rec_len(words, off, 0, i);
 		nf = len >= Lp ? (len - Lp) / D + 1 : 0;
 		const uint32_t tl = len - nf * D;
 		if (tl >= kmin && len >= kmin) {
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(256) retile_fill_kernel(const uint32_t* __rest
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	for (uint32_t i = warp; i < n_rec; i += nwarps) {
 		const uint32_t* r = words + __ldg(off + i);
-		const uint32_t len = __ldg(r), nw = (len + 15) / 16;
+		const uint32_t len = rec_len(words, off, 0, i), nw = (len + 15) / 16;
 		const uint32_t f0 = full_first[i], nf = full_first[i + 1] - f0;
 		uint32_t* ou = out_uniform + (size_t)f0 * stride;
 		for (uint32_t x = lane; x < nf * stride; x += 32) {
@@ -151,7 +162,7 @@ __global__ void __launch_bounds__(256) roll64_kernel(const uint32_t* __restrict_
 			a = (piece - piece_first[rec]) * PIECE_STARTS;
 		}
 		const uint32_t* r = words + rec_offset(off, stride, rec);
-		const uint32_t len = __ldg(r);
+		const uint32_t len = rec_len(words, off, stride, rec);
 		for (uint32_t ki = 0; ki < sp.nK; ki++) {
 			if (!((kmask >> ki) & 1u))
 				continue;
@@ -353,6 +364,34 @@ cudaError_t launch_pad_ragged(const uint32_t* d_in, const uint32_t* d_off, uint3
 	if (n == 0)
 		return cudaSuccess;
 	pad_ragged_kernel<<<grid_for(n, 256, (unsigned)n_sm * 32u), 256, 0, st>>>(d_in, d_off, stride_out, n, d_out);
+	return cudaGetLastError();
+}
+
+// ntc_check_offsets on the device, for ragged batches that are already resident there: out[0] = words of the longest record,
+// out[1] != 0 when the offsets are not a non-decreasing sequence from 0 to at most n_words (out zeroed by the caller)
+__global__ void __launch_bounds__(256) check_offsets_kernel(const uint32_t* __restrict__ off, uint32_t n_rec, uint64_t n_words, uint32_t* __restrict__ out)
+{
+	uint32_t mx = 0, bad = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
+		const uint32_t a = __ldg(off + i), b = __ldg(off + i + 1);
+		if (b < a || (uint64_t)b > n_words || (i == 0 && a != 0))
+			bad = 1;
+		else
+			mx = max(mx, b - a);
+	}
+	mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+	bad = __reduce_max_sync(0xFFFFFFFFu, bad);
+	if ((threadIdx.x & 31u) == 0) {
+		if (mx)
+			atomicMax(out, mx);
+		if (bad)
+			atomicMax(out + 1, 1u);
+	}
+}
+
+cudaError_t launch_check_offsets(const uint32_t* d_off, uint32_t n_rec, uint64_t n_words, uint32_t* d_out, int n_sm, cudaStream_t st)
+{
+	check_offsets_kernel<<<grid_for(n_rec, 256, (unsigned)n_sm * 8u), 256, 0, st>>>(d_off, n_rec, n_words, d_out);
 	return cudaGetLastError();
 }
 

@@ -552,6 +552,104 @@ def test_hit_log_exchange_between_two_contexts_on_one_gpu(oracle):
         assert np.array_equal(t.reshape(-1), want) and np.array_equal(f1b, wf1)
 
 
+@pytest.mark.parametrize("name,n,L,kList,sBits,S,mode", [
+    ("config 2 (full)", 10_000_000, 150, [32], 7, 1, 0),
+    ("config 3 (10M-read prefix)", 10_000_000, 150, [32, 64, 96, 128], 7, 2, 0),
+    ("config 4 (10M-read prefix of GPU 0's shard)", 10_000_000, 150, [64], 11, 3, 0),
+    ("config 5 (1M-read prefix, with N)", 1_000_000, 10_000, [31], 11, 4, 2),
+])
+def test_at_size_against_the_reference(oracle, name, n, L, kList, sBits, S, mode):
+    """BASELINE configs at size (SURVEY 8d prefixes) against the UNMODIFIED reference's own ntRead (oracle/_ref, OpenMP over
+    reads on the host cores; the oracle port where _ref was not built): r = 27 as in ntcard.cpp:57, the device's counter-value
+    histogram must equal the bincount of the reference's uint16 sketch, table by table, and F1 must be equal."""
+    import os
+    from oracle.pyoracle import Reference
+    rBits, threads = 27, os.cpu_count() or 1
+    nK, rB = len(kList), 1 << 27
+    want_p = np.zeros((nK, 2, 65536), dtype=np.int64)
+    want_f1 = np.zeros(nK, dtype=np.uint64)
+    ref = Reference() if Reference.available() else None
+    want_sk = np.zeros(nK * 2 * rB, dtype=np.uint16)
+    chunk = 2_000_000 if L <= 300 else 100_000          # reads per host chunk (ASCII in RAM: <= 1 GB)
+    with nt.Sketch(kList, rBits=rBits, sBits=sBits) as sk:
+        if ref is not None:
+            ref.set_opts(rBits, sBits, nK)
+        for c0 in range(0, n, chunk):
+            nc = min(chunk, n - c0)
+            reads = oracle.gen_reads(S, c0, nc, L, mode, 0)
+            off = np.arange(nc + 1, dtype=np.uint64) * L
+            tot = np.zeros(nK, dtype=np.uint64)
+            if ref is not None:
+                ref.ntread_batch(reads, off, kList, want_sk, tot, threads)
+            else:
+                oracle.ntread_batch(reads, off, kList, rBits, sBits, want_sk, tot, threads)
+            want_f1 += tot
+            if mode == 2:                                # reads with N: the documented host route (packer -> ragged batch)
+                w, o = nt.pack_chars(reads, off, min_len=min(kList))
+                sk.submit(w, o)
+            else:                                        # uniform reads: the same reads from the device generator
+                stride = nt.stride_words(L)
+                sk.submit(nt.gen_packed(S, c0, nc, L, 0, 0, stride), None, nc, stride)
+            del reads
+        _, f1, p = sk.finish(counters=False, hist=True)
+    for t in range(2 * nK):
+        want_p.reshape(-1, 65536)[t] = np.bincount(want_sk[t * rB:(t + 1) * rB], minlength=65536)
+    assert np.array_equal(f1, want_f1), (name, f1, want_f1)
+    assert np.array_equal(p.astype(np.int64), want_p), name
+    assert int(want_p[:, :, 1:].sum()) > 0
+
+
+def test_device_resident_ragged_batches(oracle):
+    """Ragged batches that already live in device memory (ntc_submit_device with offsets): the library finds the longest
+    record and checks the offsets ON the device, then short records are padded for the pipeline and long ones re-tiled --
+    same result as the oracle either way; broken offsets are refused."""
+    import torch
+    kList, rBits, sBits = [31, 64], 22, 7
+    for L, n in ((150, 30000), (6000, 600)):
+        a = oracle.gen_reads(72, 0, n, L, 2, 0)
+        reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+        want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+        w, off = nt.pack_reads(reads, min_len=min(kList))
+        dw = torch.from_numpy(w.view(np.int32)).cuda()
+        do = torch.from_numpy(off.view(np.int32)).cuda()
+        with nt.Sketch(kList, rBits=rBits, sBits=sBits) as sk:
+            sk.submit_device(dw.data_ptr(), len(w), len(off) - 1, 0, d_off=do.data_ptr())
+            t, f1, _ = sk.finish(counters=True, hist=False)
+            assert np.array_equal(f1, wf1) and np.array_equal(t.reshape(-1), want), L
+            bad = off.copy()
+            bad[len(bad) // 2] = bad[-1] + 7          # not monotonic / past the end
+            db = torch.from_numpy(bad.view(np.int32)).cuda()
+            with pytest.raises(nt.NtcError):
+                sk.submit_device(dw.data_ptr(), len(w), len(off) - 1, 0, d_off=db.data_ptr())
+
+
+def test_concurrent_submit_from_several_threads(oracle):
+    """ntRead is called concurrently on one shared sketch (one OpenMP thread per file, ntcard.cpp:445); so may ntc_submit be:
+    four host threads submit interleaved batches (ragged and uniform) to ONE context; the sketch must equal the oracle's."""
+    import threading
+    n, L, kList, rBits, sBits = 40000, 150, [32, 64], 22, 7
+    a = oracle.gen_reads(71, 0, n, L, 2, 0)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+    errors = []
+    with nt.Sketch(kList, rBits=rBits, sBits=sBits) as sk:
+        def worker(t):
+            try:
+                for b0 in range(t * 500, n, 4 * 500):
+                    sk.submit_reads(reads[b0:b0 + 500])
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        assert not errors, errors
+        t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1)
+    assert np.array_equal(t.reshape(-1), want)
+
+
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_peer_memory_reduction_between_contexts_on_one_gpu(oracle, world):
     """The multi-GPU reduction over peer memory (ntc_log_status_device / ntc_reduce_owned) exercised on ONE device: `world`
