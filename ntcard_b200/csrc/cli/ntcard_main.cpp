@@ -13,9 +13,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <getopt.h>
 #include <iomanip>
 #include <iostream>
+#include <future>
 #include <mutex>
 #include <sstream>
 #include <string>
@@ -223,14 +225,21 @@ int main(int argc, char** argv)
 			          << std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() << " s since start\n";
 	};
 	lap("options parsed");
-	ntc_ctx* ctx = NULL;
-	if (ntc_create(&ctx, kList.data(), (unsigned)kList.size(), opt::rBits, opt::sBits, opt::gpu, NULL, NULL))
-		die_ntc("cannot create the device sketch");
-	if (opt::kernel != NTC_KERNEL_AUTO && ntc_set_kernel(ctx, opt::kernel))
-		die_ntc("kernel");
-	if (opt::gap != 0 && ntc_set_gap(ctx, opt::gap)) // stRead instead of ntRead, ntcard.cpp:184-185, 204-205, 231-232
-		die_ntc("gap seed");
-	lap("device context created");
+	// The device context (CUDA initialisation + the sketch, ntcard.cpp:437-439) is created on a side thread WHILE the readers
+	// already parse and pack: they only need it when their first batch is full.
+	std::promise<ntc_ctx*> ctx_promise;
+	std::shared_future<ntc_ctx*> ctx_future = ctx_promise.get_future().share();
+	std::thread creator([&]() {
+		ntc_ctx* c = NULL;
+		if (ntc_create(&c, kList.data(), (unsigned)kList.size(), opt::rBits, opt::sBits, opt::gpu, NULL, NULL))
+			die_ntc("cannot create the device sketch");
+		if (opt::kernel != NTC_KERNEL_AUTO && ntc_set_kernel(c, opt::kernel))
+			die_ntc("kernel");
+		if (opt::gap != 0 && ntc_set_gap(c, opt::gap)) // stRead instead of ntRead, ntcard.cpp:184-185, 204-205, 231-232
+			die_ntc("gap seed");
+		lap("device context created (side thread)");
+		ctx_promise.set_value(c);
+	});
 	unsigned kmin = kList[0];
 	for (unsigned k : kList)
 		kmin = k < kmin ? k : kmin;
@@ -241,10 +250,13 @@ int main(int argc, char** argv)
 	unsigned nthreads = opt::nThrd < 1 ? 1 : opt::nThrd;
 	if (nthreads > inFiles.size())
 		nthreads = (unsigned)inFiles.size();
+	// -t larger than the number of files: the spare threads parse pieces of the same (uncompressed FASTQ / FASTA) file
+	const unsigned per_file = (opt::nThrd < 1 ? 1u : opt::nThrd) / (nthreads ? nthreads : 1u);
+	const std::function<ntc_ctx*()> ctx_source = [ctx_future]() { return ctx_future.get(); };
 	std::atomic<int> worker_id(0);
 	auto worker = [&]() {
 		const auto w0 = std::chrono::steady_clock::now();
-		ntcb::BatchSubmitter sub(ctx, kmin, &submit_mu);
+		ntcb::BatchSubmitter sub([ctx_future]() { return ctx_future.get(); }, kmin, &submit_mu);
 		const auto w1 = std::chrono::steady_clock::now();
 		struct Report {
 			bool on;
@@ -265,7 +277,10 @@ int main(int argc, char** argv)
 			size_t i = next_file.fetch_add(1);
 			if (i >= inFiles.size())
 				break;
-			if (!ntcb::read_file(inFiles[i], sub)) {
+			bool handled = false;
+			if (per_file > 1)
+				ntcb::read_file_parallel(inFiles[i], ctx_source, kmin, &submit_mu, per_file, &handled);
+			if (!handled && !ntcb::read_file(inFiles[i], sub)) {
 				std::cerr << "Error in reading file: " << inFiles[i] << std::endl; // ntcard.cpp:459-462
 				exit(EXIT_FAILURE);
 			}
@@ -283,6 +298,8 @@ int main(int argc, char** argv)
 			t.join();
 	}
 
+	creator.join();
+	ntc_ctx* ctx = ctx_future.get();
 	lap("files read, packed and submitted");
 	std::vector<uint64_t> totalKmers(kList.size(), 0);
 	std::vector<uint32_t> p_hist(kList.size() * 2 * 65536);

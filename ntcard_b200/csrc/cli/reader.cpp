@@ -5,7 +5,12 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <iostream>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 #include <vector>
 
 namespace ntcb {
@@ -114,12 +119,30 @@ bool LineReader::next(const char** line, size_t* len)
 BatchSubmitter::BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer)
     : ctx_(ctx), min_len_(min_len), mu_(submit_mu)
 {
+	init(words_per_buffer, true);
+}
+
+BatchSubmitter::BatchSubmitter(std::function<ntc_ctx*()> ctx_source, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer)
+    : ctx_(nullptr), ctx_source_(std::move(ctx_source)), min_len_(min_len), mu_(submit_mu)
+{
+	init(words_per_buffer, false); // pageable: pinning would wait for the CUDA initialisation this constructor is meant to overlap
+}
+
+void BatchSubmitter::init(size_t words_per_buffer, bool pinned)
+{
 	for (auto& b : uni_.buf)
-		alloc(b, words_per_buffer, 1);
+		alloc(b, words_per_buffer, 1, pinned);
 	for (auto& b : rag_.buf)
-		alloc(b, words_per_buffer / 4, words_per_buffer / 16);
+		alloc(b, words_per_buffer / 4, words_per_buffer / 16, pinned);
 	tmp_words_.resize(1 << 16);
 	tmp_off_.resize((1 << 14) + 1);
+}
+
+ntc_ctx* BatchSubmitter::ctx()
+{
+	if (!ctx_ && ctx_source_)
+		ctx_ = ctx_source_(); // blocks until the context exists
+	return ctx_;
 }
 
 BatchSubmitter::~BatchSubmitter()
@@ -136,14 +159,21 @@ static void die_ntc()
 	exit(EXIT_FAILURE);
 }
 
-void BatchSubmitter::alloc(Buf& b, size_t words, size_t recs)
+void BatchSubmitter::alloc(Buf& b, size_t words, size_t recs, bool pinned)
 {
-	b.words = (uint32_t*)ntc_host_alloc(words * sizeof(uint32_t));
-	b.off = (uint32_t*)ntc_host_alloc((recs + 1) * sizeof(uint32_t));
+	if (pinned) {
+		b.words = (uint32_t*)ntc_host_alloc(words * sizeof(uint32_t));
+		b.off = (uint32_t*)ntc_host_alloc((recs + 1) * sizeof(uint32_t));
+	} else {
+		b.words = (uint32_t*)malloc(words * sizeof(uint32_t));
+		b.off = (uint32_t*)malloc((recs + 1) * sizeof(uint32_t));
+	}
 	if (!b.words || !b.off) {
-		std::cerr << "ntCard: cannot allocate pinned host memory: " << ntc_last_error() << "\n";
+		std::cerr << "ntCard: cannot allocate host memory: " << (pinned ? ntc_last_error() : "malloc failed") << "\n";
 		exit(EXIT_FAILURE);
 	}
+	b.pinned = pinned;
+	b.submits = 0;
 	b.cap_words = words;
 	b.cap_rec = recs;
 	b.n_words = b.n_rec = 0;
@@ -152,8 +182,13 @@ void BatchSubmitter::alloc(Buf& b, size_t words, size_t recs)
 
 void BatchSubmitter::release(Buf& b)
 {
-	ntc_host_free(b.words);
-	ntc_host_free(b.off);
+	if (b.pinned) {
+		ntc_host_free(b.words);
+		ntc_host_free(b.off);
+	} else {
+		free(b.words);
+		free(b.off);
+	}
 	b.words = b.off = nullptr;
 }
 
@@ -166,11 +201,22 @@ void BatchSubmitter::flush_stream(Stream& st)
 	} timer{ &submit_seconds_ };
 	Buf& b = st.buf[st.cur];
 	if (b.n_rec > 0) {
-		std::lock_guard<std::mutex> lk(*mu_);
-		const int rc = st.stride ? ntc_submit(ctx_, b.words, b.n_words, NULL, b.n_rec, st.stride, &b.ticket)
-		                         : ntc_submit(ctx_, b.words, b.n_words, b.off, b.n_rec, 0, &b.ticket);
-		if (rc)
-			die_ntc();
+		ntc_ctx* c = ctx();
+		{
+			std::lock_guard<std::mutex> lk(*mu_);
+			const int rc = st.stride ? ntc_submit(c, b.words, b.n_words, NULL, b.n_rec, st.stride, &b.ticket)
+			                         : ntc_submit(c, b.words, b.n_words, b.off, b.n_rec, 0, &b.ticket);
+			if (rc)
+				die_ntc();
+		}
+		if (!b.pinned) {
+			b.ticket = 0; // pageable memory was copied to the library's staging before ntc_submit returned
+			if (++b.submits >= 4) { // a buffer that keeps being reused is worth pinning (DMA straight from it, no staging copy)
+				const size_t w = b.cap_words, r = b.cap_rec;
+				release(b);
+				alloc(b, w, r, true);
+			}
+		}
 	}
 	st.cur ^= 1;
 	Buf& n = st.buf[st.cur];
@@ -207,8 +253,9 @@ void BatchSubmitter::append(Stream& st, const uint32_t* rec, size_t nwords)
 		// a single record larger than an empty buffer (e.g. a chromosome): grow this buffer
 		if (b.ticket && ntc_wait(ctx_, b.ticket))
 			die_ntc();
+		const bool was_pinned = b.pinned;
 		release(b);
-		alloc(b, need + (need >> 2), b.cap_rec);
+		alloc(b, need + (need >> 2), b.cap_rec, was_pinned);
 	}
 	std::cerr << "ntCard: internal error: record does not fit the batch buffer\n";
 	exit(EXIT_FAILURE);
@@ -218,7 +265,7 @@ void BatchSubmitter::add(const char* seq, size_t len)
 {
 	if (len < min_len_)
 		return; // no window fits (ntHashIterator.hpp:61-64)
-	const size_t bound = ntc_pack_bound(1, len);
+	const size_t bound = ntc_pack_bound_k(1, len, min_len_);
 	if (tmp_words_.size() < bound)
 		tmp_words_.resize(bound);
 	const size_t rec_bound = len / (min_len_ ? min_len_ : 1) + 2;
@@ -400,6 +447,151 @@ bool read_file(const std::string& path, BatchSubmitter& sub, bool nthll_rules)
 		return true;
 	}
 	return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Piece {
+	size_t a, b;          // byte range
+	size_t newlines = 0;  // '\n' in [a, b)
+	size_t first_line = 0; // number of newlines before a = index of the line that contains byte a
+};
+
+// FASTQ: sequence lines are the lines with index % 4 == 1 (line 0 = the header the sniffer consumed); hashed iff line index + 2 exists
+void parse_fastq_piece(const char* d, size_t size, const Piece& pc, size_t n_lines, BatchSubmitter& sub)
+{
+	size_t p = pc.a, idx = pc.first_line;
+	if (p > 0 && d[p - 1] != '\n') { // the line containing a started in the previous piece: skip to the next line start
+		const char* nl = (const char*)memchr(d + p, '\n', size - p);
+		if (!nl)
+			return;
+		p = (size_t)(nl - d) + 1;
+		idx++;
+	}
+	while (p < pc.b && p < size) {
+		const char* nl = (const char*)memchr(d + p, '\n', size - p);
+		const size_t e = nl ? (size_t)(nl - d) : size;
+		if ((idx & 3u) == 1u && idx + 2 < n_lines)
+			sub.add(d + p, e - p);
+		if (!nl)
+			return;
+		p = e + 1;
+		idx++;
+	}
+}
+
+// FASTA: a record belongs to the piece in which its '>' line starts; its sequence is every following line up to the next '>' line
+void parse_fasta_piece(const char* d, size_t size, const Piece& pc, BatchSubmitter& sub)
+{
+	size_t p = pc.a;
+	if (p > 0 && d[p - 1] != '\n') {
+		const char* nl = (const char*)memchr(d + p, '\n', size - p);
+		if (!nl)
+			return;
+		p = (size_t)(nl - d) + 1;
+	}
+	std::string seq;
+	bool in_record = false; // inside a record whose header line started in this piece
+	while (p < size) {
+		const char* nl = (const char*)memchr(d + p, '\n', size - p);
+		const size_t e = nl ? (size_t)(nl - d) : size;
+		if (e > p && d[p] == '>') {
+			if (in_record)
+				sub.add(seq.data(), seq.size());
+			if (p >= pc.b) // the next piece's record
+				return;
+			seq.clear();
+			in_record = true;
+		} else if (in_record) {
+			seq.append(d + p, e - p);
+		}
+		if (!nl)
+			break;
+		p = e + 1;
+	}
+	if (in_record)
+		sub.add(seq.data(), seq.size());
+}
+} // namespace
+
+bool read_file_parallel(const std::string& path, const std::function<ntc_ctx*()>& ctx_source, unsigned min_len, std::mutex* submit_mu,
+    unsigned nthreads, bool* handled)
+{
+	*handled = false;
+	if (nthreads < 2 || ends_with(path, ".gz") || ends_with(path, ".Z") || ends_with(path, ".bz2") || ends_with(path, ".xz"))
+		return true;
+	const int fd = open(path.c_str(), O_RDONLY);
+	if (fd < 0)
+		return true; // read_file reports the error the reference's way
+	struct stat st;
+	if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || (size_t)st.st_size < ((size_t)8 << 20) * nthreads) {
+		close(fd);
+		return true;
+	}
+	const size_t size = (size_t)st.st_size;
+	const char* d = (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if (d == MAP_FAILED)
+		return true;
+	madvise((void*)d, size, MADV_SEQUENTIAL);
+	// getftype (ntcard.cpp:105-130) on the first line: only FASTA and FASTQ are cut up; SAM and anything else go the serial way
+	int type = -1;
+	if (d[0] == '>') {
+		type = 1;
+	} else if (d[0] == '@') {
+		const char a = size > 1 ? d[1] : 0, b = size > 2 ? d[2] : 0;
+		const bool sam = (a == 'H' && b == 'D') || (a == 'S' && b == 'Q') || (a == 'R' && b == 'G') || (a == 'P' && b == 'G') || (a == 'C' && b == 'O');
+		if (!sam)
+			type = 0;
+	}
+	if (type < 0) {
+		munmap((void*)d, size);
+		return true;
+	}
+	*handled = true;
+	std::vector<Piece> pc(nthreads);
+	for (unsigned t = 0; t < nthreads; t++) {
+		pc[t].a = size / nthreads * t;
+		pc[t].b = t + 1 == nthreads ? size : size / nthreads * (t + 1);
+	}
+	std::vector<std::thread> th;
+	for (unsigned t = 0; t < nthreads; t++) // pass 1: newlines per piece
+		th.emplace_back([&, t]() {
+			size_t n = 0;
+			const char* p = d + pc[t].a;
+			const char* const e = d + pc[t].b;
+			while (p < e) {
+				const char* nl = (const char*)memchr(p, '\n', (size_t)(e - p));
+				if (!nl)
+					break;
+				n++;
+				p = nl + 1;
+			}
+			pc[t].newlines = n;
+		});
+	for (auto& x : th)
+		x.join();
+	th.clear();
+	size_t total_nl = 0;
+	for (unsigned t = 0; t < nthreads; t++) {
+		pc[t].first_line = total_nl;
+		total_nl += pc[t].newlines;
+	}
+	const size_t n_lines = total_nl + (d[size - 1] != '\n' ? 1 : 0); // a last line without '\n' counts (std::getline)
+	for (unsigned t = 0; t < nthreads; t++) // pass 2: parse + pack + submit
+		th.emplace_back([&, t]() {
+			BatchSubmitter sub(ctx_source, min_len, submit_mu);
+			if (type == 0)
+				parse_fastq_piece(d, size, pc[t], n_lines, sub);
+			else
+				parse_fasta_piece(d, size, pc[t], sub);
+			sub.flush();
+			sub.finish();
+		});
+	for (auto& x : th)
+		x.join();
+	munmap((void*)d, size);
+	return true;
 }
 
 } // namespace ntcb

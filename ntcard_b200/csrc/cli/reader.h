@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -36,9 +37,13 @@ private:
 // streams, each double buffered: records whose padded size equals that of the first record seen (the common
 // read length, e.g. 150 bp -> 12 words) go into a UNIFORM-STRIDE batch, which the device runs through the
 // bit-sliced kernel; everything else (segments cut short by an N, odd lengths) goes into a ragged batch.
+// The context may still be under construction when the readers start (creating it -- CUDA initialisation -- takes longer than
+// parsing a few hundred MB): with a context SOURCE the submitter starts on pageable buffers, asks for the context only when its
+// first batch is full (blocking until it exists), and moves a buffer to pinned memory once it has been submitted a few times.
 class BatchSubmitter {
 public:
 	BatchSubmitter(ntc_ctx* ctx, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer = (size_t)2 << 20); // 8 MB per pinned buffer: pinning is slow (~1 GB/s), 16 reader threads x 84 MB cost 1 s
+	BatchSubmitter(std::function<ntc_ctx*()> ctx_source, unsigned min_len, std::mutex* submit_mu, size_t words_per_buffer = (size_t)2 << 20);
 	~BatchSubmitter();
 	void add(const char* seq, size_t len); // == one ntRead(seq, ...) call of the reference
 	void flush();                           // submit what is buffered (both streams)
@@ -53,17 +58,22 @@ private:
 		size_t cap_words = 0, cap_rec = 0;
 		size_t n_words = 0, n_rec = 0;
 		uint64_t ticket = 0;
+		bool pinned = false;
+		unsigned submits = 0;
 	};
 	struct Stream {
 		Buf buf[2];
 		int cur = 0;
 		uint32_t stride = 0; // > 0: uniform-stride stream
 	};
-	void alloc(Buf& b, size_t words, size_t recs);
+	void alloc(Buf& b, size_t words, size_t recs, bool pinned);
 	void release(Buf& b);
+	void init(size_t words_per_buffer, bool pinned);
+	ntc_ctx* ctx();
 	void flush_stream(Stream& st);
 	void append(Stream& st, const uint32_t* rec, size_t nwords);
 	ntc_ctx* ctx_;
+	std::function<ntc_ctx*()> ctx_source_;
 	unsigned min_len_;
 	std::mutex* mu_;
 	Stream uni_, rag_;
@@ -75,5 +85,15 @@ private:
 // nthll_rules: the sniffer of nthll.cpp:73-90 instead -- the same three formats, but whatever is not FASTA / FASTQ /
 // SAM-with-header is read as header-less SAM, and unreadable files are skipped silently; never returns false.
 bool read_file(const std::string& path, BatchSubmitter& sub, bool nthll_rules = false);
+
+// One large uncompressed FASTQ / FASTA file parsed by `nthreads` threads (the reference reads a file with ONE thread however
+// many -t says, ntcard.cpp:445).  The file is mapped and cut at arbitrary byte offsets; a first pass counts the newlines of
+// every piece in parallel, which gives every piece the index of its first line -- so the FASTQ rule "lines 1, 5, 9, ... are
+// sequences, hashed only if their quality line exists" (getEfq, ntcard.cpp:173-189) is applied exactly, with no guessing at
+// '@' / '+' characters; FASTA records (getEfa, ntcard.cpp:191-208) belong to the piece their '>' line starts in.  Every
+// thread has its own BatchSubmitter; the sketch does not depend on the order of the sequences.
+// *handled = false (and nothing read) when the file is compressed, small, SAM or unrecognised: use read_file then.
+bool read_file_parallel(const std::string& path, const std::function<ntc_ctx*()>& ctx_source, unsigned min_len, std::mutex* submit_mu,
+    unsigned nthreads, bool* handled);
 
 } // namespace ntcb

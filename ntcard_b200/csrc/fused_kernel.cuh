@@ -127,16 +127,7 @@ static __device__ __noinline__ bool fused_drain(const FusedArgs& a, uint32_t til
 		sm.wcnt[b] = f;
 	}
 	__syncwarp();
-	HashK K;
-	K.k = a.hk_k;
-	K.tprime = a.hk_tprime;
-	K.nblk = a.hk_nblk;
-	K.head_ra = a.hk_head_ra;
-	K.head_rb = a.hk_head_rb;
-	K.head_c = a.hk_head_c;
-	K.head_d = a.hk_head_d;
-	K.rot_a = a.hk_rot_a;
-	K.rot_b = a.hk_rot_b;
+	const HashK K = a.hk;
 	const uint32_t rBits = P.rBits, S = a.sBits, bin_shift = P.bin_shift, n_rec = a.n_rec, ngroups = a.stride >> 2;
 	const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(a.words);
 	const uint32_t lt = (1u << lane) - 1u;

@@ -1,6 +1,15 @@
 // hit_hash.cuh -- the full 64-bit canonical ntHash of one sampled k-mer from the packed bases, and ntComp
-// (ntcard.cpp:132-145) on it: shared by the fused sketch kernel (fused_kernel.cuh) and the stand-alone hit kernel
-// (hit_kernels.cu).  Byte-indexed tables in shared memory: 8 x 128-bit lookups per 32 bases.
+// (ntcard.cpp:132-145) on it: shared by the stand-alone hit kernel (hit_kernels.cu) and the fused sketch kernel
+// (fused_kernel.cuh).  Byte-indexed tables in shared memory: 8 x 128-bit lookups per 32 bases.
+//
+// Block-wise for ANY k.  k = tprime + 32 (nblk - 1), 1 <= tprime <= 32: the first tprime bases form the HEAD block, put through
+// the byte tables with the other 32 - tprime codes masked to 0 ('A'); what those A's contribute is a constant per k
+// (head_c / head_d), and the head's hash sits 32 - tprime rotations too far left:
+//   fh = sror^(32-tprime)( FB(head) ^ head_c ),  rh = RB(head) ^ head_d;   then per full block m = 1 .. nblk-1:
+//   fh = srol^32(fh) ^ FB_m,                      rh ^= srol^(tprime + 32 (m-1)) RB_m
+// with FB = XOR_i srol^(31-i) seed[c_i], RB = XOR_i srol^i seed[3-c_i] over the 32 codes of a block (NTF64 / NTR64 base forms,
+// nthash.hpp:220-239, regrouped; checked against the oracle for every k class by tests/test_parity_gpu.py::test_bitslice_every_k_class).  No per-base loop:
+// k = 25 costs one block like k = 32, k = 31 one, k = 64 two.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,132 +21,6 @@ namespace ntc {
 namespace pl {
 
 constexpr size_t kTabBytes = 8 * 256 * 16;
-
-// ------------------------------------------------------------------------------------------------
-// full 64-bit canonical hash of one k-mer from the packed bases
-// ------------------------------------------------------------------------------------------------
-// srol applied n times, for n given as (a, b) = (n % 31, n % 33): rotate the upper ring by a, the lower by b.
-__device__ __forceinline__ uint64_t srol_ab(uint64_t v, uint32_t a, uint32_t b)
-{
-	uint32_t hi = (uint32_t)(v >> 33);
-	uint64_t lo = v & 0x1FFFFFFFFull;
-	hi = ((hi << a) | (hi >> (31u - a))) & 0x7FFFFFFFu;
-	lo = ((lo << b) | (lo >> (33u - b))) & 0x1FFFFFFFFull;
-	return ((uint64_t)hi << 33) | lo;
-}
-
-struct HashCtx {
-	const uint32_t* __restrict__ words;
-	uint32_t stride, k, rBits, sBits;
-	const uint4* tab; // shared: [8][256] {FB.lo, FB.hi, RB.lo, RB.hi}
-	uint64_t rot_a, rot_b;
-};
-
-struct HitLoad { // the packed words of a candidate's first 32-base block, in flight
-	uint32_t x0, x1, x2;
-};
-
-// rec_words: the base words of the record (word 0 = length skipped); p: k-mer start; last: index of the last base word
-// that may be read (the record's slot in the uniform-stride batch)
-template <bool kStaged> __device__ __forceinline__ uint32_t ld_word(const uint32_t* p)
-{
-	return kStaged ? *p : __ldg(p); // staged: the tile's packed reads sit in shared memory
-}
-
-template <bool kStaged>
-__device__ __forceinline__ HitLoad hit_issue(const HashCtx& c, const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
-{
-	HitLoad h;
-	const uint32_t wi = (p + (c.k & 31u)) >> 4;
-	h.x0 = ld_word<kStaged>(rec_words + min(wi, last));
-	h.x1 = ld_word<kStaged>(rec_words + min(wi + 1, last));
-	h.x2 = ld_word<kStaged>(rec_words + min(wi + 2, last));
-	return h;
-}
-
-// 32 bases (two packed words) through the byte tables: FB = XOR_i srol^(31-i) seed[c_i], RB = XOR_i srol^i seed[3-c_i]
-__device__ __forceinline__ void block_tables(const uint4* __restrict__ tab, uint32_t w0, uint32_t w1, uint32_t& f0, uint32_t& f1,
-    uint32_t& r0, uint32_t& r1)
-{
-	f0 = f1 = r0 = r1 = 0;
-#pragma unroll
-	for (int j = 0; j < 8; j++) {
-		const uint32_t w = j < 4 ? w0 : w1;
-		const int sh = 8 * (j & 3) - 4; // byte j scaled by 16 (the entry size)
-		const uint32_t off = (sh < 0 ? (w << 4) : (w >> sh)) & 0xFF0u;
-		const uint4 e = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(tab) + j * 4096 + off);
-		f0 ^= e.x;
-		f1 ^= e.y;
-		r0 ^= e.z;
-		r1 ^= e.w;
-	}
-}
-
-// Canonical hash of the k-mer and ntComp (ntcard.cpp:132-145).  k = t + 32*M: the t head bases one at a time
-// (NTF64/NTR64 base forms, nthash.hpp:220-239), then M blocks of 32 bases:
-//   fh = srol^32(fh) ^ FB_m        rh ^= srol^(t+32m) RB_m
-// Returns the counter index inside the k's [2][2^rBits] sub-sketch, or kVoid when ntComp does not sample it.
-template <bool kStaged>
-__device__ __forceinline__ uint32_t hit_finish(const HashCtx& c, const HitLoad& h, const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
-{
-	const uint32_t t = c.k & 31u, M = c.k >> 5;
-	uint32_t hh, hl; // canonical hash, high / low word
-	if (t == 0 && M == 1) { // k = 32: pure 32-bit path
-		const uint32_t sh = (p & 15u) * 2u;
-		uint32_t f0, f1, r0, r1;
-		block_tables(c.tab, __funnelshift_r(h.x0, h.x1, sh), __funnelshift_r(h.x1, h.x2, sh), f0, f1, r0, r1);
-		const bool rlt = r1 < f1 || (r1 == f1 && r0 < f0);
-		hh = rlt ? r1 : f1;
-		hl = rlt ? r0 : f0;
-	} else {
-		uint64_t fh = 0, rh = 0;
-		for (uint32_t i = 0; i < t; i++) {
-			const uint32_t code = (ld_word<kStaged>(rec_words + ((p + i) >> 4)) >> (((p + i) & 15u) * 2u)) & 3u;
-			fh = srol(fh) ^ seed_of(code);
-			rh ^= srol_n(seed_of(3u - code), i);
-		}
-		uint32_t x0 = h.x0, x1 = h.x1, x2 = h.x2;
-		for (uint32_t m = 0; m < M; m++) {
-			const uint32_t o = p + t + 32u * m, sh = (o & 15u) * 2u;
-			if (m) {
-				const uint32_t wi = o >> 4;
-				x0 = ld_word<kStaged>(rec_words + wi);
-				x1 = ld_word<kStaged>(rec_words + wi + 1);
-				x2 = ld_word<kStaged>(rec_words + min(wi + 2, last));
-			}
-			uint32_t f0, f1, r0, r1;
-			block_tables(c.tab, __funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), f0, f1, r0, r1);
-			const uint64_t FB = ((uint64_t)f1 << 32) | f0, RB = ((uint64_t)r1 << 32) | r0;
-			fh = (m || t) ? (srol_ab(fh, 1, 32) ^ FB) : FB;
-			const uint32_t ra = (uint32_t)(c.rot_a >> (8 * m)) & 0xFFu, rb = (uint32_t)(c.rot_b >> (8 * m)) & 0xFFu;
-			rh ^= (ra | rb) ? srol_ab(RB, ra, rb) : RB;
-		}
-		const uint64_t hm = rh < fh ? rh : fh;
-		hh = (uint32_t)(hm >> 32);
-		hl = (uint32_t)hm;
-	}
-	// ntComp: both tests look at the top S+1 <= 32 bits; the bucket at the low rBits <= 30 bits
-	const uint32_t S = c.sBits;
-	const bool t0 = (hh >> (31 - S)) == 1u;
-	const bool t1 = (hh >> (32 - S)) == ((1u << (S - 1)) - 1u);
-	if (!(t0 || t1))
-		return kVoid;
-	return ((t1 ? 1u : 0u) << c.rBits) | (hl & ((1u << c.rBits) - 1u));
-}
-
-// ---- block-wise full hash with 128-bit gathers (fused kernel) ---------------------------------------------------------------
-// k = tprime + 32 (nblk - 1), 1 <= tprime <= 32: the first tprime bases form the HEAD block, put through the byte tables with the
-// other 32 - tprime codes masked to 0 ('A'); what those A's contribute is a constant per k (head_c / head_d), and the head's hash
-// sits 32 - tprime rotations too far left:
-//   fh = sror^(32-tprime)( FB(head) ^ head_c ),  rh = RB(head) ^ head_d;   then per full block m = 1 .. nblk-1:
-//   fh = srol^32(fh) ^ FB_m,                      rh ^= srol^(tprime + 32 (m-1)) RB_m
-// (NTF64 / NTR64 base forms, nthash.hpp:220-239, regrouped; checked against them for k = 1 .. 287 on the host.)
-struct HashK {
-	uint32_t k, tprime, nblk;
-	uint32_t head_ra, head_rb;   // srol amounts (mod 31, mod 33) equal to sror^(32 - tprime)
-	uint64_t head_c, head_d;
-	uint64_t rot_a, rot_b;       // byte m-1: (tprime + 32 (m-1)) % 31 and % 33
-};
 
 inline HashK make_hashk(uint32_t k)
 {
@@ -161,6 +44,116 @@ inline HashK make_hashk(uint32_t k)
 }
 
 #if defined(__CUDACC__)
+// srol applied n times, for n given as (a, b) = (n % 31, n % 33): rotate the upper ring by a, the lower by b.
+__device__ __forceinline__ uint64_t srol_ab(uint64_t v, uint32_t a, uint32_t b)
+{
+	uint32_t hi = (uint32_t)(v >> 33);
+	uint64_t lo = v & 0x1FFFFFFFFull;
+	hi = ((hi << a) | (hi >> (31u - a))) & 0x7FFFFFFFu;
+	lo = ((lo << b) | (lo >> (33u - b))) & 0x1FFFFFFFFull;
+	return ((uint64_t)hi << 33) | lo;
+}
+
+struct HitLoad { // three consecutive packed words: 32 bases at any 2-bit offset
+	uint32_t x0, x1, x2;
+};
+
+// 32 bases (two packed words) through the byte tables
+__device__ __forceinline__ void block_tables(const uint4* __restrict__ tab, uint32_t w0, uint32_t w1, uint32_t& f0, uint32_t& f1,
+    uint32_t& r0, uint32_t& r1)
+{
+	f0 = f1 = r0 = r1 = 0;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const uint32_t w = j < 4 ? w0 : w1;
+		const int sh = 8 * (j & 3) - 4; // byte j scaled by 16 (the entry size)
+		const uint32_t off = (sh < 0 ? (w << 4) : (w >> sh)) & 0xFF0u;
+		const uint4 e = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(tab) + j * 4096 + off);
+		f0 ^= e.x;
+		f1 ^= e.y;
+		r0 ^= e.z;
+		r1 ^= e.w;
+	}
+}
+
+// ntComp on the canonical hash (hh = high word, hl = low word): both tests look at the top S+1 <= 32 bits; the bucket at the low
+// rBits <= 30 bits.  Returns the counter index inside the k's [2][2^rBits] sub-sketch, or kVoid when not sampled.
+__device__ __forceinline__ uint32_t ntcomp_index(uint32_t hh, uint32_t hl, uint32_t rBits, uint32_t S)
+{
+	const bool t0 = (hh >> (31 - S)) == 1u;
+	const bool t1 = (hh >> (32 - S)) == ((1u << (S - 1)) - 1u);
+	if (!(t0 || t1))
+		return kVoid;
+	return ((t1 ? 1u : 0u) << rBits) | (hl & ((1u << rBits) - 1u)); // the later test wins (ntcard.cpp:136-139)
+}
+
+// The head block: x = the three words that hold bases p .. p+31 of the record.  For k = 32 this is the whole hash.
+__device__ __forceinline__ void hash_head(const HashK& K, const uint4* __restrict__ tab, const HitLoad& x, uint32_t p, uint64_t& fh, uint64_t& rh)
+{
+	const uint32_t sh = (p & 15u) * 2u, t = K.tprime;
+	uint32_t w0 = __funnelshift_r(x.x0, x.x1, sh), w1 = __funnelshift_r(x.x1, x.x2, sh);
+	if (t <= 16) {
+		w0 &= t == 16 ? 0xFFFFFFFFu : ((1u << (2u * t)) - 1u);
+		w1 = 0;
+	} else if (t < 32) {
+		w1 &= (1u << (2u * (t - 16u))) - 1u;
+	}
+	uint32_t f0, f1, r0, r1;
+	block_tables(tab, w0, w1, f0, f1, r0, r1);
+	fh = (((uint64_t)f1 << 32) | f0) ^ K.head_c;
+	rh = (((uint64_t)r1 << 32) | r0) ^ K.head_d;
+	if (t < 32)
+		fh = srol_ab(fh, K.head_ra, K.head_rb);
+}
+
+// One more full block: y = the three words that hold its 32 bases, o = index of its first base in the record, m >= 1
+__device__ __forceinline__ void hash_block(const HashK& K, const uint4* __restrict__ tab, const HitLoad& y, uint32_t o, uint32_t m, uint64_t& fh,
+    uint64_t& rh)
+{
+	const uint32_t sh = (o & 15u) * 2u;
+	uint32_t f0, f1, r0, r1;
+	block_tables(tab, __funnelshift_r(y.x0, y.x1, sh), __funnelshift_r(y.x1, y.x2, sh), f0, f1, r0, r1);
+	const uint64_t FB = ((uint64_t)f1 << 32) | f0, RB = ((uint64_t)r1 << 32) | r0;
+	fh = srol_ab(fh, 1, 32) ^ FB;
+	const uint32_t ra = (uint32_t)(K.rot_a >> (8u * (m - 1u))) & 0xFFu, rb = (uint32_t)(K.rot_b >> (8u * (m - 1u))) & 0xFFu;
+	rh ^= (ra | rb) ? srol_ab(RB, ra, rb) : RB;
+}
+
+// ---- 32-bit word loads (hit kernel: the tile staged in shared memory, or global memory) ---------------------------------------
+template <bool kStaged> __device__ __forceinline__ uint32_t ld_word(const uint32_t* p)
+{
+	return kStaged ? *p : __ldg(p); // staged: the tile's packed reads sit in shared memory
+}
+
+// rec_words: the base words of the record (word 0 = length skipped); o: first base of the block; last: index of the last base
+// word that may be read (the record's slot in the uniform-stride batch)
+template <bool kStaged>
+__device__ __forceinline__ HitLoad hit_issue(const uint32_t* __restrict__ rec_words, uint32_t o, uint32_t last)
+{
+	HitLoad h;
+	const uint32_t wi = o >> 4;
+	h.x0 = ld_word<kStaged>(rec_words + min(wi, last));
+	h.x1 = ld_word<kStaged>(rec_words + min(wi + 1, last));
+	h.x2 = ld_word<kStaged>(rec_words + min(wi + 2, last));
+	return h;
+}
+
+// Canonical hash of the k-mer starting at base p and ntComp.  h0 = hit_issue(rec_words, p, last), requested earlier.
+template <bool kStaged>
+__device__ __forceinline__ uint32_t hit_finish(const HashK& K, const uint4* __restrict__ tab, uint32_t rBits, uint32_t S, const HitLoad& h0,
+    const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
+{
+	uint64_t fh, rh;
+	hash_head(K, tab, h0, p, fh, rh);
+	for (uint32_t m = 1; m < K.nblk; m++) {
+		const uint32_t o = p + K.tprime + 32u * (m - 1u);
+		hash_block(K, tab, hit_issue<kStaged>(rec_words, o, last), o, m, fh, rh);
+	}
+	const uint64_t hm = rh < fh ? rh : fh;
+	return ntcomp_index((uint32_t)(hm >> 32), (uint32_t)hm, rBits, S);
+}
+
+// ---- 128-bit gathers (fused kernel) ---------------------------------------------------------------------------------------------
 struct HitLoadV { // the one or two 16-byte groups of a record that hold three consecutive packed words, in flight
 	uint4 g0, g1;
 };
@@ -191,52 +184,18 @@ __device__ __forceinline__ HitLoad hit_select(const HitLoadV& h, uint32_t w)
 	return r;
 }
 
-// Canonical hash of the k-mer starting at base p of the record and ntComp (ntcard.cpp:132-145): the counter index inside the
-// k's [2][2^rBits] sub-sketch, or kVoid when ntComp does not sample it.  h0: hit_issue_v(rec, ngroups, 1 + (p >> 4)).
+// h0: hit_issue_v(rec, ngroups, 1 + (p >> 4)), requested earlier
 __device__ __forceinline__ uint32_t hash_kmer_v(const HashK& K, const uint4* __restrict__ tab, uint32_t rBits, uint32_t S, const HitLoadV& h0,
     const uint4* __restrict__ rec, uint32_t ngroups, uint32_t p)
 {
-	uint32_t hh, hl;
-	const uint32_t sh = (p & 15u) * 2u;
-	const HitLoad x = hit_select(h0, 1u + (p >> 4));
-	uint32_t w0 = __funnelshift_r(x.x0, x.x1, sh), w1 = __funnelshift_r(x.x1, x.x2, sh);
-	uint32_t f0, f1, r0, r1;
-	if (K.nblk == 1 && K.tprime == 32) { // k = 32: pure 32-bit path
-		block_tables(tab, w0, w1, f0, f1, r0, r1);
-		const bool rlt = r1 < f1 || (r1 == f1 && r0 < f0);
-		hh = rlt ? r1 : f1;
-		hl = rlt ? r0 : f0;
-	} else {
-		const uint32_t t = K.tprime;
-		if (t <= 16) {
-			w0 &= t == 16 ? 0xFFFFFFFFu : ((1u << (2u * t)) - 1u);
-			w1 = 0;
-		} else if (t < 32) {
-			w1 &= (1u << (2u * (t - 16u))) - 1u;
-		}
-		block_tables(tab, w0, w1, f0, f1, r0, r1);
-		uint64_t fh = (((uint64_t)f1 << 32) | f0) ^ K.head_c, rh = (((uint64_t)r1 << 32) | r0) ^ K.head_d;
-		if (t < 32)
-			fh = srol_ab(fh, K.head_ra, K.head_rb);
-		for (uint32_t m = 1; m < K.nblk; m++) {
-			const uint32_t o = p + t + 32u * (m - 1u), wm = 1u + (o >> 4), shm = (o & 15u) * 2u;
-			const HitLoadV hv = hit_issue_v(rec, ngroups, wm);
-			const HitLoad y = hit_select(hv, wm);
-			block_tables(tab, __funnelshift_r(y.x0, y.x1, shm), __funnelshift_r(y.x1, y.x2, shm), f0, f1, r0, r1);
-			const uint64_t FB = ((uint64_t)f1 << 32) | f0, RB = ((uint64_t)r1 << 32) | r0;
-			fh = srol_ab(fh, 1, 32) ^ FB;
-			const uint32_t ra = (uint32_t)(K.rot_a >> (8u * (m - 1u))) & 0xFFu, rb = (uint32_t)(K.rot_b >> (8u * (m - 1u))) & 0xFFu;
-			rh ^= (ra | rb) ? srol_ab(RB, ra, rb) : RB;
-		}
-		const uint64_t hm = rh < fh ? rh : fh;
-		hh = (uint32_t)(hm >> 32);
-		hl = (uint32_t)hm;
+	uint64_t fh, rh;
+	hash_head(K, tab, hit_select(h0, 1u + (p >> 4)), p, fh, rh);
+	for (uint32_t m = 1; m < K.nblk; m++) {
+		const uint32_t o = p + K.tprime + 32u * (m - 1u), wm = 1u + (o >> 4);
+		hash_block(K, tab, hit_select(hit_issue_v(rec, ngroups, wm), wm), o, m, fh, rh);
 	}
-	const bool t0 = (hh >> (31 - S)) == 1u;
-	const bool t1 = (hh >> (32 - S)) == ((1u << (S - 1)) - 1u);
-	if (!(t0 || t1))
-		return kVoid;
-	return ((t1 ? 1u : 0u) << rBits) | (hl & ((1u << rBits) - 1u));
+	const uint64_t hm = rh < fh ? rh : fh;
+	return ntcomp_index((uint32_t)(hm >> 32), (uint32_t)hm, rBits, S);
 }
 #endif
 

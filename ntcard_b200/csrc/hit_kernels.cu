@@ -149,7 +149,7 @@ __device__ __forceinline__ void top_up(const GroupSmem& sm, const HitArgs& a, ui
 }
 
 template <bool kStaged>
-__device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs& a, const HashCtx& c, uint32_t n, const Unit& U, uint32_t g,
+__device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs& a, const uint4* __restrict__ tab, uint32_t n, const Unit& U, uint32_t g,
     uint32_t gtid, Spare& sp)
 {
 	const Pool& P = a.pool;
@@ -163,8 +163,8 @@ __device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs
 			if (i < n) {
 				uint32_t rec, rl, p;
 				decode(a, U, sm.queue[i], rec, rl, p);
-				const uint32_t* rw = kStaged ? sm.tile + rl * c.stride + 1 : c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1;
-				h[u] = hit_issue<kStaged>(c, rw, p, last);
+				const uint32_t* rw = kStaged ? sm.tile + rl * a.stride + 1 : a.words + (uint64_t)min(rec, a.n_rec - 1u) * a.stride + 1;
+				h[u] = hit_issue<kStaged>(rw, p, last);
 			}
 		}
 #pragma unroll
@@ -173,9 +173,9 @@ __device__ __forceinline__ void process_queue(const GroupSmem& sm, const HitArgs
 			if (i < n) {
 				uint32_t rec, rl, p;
 				decode(a, U, sm.queue[i], rec, rl, p);
-				const uint32_t* rw = kStaged ? sm.tile + rl * c.stride + 1 : c.words + (uint64_t)min(rec, a.n_rec - 1u) * c.stride + 1;
+				const uint32_t* rw = kStaged ? sm.tile + rl * a.stride + 1 : a.words + (uint64_t)min(rec, a.n_rec - 1u) * a.stride + 1;
 				// slots past the end of the batch, and positions past the end of a record of a mixed-length tile (scan_kernel.cuh)
-				const uint32_t idx = (rec < a.n_rec && p + a.k <= (kStaged ? rw[-1] : __ldg(rw - 1))) ? hit_finish<kStaged>(c, h[u], rw, p, last) : kVoid;
+				const uint32_t idx = (rec < a.n_rec && p + a.k <= (kStaged ? rw[-1] : __ldg(rw - 1))) ? hit_finish<kStaged>(a.hk, tab, P.rBits, a.sBits, h[u], rw, p, last) : kVoid;
 				uint32_t after = 0;
 				if (idx != kVoid && !append(sm, a, idx)) {
 					after = idx | kPendingBit;
@@ -269,15 +269,6 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_
 	__syncthreads();
 	if (gtid < nb && active && !resume)
 		top_up(sm, a, gtid, sp); // open a first block for every bin
-	HashCtx c;
-	c.words = a.words;
-	c.stride = a.stride;
-	c.k = a.k;
-	c.rBits = a.pool.rBits;
-	c.sBits = a.sBits;
-	c.tab = tab;
-	c.rot_a = a.rot_a;
-	c.rot_b = a.rot_b;
 	constexpr int kW = 8; // mask words per thread in flight
 	uint32_t phase = 0;
 	for (uint32_t unit = blockIdx.x * kGroups + g; unit < a.n_units; unit += gridDim.x * kGroups) {
@@ -346,7 +337,7 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_
 		if (!sm.scal[1]) {
 			const uint32_t n = sm.scal[0];
 			if (n)
-				process_queue<kStaged>(sm, a, c, n, U, g, gtid, sp);
+				process_queue<kStaged>(sm, a, tab, n, U, g, gtid, sp);
 		} else {
 			// skewed data: more candidates than the queue holds -> two mask rows (<= 2048 candidates) per round
 			for (uint32_t w0 = 0; w0 < nw; w0 += 64) {
@@ -363,7 +354,7 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_
 				group_sync(g);
 				const uint32_t n = sm.scal[0];
 				if (n)
-					process_queue<kStaged>(sm, a, c, n, U, g, gtid, sp);
+					process_queue<kStaged>(sm, a, tab, n, U, g, gtid, sp);
 			}
 		}
 		group_sync(g); // the staged tile and the queue are free again

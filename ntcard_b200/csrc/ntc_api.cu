@@ -87,7 +87,6 @@ struct ntc_ctx {
 	uint4* d_bs_tab = nullptr;            // hit-path byte tables of the bit-sliced kernel
 	struct KInit {                          // per-k constants of the scan / hit kernels
 		uint32_t F0[31], R0[31];            // initial bit-sliced state (bitslice_core.cuh init_state)
-		uint64_t rot_a, rot_b;              // byte m: (k%32 + 32m) % 31 and % 33 for block m of the full hash (k < 288)
 		bool polyA_sampled;                 // ntComp samples the all-A k-mer: zero padding must not be scanned (scan_kernel.cuh, mixed tiles)
 	} kinit[NTC_MAX_K];
 	bool totals_overridden = false;
@@ -516,18 +515,7 @@ int run_fused_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const Pipe
 	fa.qlane = sh.qlane;
 	fa.dbg = c->fused_dbg;
 	fa.d_tab = c->d_bs_tab;
-	{
-		const ntc::pl::HashK hk = ntc::pl::make_hashk(c->k[ki]);
-		fa.hk_k = hk.k;
-		fa.hk_tprime = hk.tprime;
-		fa.hk_nblk = hk.nblk;
-		fa.hk_head_ra = hk.head_ra;
-		fa.hk_head_rb = hk.head_rb;
-		fa.hk_head_c = hk.head_c;
-		fa.hk_head_d = hk.head_d;
-		fa.hk_rot_a = hk.rot_a;
-		fa.hk_rot_b = hk.rot_b;
-	}
+	fa.hk = ntc::pl::make_hashk(c->k[ki]);
 	fa.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 	fa.pool = P;
 	fa.tile_info = c->d_tile_info;
@@ -613,8 +601,7 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	ha.masks = c->d_masks;
 	ha.tile_info = c->d_tile_info;
 	ha.d_tab = c->d_bs_tab;
-	ha.rot_a = c->kinit[ki].rot_a;
-	ha.rot_b = c->kinit[ki].rot_b;
+	ha.hk = ntc::pl::make_hashk(c->k[ki]);
 	ha.ctr_k = c->d_counters + ((size_t)ki * NTC_NSAMP << c->rBits);
 	ha.pool = P;
 	ha.stream = c->stream;
@@ -986,7 +973,6 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 		for (unsigned ki = 0; ki < nK; ki++) {
 			ntc_ctx::KInit& L = c->kinit[ki];
 			ntc::bs::init_state(c->k[ki], L.F0, L.R0);
-			L.rot_a = L.rot_b = 0;
 			{
 				uint64_t fh = 0, rh = 0; // A^k: NTF64 / NTR64 base forms, nthash.hpp:220-239
 				for (unsigned i = 0; i < c->k[ki]; i++) {
@@ -994,10 +980,6 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 					rh = ntc::srol(rh) ^ ntc::seed_of(3);
 				}
 				L.polyA_sampled = ntc::sample_table(rh < fh ? rh : fh, sBits) < 2;
-			}
-			for (unsigned m = 0; m < 8; m++) {
-				L.rot_a |= (uint64_t)(((c->k[ki] & 31u) + 32u * m) % 31u) << (8 * m);
-				L.rot_b |= (uint64_t)(((c->k[ki] & 31u) + 32u * m) % 33u) << (8 * m);
 			}
 		}
 	}

@@ -65,6 +65,13 @@ struct PeerLogs {                // the hit logs of all ranks of one node, mappe
 	uint32_t n;
 };
 
+struct HashK {                   // per-k constants of the block-wise full hash (hit_hash.cuh: make_hashk)
+	uint32_t k, tprime, nblk;    // k = tprime + 32 (nblk - 1), 1 <= tprime <= 32
+	uint32_t head_ra, head_rb;   // srol amounts (mod 31, mod 33) equal to sror^(32 - tprime)
+	uint64_t head_c, head_d;     // what the 32 - tprime masked-out codes of the head block contribute
+	uint64_t rot_a, rot_b;       // byte m-1: (tprime + 32 (m-1)) % 31 and % 33
+};
+
 struct ScanLaunch {              // per-k constants of the scan kernel, passed by value
 	uint32_t k, ring, nwarps;    // ring: positions in a warp's plane ring (k + 16 rounded up to a multiple of 16)
 	uint32_t npos_max;           // mask rows per tile
@@ -96,8 +103,7 @@ struct FusedArgs {               // the fused sketch kernel (fused_kernel.cuh): 
 	uint32_t qlane;              // candidate slots per lane of a warp's queue (<= 2 * (ring + 3))
 	uint32_t dbg;                // timing experiments only (NTC_FUSED_DBG): 1 = skip the hash + append phase, 2 = skip the emission (results are wrong)
 	const uint4* d_tab;          // [8][256] byte tables of the full hash
-	uint32_t hk_k, hk_tprime, hk_nblk, hk_head_ra, hk_head_rb; // HashK of this k (hit_hash.cuh make_hashk), flattened
-	uint64_t hk_head_c, hk_head_d, hk_rot_a, hk_rot_b;
+	HashK hk;
 	uint32_t* ctr_k;             // counters of this k (direct increments once the sketch is materialised and the pool is full)
 	Pool pool;
 	uint32_t* tile_info;         // [n_tiles]: 0 done, kTileFlag -> fallback kernel, kTileDefer | p -> second pass
@@ -115,7 +121,7 @@ struct HitArgs {
 	const uint32_t* masks;
 	const uint32_t* tile_info;   // k-mer positions per record of every tile (0 / kTileFlag: no rows to read)
 	const uint4* d_tab;          // [8][256] byte tables of the full hash
-	uint64_t rot_a, rot_b;
+	HashK hk;
 	uint32_t* ctr_k;             // counters of this k
 	Pool pool;
 	cudaStream_t stream;

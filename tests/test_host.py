@@ -176,3 +176,38 @@ def test_bitslice_filter_selftest_on_cpu(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     assert "ALL OK" in out and " 0 mismatches" in out and "mismatches" in out
     assert all(" 0 mismatches" in l for l in out.splitlines() if "mismatches" in l)
+
+
+def test_parallel_file_reader_equals_serial(tmp_path):
+    """bin/ntcard -t N with fewer files than threads parses pieces of one FASTQ / FASTA file in parallel (reader.cpp
+    read_file_parallel).  Host-only check with the stub device of tools/reader_bench: the multiset of packed records (an
+    order-independent digest) must equal the serial reader's, also for a file truncated inside its last record, one without
+    a trailing newline, and multi-line FASTA."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rb = os.path.join(root, "tools", "reader_bench")
+    subprocess.run(["make", "-C", rb], check=True, capture_output=True)
+    n, L = 90_000, 150
+    a = nt.gen_ascii(7, 0, n, L, mode=2).reshape(n, L)
+    rec = np.empty((n, 2 * L + 7), dtype=np.uint8)
+    rec[:, 0:3] = np.frombuffer(b"@r\n", dtype=np.uint8)
+    rec[:, 3:3 + L] = a
+    rec[:, 3 + L:6 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    rec[:, 6 + L:6 + 2 * L] = np.frombuffer(b"I" * L, dtype=np.uint8)
+    rec[:, 6 + 2 * L] = 10
+    data = rec.tobytes()
+    files = {"full.fq": data, "cut.fq": data[:-L - 1], "nonl.fq": data[:-1]}
+    fa = []
+    for i in range(0, n // 8):
+        s = bytes(a[i * 8:(i + 1) * 8].reshape(-1))
+        fa.append(b">s%d\n" % i + b"\n".join(s[j:j + 70] for j in range(0, len(s), 70)) + b"\n")
+    files["multi.fa"] = b"".join(fa) * 2
+    assert all(len(b) > 3 * (8 << 20) for b in files.values())  # large enough for three pieces
+    for name, blob in files.items():
+        p = tmp_path / name
+        p.write_bytes(blob)
+        outs = [subprocess.run([os.path.join(rb, "reader_bench"), "32", str(t), str(p)], check=True, capture_output=True,
+                               text=True).stdout for t in (1, 2, 3)]
+        assert " x 1 threads" in outs[0] and " x 2 threads" in outs[1] and " x 3 threads" in outs[2]
+        tails = [o.split(");", 1)[1].split(" batches")[0].rsplit(",", 1)[0] + o.split("digest")[1] for o in outs]   # "<n> records" + digest
+        assert tails[0] == tails[1] == tails[2], (name, outs)

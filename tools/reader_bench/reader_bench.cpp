@@ -1,5 +1,6 @@
 // reader_bench.cpp -- host ingest throughput of the CLI without a device (see stub_device.cpp):
-//   reader_bench K THREADS FILE...      -> GB/s of input text, records and words produced
+//   reader_bench K THREADS FILE...      -> GB/s of input text, records and words produced, order-independent digest of the records
+// THREADS > number of files: the spare threads parse pieces of the same file (read_file_parallel), as bin/ntcard -t does
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -15,6 +16,7 @@
 extern "C" uint64_t stub_words();
 extern "C" uint64_t stub_recs();
 extern "C" uint64_t stub_batches();
+extern "C" uint64_t stub_digest();
 
 int main(int argc, char** argv)
 {
@@ -34,13 +36,20 @@ int main(int argc, char** argv)
 	std::atomic<size_t> next(0);
 	std::mutex mu;
 	const auto t0 = std::chrono::steady_clock::now();
+	const unsigned per_file = nthreads > files.size() ? nthreads / (unsigned)files.size() : 1;
+	if (nthreads > files.size())
+		nthreads = (unsigned)files.size();
+	const std::function<ntc_ctx*()> no_ctx = []() { return (ntc_ctx*)nullptr; };
 	auto worker = [&]() {
 		ntcb::BatchSubmitter sub(nullptr, k, &mu);
 		for (;;) {
 			size_t i = next.fetch_add(1);
 			if (i >= files.size())
 				break;
-			if (!ntcb::read_file(files[i], sub))
+			bool handled = false;
+			if (per_file > 1)
+				ntcb::read_file_parallel(files[i], no_ctx, k, &mu, per_file, &handled);
+			if (!handled && !ntcb::read_file(files[i], sub))
 				fprintf(stderr, "cannot read %s\n", files[i].c_str());
 		}
 		sub.flush();
@@ -52,7 +61,7 @@ int main(int argc, char** argv)
 	for (auto& t : th)
 		t.join();
 	const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-	printf("%.3f s, %.2f GB/s of text (%u threads, %zu files, %.2f GB); %llu records, %llu words, %llu batches\n", s, bytes / s / 1e9, nthreads,
-	    files.size(), bytes / 1e9, (unsigned long long)stub_recs(), (unsigned long long)stub_words(), (unsigned long long)stub_batches());
+	printf("%.3f s, %.2f GB/s of text (%u x %u threads, %zu files, %.2f GB); %llu records, %llu batches, digest %016llx\n", s, bytes / s / 1e9, nthreads,
+	    per_file, files.size(), bytes / 1e9, (unsigned long long)stub_recs(), (unsigned long long)stub_batches(), (unsigned long long)stub_digest());
 	return 0;
 }

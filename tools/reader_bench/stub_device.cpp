@@ -10,11 +10,25 @@ namespace ntc {
 const char* last_err(); // host_util.cpp
 }
 
-static std::atomic<uint64_t> g_ticket{ 1 }, g_words{ 0 }, g_recs{ 0 }, g_batches{ 0 };
+static std::atomic<uint64_t> g_ticket{ 1 }, g_words{ 0 }, g_recs{ 0 }, g_batches{ 0 }, g_digest{ 0 };
+
+// order-independent digest of the submitted records: sum over records of an FNV-1a hash of (length word, base words)
+static uint64_t record_hash(const uint32_t* r)
+{
+	const uint32_t nw = 1 + (r[0] + 15) / 16;
+	uint64_t h = 0xcbf29ce484222325ull;
+	for (uint32_t i = 0; i < nw; i++)
+		h = (h ^ r[i]) * 0x100000001b3ull;
+	return h;
+}
 
 extern "C" {
-int ntc_submit(ntc_ctx*, const uint32_t*, size_t n_words, const uint32_t*, size_t n_rec, uint32_t, uint64_t* ticket)
+int ntc_submit(ntc_ctx*, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec, uint32_t stride, uint64_t* ticket)
 {
+	uint64_t d = 0;
+	for (size_t i = 0; i < n_rec; i++)
+		d += record_hash(words + (off ? off[i] : i * stride));
+	g_digest += d;
 	g_words += n_words;
 	g_recs += n_rec;
 	g_batches++;
@@ -29,4 +43,5 @@ void ntc_host_free(void* p) { free(p); }
 uint64_t stub_words() { return g_words; }
 uint64_t stub_recs() { return g_recs; }
 uint64_t stub_batches() { return g_batches; }
+uint64_t stub_digest() { return g_digest; }
 }
