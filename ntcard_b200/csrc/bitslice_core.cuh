@@ -185,6 +185,27 @@ template <int TQ, int S> BS_HD uint32_t sampled_mask(const State& st)
 	return t0 | t1;
 }
 
+// nthll pre-filter (nthll.cpp:92-97): a k-mer can only raise a HyperLogLog register if its leading-zero count exceeds the
+// register, so once every register is >= T - 1 only hashes whose top T bits are all zero matter.  Top T <= 31 bits of
+// min(fh, rh) are zero iff those of fh are or those of rh are.
+template <int TQ, int I, int T> struct FoldOr {
+	static BS_HD void run(const State& st, uint32_t& nzA, uint32_t& nzB)
+	{
+		nzA |= st.F[TopBit<TQ, I>::jf];
+		nzB |= st.R[TopBit<TQ, I>::jr];
+		FoldOr<TQ, I + 1, T>::run(st, nzA, nzB);
+	}
+};
+template <int TQ, int T> struct FoldOr<TQ, T, T> {
+	static BS_HD void run(const State&, uint32_t&, uint32_t&) {}
+};
+template <int TQ, int T> BS_HD uint32_t zero_top_mask(const State& st)
+{
+	uint32_t nzA = 0, nzB = 0;
+	FoldOr<TQ, 0, T>::run(st, nzA, nzB);
+	return ~nzA | ~nzB;
+}
+
 // Initial state cancelling the constants the k virtual steps inject (see header comment):
 //   forward : E0 = XOR_{i<k} sror^{1+i}( srol^k(seed[A]) )        reverse : E0 = XOR_{i<k} srol^i( seed[T] )
 // Physical register j holds logical bit j at q = 0.  Returns broadcast words (0 / 0xFFFFFFFF).

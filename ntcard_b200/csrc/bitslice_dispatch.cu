@@ -10,7 +10,7 @@
 namespace ntc {
 namespace pl {
 
-#define X(n) cudaError_t launch_scan_km_##n(unsigned sBits, const ScanArgs& a); cudaError_t launch_fused_km_##n(unsigned sBits, const FusedArgs& a);
+#define X(n) cudaError_t launch_scan_km_##n(unsigned sBits, const ScanArgs& a); cudaError_t launch_fused_km_##n(unsigned sBits, const FusedArgs& a); cudaError_t launch_hllscan_km_##n(unsigned T, const ScanArgs& a);
 BS_KM_LIST
 #undef X
 
@@ -30,6 +30,16 @@ cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a)
 {
 	switch (k % 31) {
 #define X(n) case n: return launch_scan_km_##n(sBits, a);
+		BS_KM_LIST
+#undef X
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+cudaError_t launch_hllscan(unsigned k, unsigned T, const ScanArgs& a)
+{
+	switch (k % 31) {
+#define X(n) case n: return launch_hllscan_km_##n(T, a);
 		BS_KM_LIST
 #undef X
 	default: return cudaErrorInvalidValue;

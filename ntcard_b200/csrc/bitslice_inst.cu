@@ -23,6 +23,16 @@ cudaError_t BS_CAT(launch_scan_km_, BS_KM)(unsigned sBits, const ScanArgs& a)
 	return cudaErrorInvalidValue;
 }
 
+// nthll pre-filter variants: candidates = k-mers whose canonical hash has its top T bits zero
+cudaError_t BS_CAT(launch_hllscan_km_, BS_KM)(unsigned T, const ScanArgs& a)
+{
+	if (T == 9)
+		return launch_scan_one<BS_KM, 9, 1>(a);
+	if (T == 13)
+		return launch_scan_one<BS_KM, 13, 1>(a);
+	return cudaErrorInvalidValue;
+}
+
 cudaError_t BS_CAT(launch_fused_km_, BS_KM)(unsigned sBits, const FusedArgs& a)
 {
 	if (sBits == 7)

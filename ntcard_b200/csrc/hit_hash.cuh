@@ -138,10 +138,11 @@ __device__ __forceinline__ HitLoad hit_issue(const uint32_t* __restrict__ rec_wo
 	return h;
 }
 
-// Canonical hash of the k-mer starting at base p and ntComp.  h0 = hit_issue(rec_words, p, last), requested earlier.
+// Canonical hash (NTC64, nthash.hpp:275-279: min of the two strands) of the k-mer starting at base p.
+// h0 = hit_issue(rec_words, p, last), requested earlier.
 template <bool kStaged>
-__device__ __forceinline__ uint32_t hit_finish(const HashK& K, const uint4* __restrict__ tab, uint32_t rBits, uint32_t S, const HitLoad& h0,
-    const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
+__device__ __forceinline__ uint64_t canonical_hash(const HashK& K, const uint4* __restrict__ tab, const HitLoad& h0, const uint32_t* __restrict__ rec_words,
+    uint32_t p, uint32_t last)
 {
 	uint64_t fh, rh;
 	hash_head(K, tab, h0, p, fh, rh);
@@ -149,7 +150,15 @@ __device__ __forceinline__ uint32_t hit_finish(const HashK& K, const uint4* __re
 		const uint32_t o = p + K.tprime + 32u * (m - 1u);
 		hash_block(K, tab, hit_issue<kStaged>(rec_words, o, last), o, m, fh, rh);
 	}
-	const uint64_t hm = rh < fh ? rh : fh;
+	return rh < fh ? rh : fh;
+}
+
+// ... and ntComp on it
+template <bool kStaged>
+__device__ __forceinline__ uint32_t hit_finish(const HashK& K, const uint4* __restrict__ tab, uint32_t rBits, uint32_t S, const HitLoad& h0,
+    const uint32_t* __restrict__ rec_words, uint32_t p, uint32_t last)
+{
+	const uint64_t hm = canonical_hash<kStaged>(K, tab, h0, rec_words, p, last);
 	return ntcomp_index((uint32_t)(hm >> 32), (uint32_t)hm, rBits, S);
 }
 

@@ -622,32 +622,54 @@ __global__ void __launch_bounds__(kApplyThreads) apply_owned_kernel(const Pool P
 					__nanosleep(20);
 			role_sync(role);
 			uint32_t* ctr = counters + (size_t)(s / P.nbins) * per_k;
-			for (uint32_t q = 0; q < G.n; q++) {
-				const uint32_t nbq = min(__ldcg(G.slice_nblk[q] + s), P.slice_cap);
-				const uint32_t* list = G.slice_blocks[q] + (size_t)s * P.slice_cap;
-				const uint32_t* ent = G.entries[q];
-				for (uint32_t j = j0; j < nbq; j += 2 * jstep) { // two blocks in flight per warp (remote latency)
-					const uint32_t ja = j, jb = j + jstep;
-					const uint32_t la = __ldcg(list + ja), lb = jb < nbq ? __ldcg(list + jb) : kVoid;
-					const uint32_t fa = la == kVoid ? 0u : min(la & 511u, kBlkEntries), fb = lb == kVoid ? 0u : min(lb & 511u, kBlkEntries);
-					const uint32_t* ea = ent + (size_t)(la >> 9) * kBlkEntries;
-					const uint32_t* eb = ent + (size_t)(lb >> 9) * kBlkEntries;
-					uint32_t va[kV], vb[kV];
+			// The blocks of slice s in ALL logs form one index space (peer q', block j), walked by all warps together: a loop over
+			// the peers with a loop over blocks inside costs one NVLink round trip per (slice, peer) and leaves most warps idle
+			// (N = 8, 64 slices per k: 0.53 ms against 0.36 ms).  The peers are visited starting behind this rank, so that the
+			// ranks do not all pull from rank 0 at the same time.
+			uint32_t first[kMaxPeers + 1];
+			first[0] = 0;
 #pragma unroll
-					for (int u = 0; u < kV; u++)
-						va[u] = lane + 32u * u < fa ? __ldcg(ea + lane + 32u * u) : kVoid;
+			for (uint32_t i = 0; i < kMaxPeers; i++) {
+				const uint32_t q = (G.self + 1u + i) % G.n;
+				first[i + 1] = first[i] + (i < G.n ? min(__ldcg(G.slice_nblk[q] + s), P.slice_cap) : 0u);
+			}
+			const uint32_t total = first[kMaxPeers];
+			auto locate = [&](uint32_t g, const uint32_t*& list, const uint32_t*& ent, uint32_t& j) {
+				uint32_t i = 0;
 #pragma unroll
-					for (int u = 0; u < kV; u++)
-						vb[u] = lane + 32u * u < fb ? __ldcg(eb + lane + 32u * u) : kVoid;
+				for (uint32_t t = 1; t < kMaxPeers; t++)
+					i += g >= first[t] ? 1u : 0u;
+				const uint32_t q = (G.self + 1u + i) % G.n;
+				list = G.slice_blocks[q] + (size_t)s * P.slice_cap;
+				ent = G.entries[q];
+				j = g - first[i];
+			};
+			for (uint32_t g = j0; g < total; g += 2 * jstep) { // two blocks in flight per warp (remote latency)
+				const uint32_t *la_list, *ea_base, *lb_list = nullptr, *eb_base = nullptr;
+				uint32_t ja, jb = 0;
+				locate(g, la_list, ea_base, ja);
+				const bool have_b = g + jstep < total;
+				if (have_b)
+					locate(g + jstep, lb_list, eb_base, jb);
+				const uint32_t la = __ldcg(la_list + ja), lb = have_b ? __ldcg(lb_list + jb) : kVoid;
+				const uint32_t fa = la == kVoid ? 0u : min(la & 511u, kBlkEntries), fb = lb == kVoid ? 0u : min(lb & 511u, kBlkEntries);
+				const uint32_t* ea = ea_base + (size_t)(la >> 9) * kBlkEntries;
+				const uint32_t* eb = have_b ? eb_base + (size_t)(lb >> 9) * kBlkEntries : ea;
+				uint32_t va[kV], vb[kV];
 #pragma unroll
-					for (int u = 0; u < kV; u++)
-						if (va[u] != kVoid)
-							atomicAdd(ctr + va[u], 1u);
+				for (int u = 0; u < kV; u++)
+					va[u] = lane + 32u * u < fa ? __ldcg(ea + lane + 32u * u) : kVoid;
 #pragma unroll
-					for (int u = 0; u < kV; u++)
-						if (vb[u] != kVoid)
-							atomicAdd(ctr + vb[u], 1u);
-				}
+				for (int u = 0; u < kV; u++)
+					vb[u] = lane + 32u * u < fb ? __ldcg(eb + lane + 32u * u) : kVoid;
+#pragma unroll
+				for (int u = 0; u < kV; u++)
+					if (va[u] != kVoid)
+						atomicAdd(ctr + va[u], 1u);
+#pragma unroll
+				for (int u = 0; u < kV; u++)
+					if (vb[u] != kVoid)
+						atomicAdd(ctr + vb[u], 1u);
 			}
 			role_sync(role);
 			if (rtid == 0)

@@ -9,7 +9,9 @@
 // common case is one shared-memory byte load per k-mer; the rare rise is a compare-and-swap of the 32-bit word holding
 // the byte (per-byte max = __vmaxu4).  A CTA starts from the registers already in HBM and merges back only the words
 // that rose.  nBits > 17 does not fit shared memory: the same update runs on the registers in global memory (L2 resident).
+#include "hit_hash.cuh"
 #include "launch.h"
+#include "pipeline.h"
 #include "sketch_common.cuh"
 
 namespace ntc {
@@ -196,6 +198,85 @@ cudaError_t launch_hll(const BatchView& b, bool record_is_piece, uint64_t n_piec
 			NTC_HLL_LAUNCH(false, false);
 	}
 #undef NTC_HLL_LAUNCH
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: bit-sliced pre-filter (scan_kernel, MODE 1) + this kernel
+// ------------------------------------------------------------------------------------------------
+// Once every register is >= T - 1, only k-mers whose canonical hash has its top T bits zero can raise one (ntComp raises a
+// register only when clz > register, nthll.cpp:94-95).  The scan kernel marks exactly those (1 in 2^(T-1): T = 9 -> 0.4 %) at
+// ~5 instructions per k-mer instead of the ~100 of the 64-bit recurrence above; this kernel walks the mask words, re-hashes
+// the marked k-mers in full (hit_hash.cuh) and applies ntComp to the registers in global memory (64 KB: L2 resident).
+// Registers stay bit-exact: the filter has no false negatives, and every candidate goes through the same ntComp.
+__global__ void __launch_bounds__(256) hll_hit_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles,
+    uint32_t npos_max, const uint32_t* __restrict__ masks, const uint32_t* __restrict__ tile_info, const uint4* __restrict__ d_tab,
+    const pl::HashK K, uint32_t nBits, uint32_t* __restrict__ regs)
+{
+	__shared__ uint4 tab[8 * 256];
+	for (uint32_t i = threadIdx.x; i < 8 * 256; i += blockDim.x)
+		tab[i] = d_tab[i];
+	__syncthreads();
+	const uint64_t low_mask = ((uint64_t)1 << nBits) - 1;
+	const uint32_t last = stride - 2u;
+	const uint64_t per_tile = (uint64_t)npos_max * 32u, total = (uint64_t)n_tiles * per_tile;
+	for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t x = __ldcs(masks + w);
+		if (!x)
+			continue;
+		const uint32_t tile = (uint32_t)(w / per_tile), r = (uint32_t)((w - (uint64_t)tile * per_tile) >> 5), ln = (uint32_t)w & 31u;
+		const uint32_t info = __ldg(tile_info + tile);
+		if (info == pl::kTileFlag || r >= info) // rows past the tile's k-mer positions hold nothing (the scan kernel zeroed them)
+			continue;
+		while (x) {
+			const uint32_t s = 31u - (uint32_t)__clz(x);
+			x ^= 1u << s;
+			const uint32_t rec = tile * pl::kTileRecs + s * 32u + ln;
+			if (rec >= n_rec)
+				continue; // slots past the end of the batch
+			const uint32_t* rw = words + (uint64_t)rec * stride + 1;
+			if (r + K.k > __ldg(rw - 1))
+				continue; // past the end of a shorter record of a mixed-length tile (it ran on the padding)
+			const uint64_t h = pl::canonical_hash<false>(K, tab, pl::hit_issue<false>(rw, r, last), rw, r, last);
+			hll_comp(h, regs, low_mask);
+		}
+	}
+}
+
+cudaError_t launch_hll_hit(const uint32_t* d_words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, uint32_t npos_max, const uint32_t* d_masks,
+    const uint32_t* d_tile_info, const uint4* d_tab, uint32_t k, uint32_t nBits, uint8_t* d_regs, int n_sm, cudaStream_t st)
+{
+	const pl::HashK K = pl::make_hashk(k);
+	hll_hit_kernel<<<(unsigned)n_sm * 8u, 256, 0, st>>>(d_words, stride, n_rec, n_tiles, npos_max, d_masks, d_tile_info, d_tab, K, nBits,
+	    reinterpret_cast<uint32_t*>(d_regs));
+	return cudaGetLastError();
+}
+
+// smallest register (what the pre-filter may assume), one CTA
+__global__ void __launch_bounds__(1024) hll_min_kernel(const uint32_t* __restrict__ regs, uint32_t n_words, uint32_t n_regs, uint32_t* __restrict__ out)
+{
+	__shared__ uint32_t s_min;
+	if (threadIdx.x == 0)
+		s_min = 255u;
+	__syncthreads();
+	uint32_t m = 0xFFFFFFFFu; // per-byte minimum
+	for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x)
+		m = __vminu4(m, __ldcg(regs + i));
+	uint32_t v = 255u;
+	for (uint32_t j = 0; j < 4 && j < n_regs; j++)
+		v = min(v, (m >> (8 * j)) & 0xFFu);
+	v = __reduce_min_sync(0xFFFFFFFFu, v);
+	if ((threadIdx.x & 31u) == 0)
+		atomicMin(&s_min, v);
+	__syncthreads();
+	if (threadIdx.x == 0)
+		*out = s_min;
+}
+
+cudaError_t launch_hll_min(const uint8_t* d_regs, uint32_t nBits, uint32_t* d_out, cudaStream_t st)
+{
+	const uint32_t n_regs = 1u << nBits, n_words = nBits >= 2 ? (1u << (nBits - 2)) : 1u;
+	hll_min_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const uint32_t*>(d_regs), n_words, n_regs, d_out);
 	return cudaGetLastError();
 }
 

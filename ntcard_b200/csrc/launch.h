@@ -41,6 +41,10 @@ cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_p
 cudaError_t launch_hll(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,
     const uint32_t* d_piece_rec, const DevParams* d_params, uint32_t nBits, uint8_t* d_regs, unsigned long long* d_f1, int n_sm,
     cudaStream_t st);
+// nthll fast path: mask words of the pre-filter scan -> full hash -> ntComp on the registers; smallest register
+cudaError_t launch_hll_hit(const uint32_t* d_words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, uint32_t npos_max, const uint32_t* d_masks,
+    const uint32_t* d_tile_info, const uint4* d_tab, uint32_t k, uint32_t nBits, uint8_t* d_regs, int n_sm, cudaStream_t st);
+cudaError_t launch_hll_min(const uint8_t* d_regs, uint32_t nBits, uint32_t* d_out, cudaStream_t st);
 cudaError_t launch_narrow_hist(const uint32_t* d_counters, uint32_t n_tables, uint64_t n_per_table, uint16_t* d_narrow,
     uint32_t* d_phist, cudaStream_t st);
 cudaError_t launch_hist_range(const uint32_t* d_src, uint64_t first, uint64_t n, uint32_t rBits, uint32_t* d_phist, cudaStream_t st);

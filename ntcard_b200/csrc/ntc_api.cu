@@ -79,6 +79,13 @@ struct ntc_ctx {
 	uint8_t* d_hll = nullptr; // 2^hll_bits one-byte registers
 	bool own_hll = false;
 	size_t hll_bytes = 0;
+	// nthll fast path: the smallest register as last seen by the host (registers only rise, so a stale value is a safe bound)
+	uint32_t hll_min = 0;
+	uint32_t* d_hll_scratch = nullptr;   // [0] smallest register (hll_min_kernel), [2..3] candidate count, [4..] scan-kernel control words
+	uint32_t* h_hll_min = nullptr;       // pinned
+	cudaEvent_t hll_min_ev = nullptr;
+	bool hll_min_pending = false;
+	bool hll_fast = true;                // NTC_HLL_FAST=0: the 64-bit recurrence only
 	uint32_t* d_counters = nullptr;
 	bool own_counters = false;
 	size_t n_counters = 0;
@@ -268,7 +275,9 @@ int pool_create(ntc_ctx* c)
 	P.ahead = getenv("NTC_APPLY_AHEAD") ? (uint32_t)atoi(getenv("NTC_APPLY_AHEAD")) : 2u;
 	const uint32_t idx_bits = c->rBits + 1;
 	{
-		const uint32_t ss = getenv("NTC_SLICE_SHIFT") ? (uint32_t)atoi(getenv("NTC_SLICE_SHIFT")) : 23u; // 2^23 counters = 32 MiB
+		// 2^22 counters = 16 MiB per slice, 64 slices per k at r = 27 (measured, 10 M reads: apply 0.347 ms against 0.371 ms with 2^23,
+		// 0.74 ms with 2^24 -- the slices being zeroed, applied and evicted must all fit L2; profiles/r02_apply_tuning.txt)
+		const uint32_t ss = getenv("NTC_SLICE_SHIFT") ? (uint32_t)atoi(getenv("NTC_SLICE_SHIFT")) : 22u;
 		P.bin_shift = idx_bits <= ss ? idx_bits : std::max(ss, idx_bits - 6u); // <= 64 slices per k
 	}
 	P.nbins = 1u << (idx_bits - P.bin_shift);
@@ -654,7 +663,7 @@ int run_roll64(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece, uint32
 }
 
 // nthll mode: every canonical hash of the batch into the HyperLogLog registers (hll_kernels.cu)
-int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
+int run_hll_general(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 {
 	int rc;
 	uint64_t bound = 0;
@@ -663,6 +672,116 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 	CK(ntc::launch_hll(b, record_is_piece, bound, c->d_piece_first, c->d_piece_rec, c->d_params, c->hll_bits, c->d_hll, c->d_f1, c->n_sm,
 	    c->stream));
 	c->n_launches += 1;
+	return NTC_OK;
+}
+
+// smallest register -> pinned host word, asynchronously; hll_min_poll() picks it up when it has arrived
+int hll_min_request(ntc_ctx* c)
+{
+	if (!c->d_hll_scratch) {
+		CK(cudaMalloc((void**)&c->d_hll_scratch, 16 * sizeof(uint32_t)));
+		CK(cudaMemset(c->d_hll_scratch, 0, 16 * sizeof(uint32_t)));
+		CK(cudaHostAlloc((void**)&c->h_hll_min, sizeof(uint32_t), cudaHostAllocDefault));
+		CK(cudaEventCreateWithFlags(&c->hll_min_ev, cudaEventDisableTiming));
+	}
+	CK(ntc::launch_hll_min(c->d_hll, c->hll_bits, c->d_hll_scratch, c->stream));
+	CK(cudaMemcpyAsync(c->h_hll_min, c->d_hll_scratch, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaEventRecord(c->hll_min_ev, c->stream));
+	c->hll_min_pending = true;
+	c->n_launches++;
+	return NTC_OK;
+}
+int hll_min_poll(ntc_ctx* c, bool wait)
+{
+	if (!c->hll_min_pending)
+		return NTC_OK;
+	cudaError_t e = wait ? cudaEventSynchronize(c->hll_min_ev) : cudaEventQuery(c->hll_min_ev);
+	if (e == cudaErrorNotReady) {
+		cudaGetLastError();
+		return NTC_OK;
+	}
+	CK(e);
+	c->hll_min = std::max(c->hll_min, *c->h_hll_min);
+	c->hll_min_pending = false;
+	return NTC_OK;
+}
+
+// nthll mode: every canonical hash of the batch into the HyperLogLog registers (hll_kernels.cu).  Uniform-stride batches take
+// the bit-sliced pre-filter (scan kernel, "top T bits zero") + hll_hit_kernel as soon as every register has reached T - 1;
+// until then -- the first ~2 M reads of a run at 2^16 registers -- chunks go through the 64-bit recurrence.
+int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
+{
+	int rc;
+	const unsigned k = c->k[0];
+	const uint32_t max_len = b.off ? 0 : (b.stride - 1) * 16;
+	const bool eligible = c->hll_fast && c->use_pipeline && !b.off && record_is_piece && b.stride >= 4 && !(b.stride & 3u) && b.n_rec >= 4096 &&
+	                      !(reinterpret_cast<uintptr_t>(b.words) & 15u) && k < 288 && max_len >= k && max_len - k + 1 <= 65535 &&
+	                      ntc::pl::have_scan_kernel(k, 7);
+	if (!eligible)
+		return run_hll_general(c, b, record_is_piece);
+	const uint32_t ring = (k + 16 + 15) & ~15u;
+	const size_t per_warp = (size_t)(ring + 3) * 256;
+	const uint32_t nw = (uint32_t)std::min<size_t>(8, ntc::pl::kSmemMax / per_warp);
+	if (nw < 1)
+		return run_hll_general(c, b, record_is_piece);
+	const uint32_t npos_max = max_len - k + 1;
+	uint32_t done = 0;
+	while (done < b.n_rec) {
+		if ((rc = hll_min_poll(c, false)))
+			return rc;
+		const unsigned T = c->hll_min >= 12 ? 13u : c->hll_min >= 8 ? 9u : 0u;
+		ntc::BatchView sub = b;
+		sub.words = b.words + (uint64_t)done * b.stride;
+		if (!T) {
+			// registers still low: 2 M records through the 64-bit recurrence, then look at the smallest register again
+			sub.n_rec = std::min<uint32_t>(b.n_rec - done, 2u << 20);
+			sub.n_words = (uint64_t)sub.n_rec * b.stride;
+			if ((rc = run_hll_general(c, sub, true)) || (rc = hll_min_request(c)) || (rc = hll_min_poll(c, true)))
+				return rc;
+			done += sub.n_rec;
+			continue;
+		}
+		sub.n_rec = b.n_rec - done;
+		sub.n_words = (uint64_t)sub.n_rec * b.stride;
+		const uint32_t n_tiles = (sub.n_rec + 1023) / 1024;
+		if ((rc = grow(&c->d_masks, &c->cap_masks, (size_t)n_tiles * npos_max * 32, false)) ||
+		    (rc = grow(&c->d_tile_info, &c->cap_tile_info, (size_t)n_tiles, false)))
+			return rc;
+		ntc::pl::ScanArgs sa;
+		sa.words = sub.words;
+		sa.stride = sub.stride;
+		sa.n_rec = sub.n_rec;
+		sa.L.k = k;
+		sa.L.ring = ring;
+		sa.L.nwarps = nw;
+		sa.L.npos_max = npos_max;
+		sa.L.start_limit = 0;
+		sa.L.mixed_ok = 1; // a candidate on a shorter record's zero padding is dropped by its length (hll_hit_kernel)
+		sa.L.prefetch = c->scan_prefetch;
+		memcpy(sa.L.F0, c->kinit[0].F0, sizeof sa.L.F0);
+		memcpy(sa.L.R0, c->kinit[0].R0, sizeof sa.L.R0);
+		sa.masks = c->d_masks;
+		sa.tile_info = c->d_tile_info;
+		sa.f1_k = c->d_f1;
+		sa.cand = reinterpret_cast<unsigned long long*>(c->d_hll_scratch + 2);
+		sa.ctl = c->d_hll_scratch + 4;
+		sa.grid = std::min<unsigned>((unsigned)c->n_sm, n_tiles);
+		sa.smem_bytes = nw * per_warp;
+		sa.stream = c->stream;
+		if ((rc = stage_begin(c, 0)))
+			return rc;
+		CK(ntc::pl::launch_hllscan(k, T, sa));
+		if ((rc = stage_end(c)) || (rc = stage_begin(c, 1)))
+			return rc;
+		CK(ntc::launch_hll_hit(sub.words, sub.stride, sub.n_rec, n_tiles, npos_max, c->d_masks, c->d_tile_info, c->d_bs_tab, k, c->hll_bits, c->d_hll,
+		    c->n_sm, c->stream));
+		if ((rc = stage_end(c)))
+			return rc;
+		c->n_launches += 2;
+		if (T < 13 && (rc = hll_min_request(c))) // a later batch may be able to use the sharper filter
+			return rc;
+		done = b.n_rec;
+	}
 	return NTC_OK;
 }
 
@@ -965,7 +1084,7 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 	ntc::DevParams hp;
 	build_params(c, &hp);
 	CKF(cudaMemcpy(c->d_params, &hp, sizeof hp, cudaMemcpyHostToDevice));
-	if (!hll_bits) {
+	{
 		std::vector<uint32_t> tab(8 * 256 * 4);
 		ntc::pl::build_tables(tab.data());
 		CKF(cudaMalloc((void**)&c->d_bs_tab, tab.size() * sizeof(uint32_t)));
@@ -979,7 +1098,7 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 					fh = ntc::srol(fh) ^ ntc::seed_of(0);
 					rh = ntc::srol(rh) ^ ntc::seed_of(3);
 				}
-				L.polyA_sampled = ntc::sample_table(rh < fh ? rh : fh, sBits) < 2;
+				L.polyA_sampled = !hll_bits && ntc::sample_table(rh < fh ? rh : fh, sBits) < 2;
 			}
 		}
 	}
@@ -989,6 +1108,7 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 	if (getenv("NTC_FUSED_DBG"))
 		c->fused_dbg = (unsigned)atoi(getenv("NTC_FUSED_DBG"));
 	c->no_retile = getenv("NTC_NO_RETILE") != nullptr;
+	c->hll_fast = !(getenv("NTC_HLL_FAST") && atoi(getenv("NTC_HLL_FAST")) == 0);
 	// two 8-byte cudaMemsetAsync per batch (default) or one 1-thread kernel (NTC_CLEAR_MEMSET=0): measured, the kernel variant makes the host
 	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
 	c->clear_by_memset = !(getenv("NTC_CLEAR_MEMSET") && atoi(getenv("NTC_CLEAR_MEMSET")) == 0);
@@ -1085,6 +1205,9 @@ void ntc_destroy(ntc_ctx* c)
 	}
 	if (c->d_tile_info) cudaFree(c->d_tile_info);
 	if (c->d_offchk) cudaFree(c->d_offchk);
+	if (c->d_hll_scratch) cudaFree(c->d_hll_scratch);
+	if (c->h_hll_min) cudaFreeHost(c->h_hll_min);
+	if (c->hll_min_ev) cudaEventDestroy(c->hll_min_ev);
 	if (c->own_counters && c->d_counters) cudaFree(c->d_counters);
 	if (c->own_hll && c->d_hll) cudaFree(c->d_hll);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1105,6 +1228,10 @@ int ntc_reset(ntc_ctx* c)
 	if (c->hll_bits) { // nthll mode: fresh registers (nthll.cpp:200-201)
 		CK(cudaMemsetAsync(c->d_hll, 0, c->hll_bytes, c->stream));
 		CK(cudaMemsetAsync(c->d_f1, 0, NTC_MAX_K * sizeof(unsigned long long), c->stream));
+		if (c->hll_min_pending) // a minimum still in flight belongs to the old registers
+			CK(cudaEventSynchronize(c->hll_min_ev));
+		c->hll_min_pending = false;
+		c->hll_min = 0;
 		c->totals_overridden = false;
 		c->pending = false;
 		return NTC_OK;
@@ -1525,6 +1652,7 @@ int ntc_peer_attach(ntc_ctx* c, int world, int rank, const void* all_handles)
 		c->peers.slice_nblk[q] = slab + ntc::pl::CTL_WORDS;
 	}
 	c->peers.n = (uint32_t)world;
+	c->peers.self = (uint32_t)rank;
 	c->peer_world = world;
 	c->peer_rank = rank;
 	return NTC_OK;
@@ -1562,6 +1690,7 @@ int ntc_peer_attach_contexts(ntc_ctx* c, int world, int rank, ntc_ctx* const* al
 		c->peers.slice_nblk[q] = o->pool.slice_nblk;
 	}
 	c->peers.n = (uint32_t)world;
+	c->peers.self = (uint32_t)rank;
 	c->peer_world = world;
 	c->peer_rank = rank;
 	return NTC_OK;

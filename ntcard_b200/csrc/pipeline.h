@@ -62,7 +62,7 @@ struct PeerLogs {                // the hit logs of all ranks of one node, mappe
 	const uint32_t* entries[kMaxPeers];
 	const uint32_t* slice_blocks[kMaxPeers];
 	const uint32_t* slice_nblk[kMaxPeers];
-	uint32_t n;
+	uint32_t n, self;            // number of ranks, this rank
 };
 
 struct HashK {                   // per-k constants of the block-wise full hash (hit_hash.cuh: make_hashk)
@@ -133,6 +133,8 @@ bool have_scan_kernel(unsigned k, unsigned sBits);
 void build_tables(uint32_t* tab /* 8*256*4 words */);
 cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a);
 cudaError_t launch_fused(unsigned k, unsigned sBits, const FusedArgs& a);
+// nthll pre-filter (hll_kernels.cu): the scan kernel with "top T bits of the canonical hash are zero" as its predicate; T = 9 or 13
+cudaError_t launch_hllscan(unsigned k, unsigned T, const ScanArgs& a);
 size_t fused_smem_bytes(uint32_t ring, uint32_t nwarps, uint32_t qlane, uint32_t nbins);
 bool hit_can_stage(uint32_t stride, uint32_t units_per_tile, uint32_t tiles_per_unit);
 unsigned hit_groups_per_sm(bool staged);

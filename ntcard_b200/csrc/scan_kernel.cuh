@@ -44,23 +44,24 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p, uint64_t policy)
 // 0..2, so the kScanBlock slots of a block can be addressed from one base without wrapping.  The k "virtual"
 // positions before the read (window not full yet) are the k slots before slot 0, zeroed at the start of a tile.
 // pin / pout / mb: plane slot of the block's first entering / leaving position, mask row of its first position.
-template <int KM, int S, int U> struct ScanBlock {
+// MODE 0: ntComp's sampling predicate with sBits = S; MODE 1: nthll pre-filter, top S bits of the canonical hash all zero
+template <int KM, int S, int U, int MODE> struct ScanBlock {
 	static __device__ __forceinline__ void run(bs::State& st, const uint2* __restrict__ pin, const uint2* __restrict__ pout,
 	    uint32_t* __restrict__ mb, int qb, int k, int n, uint32_t& cand)
 	{
 		const uint2 in = pin[U * 32];
 		const uint2 out = pout[U * 32];
 		bs::step<KM, U>(st, in.x, in.y, out.x, out.y);
-		const uint32_t m = bs::sampled_mask<U, S>(st); // slots past the end of the batch are dropped by the hit kernel
+		const uint32_t m = MODE ? bs::zero_top_mask<U, S>(st) : bs::sampled_mask<U, S>(st); // slots past the end of the batch are dropped by the hit kernel
 		const int q = qb + U;
 		if (q >= k - 1 && q < n) {
 			__stcs(mb + U * 32, m); // streaming store: read once by the hit kernel
 			cand += __popc(m);
 		}
-		ScanBlock<KM, S, U + 1>::run(st, pin, pout, mb, qb, k, n, cand);
+		ScanBlock<KM, S, U + 1, MODE>::run(st, pin, pout, mb, qb, k, n, cand);
 	}
 };
-template <int KM, int S> struct ScanBlock<KM, S, kScanBlock> {
+template <int KM, int S, int MODE> struct ScanBlock<KM, S, kScanBlock, MODE> {
 	static __device__ __forceinline__ void run(bs::State&, const uint2* __restrict__, const uint2* __restrict__, uint32_t* __restrict__, int, int, int,
 	    uint32_t&)
 	{
@@ -88,7 +89,7 @@ __device__ __forceinline__ void zero_rows(uint32_t* __restrict__ masks, uint32_t
 		__stcs(p + (size_t)r * 32, 0u);
 }
 
-template <int KM, int S>
+template <int KM, int S, int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec, ScanLaunch L,
     uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_info, unsigned long long* __restrict__ f1_k,
     unsigned long long* __restrict__ cand_out, uint32_t* __restrict__ ctl)
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			for (int qb = q0; qb < q0 + nq; qb += kScanBlock) {
 				int ob = cout + (qb - q0);
 				ob = ob >= R ? ob - R : ob; // a block may start up to 3 slots before the end of the ring: mirror slots
-				ScanBlock<KM, S, 0>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, mptr, qb, k, n, cand);
+				ScanBlock<KM, S, 0, MODE>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, mptr, qb, k, n, cand);
 				scan_rotate_home(st);
 				mptr += kScanBlock * 32;
 			}
@@ -276,10 +277,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 	}
 }
 
-template <int KM, int S>
+template <int KM, int S, int MODE = 0>
 cudaError_t launch_scan_one(const ScanArgs& a)
 {
-	auto kern = scan_kernel<KM, S>;
+	auto kern = scan_kernel<KM, S, MODE>;
 	// the opt-in shared-memory limit is a property of (function, device): set it when it has to grow, not on every launch
 	static size_t smem_set[64] = {};
 	int dev = 0;

@@ -183,6 +183,36 @@ def test_device_hll_uniform_batches_and_modes(oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k,nBits,L", [(32, 16, 150), (25, 14, 100), (64, 16, 151)])
+def test_device_hll_fast_path_at_size_is_bit_exact(oracle, k, nBits, L):
+    """Large uniform batches: after the first chunk every register is high enough for the bit-sliced pre-filter ("top T bits
+    of the canonical hash are zero", scan kernel) + hll_hit_kernel to take over from the 64-bit recurrence.  The registers
+    must stay bit-exact against the oracle (the filter has no false negatives; every candidate goes through nthll's ntComp),
+    over several batches (the sharper T = 13 filter once the registers allow it), and after a reset."""
+    import os
+    n = 4_000_000
+    stride = nt.stride_words(L)
+    a = oracle.gen_reads(51, 0, n, L, 0, 0)
+    off = np.arange(n + 1, dtype=np.uint64) * L
+    want = np.zeros(1 << nBits, dtype=np.uint8)
+    oracle.lib.orc_hll_batch(a.ctypes.data, off.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint64)), n, k, nBits,
+                             want.ctypes.data, os.cpu_count() or 1)
+    del a
+    words = nt.gen_packed(51, 0, n, L, 0, 0, stride)
+    with nt.HllSketch(k, nBits) as h:
+        for rep in range(2):
+            h.reset()
+            half = n // 2
+            h.submit(words[:half * stride], None, half, stride)          # chunks through the recurrence, then the filter
+            h.submit(words[half * stride:], None, n - half, stride)      # filter from the start
+            regs, nk = h.finish()
+            assert nk == n * (L - k + 1)
+            assert np.array_equal(regs, want), (k, nBits, rep, int((regs != want).sum()))
+        launches = h.stats()["launches"]
+    assert launches >= 8  # (general chunk + min) + (scan + hit) ... per pass: the fast path did run
+
+
+@pytest.mark.gpu
 def test_device_hll_caller_owned_registers_merge_by_max(oracle):
     """two contexts on one device, sharded reads, registers in torch tensors, merged by max = one context over all reads
     (the N>1 path without a second GPU: ntcard_b200.dist.all_reduce_hll does torch.maximum's job across ranks)"""
