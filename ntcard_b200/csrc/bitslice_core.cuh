@@ -241,17 +241,41 @@ BS_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel)
 #endif
 }
 
-template <int JJ, uint32_t M> BS_HD void tr_stage(uint32_t (&A)[32])
+// m ? x : y, bit by bit, as ONE logic op with the mask in a register.  Written as (x & M) | (y & ~M) with a literal mask the
+// compiler emits two LOP3 per output (an instruction takes one immediate): 96 extra ALU instructions per 16 positions.
+BS_HD uint32_t bitsel(uint32_t x, uint32_t y, uint32_t m)
 {
 #if defined(__CUDA_ARCH__)
+	uint32_t d;
+	asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(x), "r"(y), "r"(m));
+	return d;
+#else
+	return (x & m) | (y & ~m);
+#endif
+}
+
+template <int JJ, uint32_t M> BS_HD void tr_stage(uint32_t (&A)[32])
+{
+	uint32_t m = M;
+#if defined(__CUDA_ARCH__)
+	asm volatile("" : "+r"(m)); // keep the mask in a register: the select below needs three register operands
 #pragma unroll
 #endif
 	for (int s = 0; s < 32; s++) {
 		if (s & JJ)
 			continue;
 		const uint32_t a = A[s], b = A[s + JJ];
-		A[s] = (a & M) | ((b << JJ) & ~M);
-		A[s + JJ] = ((a >> JJ) & M) | (b & ~M);
+#if defined(__CUDA_ARCH__)
+		// the shifts as multiplications: IMAD / IMAD.HI issue on the FMA pipe, which is idle, instead of the ALU pipe, which bounds the kernel
+		uint32_t bl, ar;
+		asm("mul.lo.u32 %0, %1, %2;" : "=r"(bl) : "r"(b), "r"(1u << JJ));
+		asm("mul.hi.u32 %0, %1, %2;" : "=r"(ar) : "r"(a), "r"(1u << (32 - JJ)));
+		A[s] = bitsel(a, bl, m);
+		A[s + JJ] = bitsel(ar, b, m);
+#else
+		A[s] = bitsel(a, b << JJ, m);
+		A[s + JJ] = bitsel(a >> JJ, b, m);
+#endif
 	}
 }
 

@@ -644,32 +644,38 @@ __global__ void __launch_bounds__(kApplyThreads) apply_owned_kernel(const Pool P
 				ent = G.entries[q];
 				j = g - first[i];
 			};
-			for (uint32_t g = j0; g < total; g += 2 * jstep) { // two blocks in flight per warp (remote latency)
-				const uint32_t *la_list, *ea_base, *lb_list = nullptr, *eb_base = nullptr;
-				uint32_t ja, jb = 0;
-				locate(g, la_list, ea_base, ja);
-				const bool have_b = g + jstep < total;
-				if (have_b)
-					locate(g + jstep, lb_list, eb_base, jb);
-				const uint32_t la = __ldcg(la_list + ja), lb = have_b ? __ldcg(lb_list + jb) : kVoid;
-				const uint32_t fa = la == kVoid ? 0u : min(la & 511u, kBlkEntries), fb = lb == kVoid ? 0u : min(lb & 511u, kBlkEntries);
-				const uint32_t* ea = ea_base + (size_t)(la >> 9) * kBlkEntries;
-				const uint32_t* eb = have_b ? eb_base + (size_t)(lb >> 9) * kBlkEntries : ea;
-				uint32_t va[kV], vb[kV];
+			constexpr int kFly = 4; // blocks in flight per warp: a list entry, then 1 KB of entries, each an NVLink round trip
+			for (uint32_t g = j0; g < total; g += kFly * jstep) {
+				const uint32_t* eb[kFly];
+				uint32_t fl[kFly];
+				uint32_t le[kFly];
 #pragma unroll
-				for (int u = 0; u < kV; u++)
-					va[u] = lane + 32u * u < fa ? __ldcg(ea + lane + 32u * u) : kVoid;
+				for (int f = 0; f < kFly; f++) {
+					const uint32_t gf = g + f * jstep;
+					le[f] = kVoid;
+					eb[f] = nullptr;
+					if (gf < total) {
+						const uint32_t* list;
+						uint32_t j;
+						locate(gf, list, eb[f], j);
+						le[f] = __ldcg(list + j);
+					}
+				}
+				uint32_t v[kFly][kV];
 #pragma unroll
-				for (int u = 0; u < kV; u++)
-					vb[u] = lane + 32u * u < fb ? __ldcg(eb + lane + 32u * u) : kVoid;
+				for (int f = 0; f < kFly; f++) {
+					fl[f] = le[f] == kVoid ? 0u : min(le[f] & 511u, kBlkEntries);
+					const uint32_t* e = eb[f] + (size_t)(le[f] >> 9) * kBlkEntries;
 #pragma unroll
-				for (int u = 0; u < kV; u++)
-					if (va[u] != kVoid)
-						atomicAdd(ctr + va[u], 1u);
+					for (int u = 0; u < kV; u++)
+						v[f][u] = lane + 32u * u < fl[f] ? __ldcg(e + lane + 32u * u) : kVoid;
+				}
 #pragma unroll
-				for (int u = 0; u < kV; u++)
-					if (vb[u] != kVoid)
-						atomicAdd(ctr + vb[u], 1u);
+				for (int f = 0; f < kFly; f++)
+#pragma unroll
+					for (int u = 0; u < kV; u++)
+						if (v[f][u] != kVoid)
+							atomicAdd(ctr + v[f][u], 1u);
 			}
 			role_sync(role);
 			if (rtid == 0)

@@ -209,46 +209,120 @@ cudaError_t launch_hll(const BatchView& b, bool record_is_piece, uint64_t n_piec
 // ~5 instructions per k-mer instead of the ~100 of the 64-bit recurrence above; this kernel walks the mask words, re-hashes
 // the marked k-mers in full (hit_hash.cuh) and applies ntComp to the registers in global memory (64 KB: L2 resident).
 // Registers stay bit-exact: the filter has no false negatives, and every candidate goes through the same ntComp.
-__global__ void __launch_bounds__(256) hll_hit_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles,
-    uint32_t npos_max, const uint32_t* __restrict__ masks, const uint32_t* __restrict__ tile_info, const uint4* __restrict__ d_tab,
-    const pl::HashK K, uint32_t nBits, uint32_t* __restrict__ regs)
+// Candidates are rare (T = 9: one mask word in 8 has a bit), so a warp first COMPACTS them: every lane pushes the set bits of its
+// mask word into the warp's queue in shared memory, and whenever 32 are waiting all 32 lanes hash one each (walking the bits
+// lane by lane left 1 lane in 8 busy: 0.8 ms per 10 M reads instead of ~0.1).
+constexpr uint32_t kHllQueue = 32 + 32 * 4; // a full batch + what one more round of mask words may add on skewed data before draining
+
+struct HllHitArgs {
+	const uint32_t* words;
+	uint32_t stride, n_rec, n_tiles, npos_max;
+	const uint32_t* masks;
+	const uint32_t* tile_info;
+	const uint4* d_tab;
+	pl::HashK K;
+	uint32_t nBits;
+	uint32_t* regs;
+};
+
+__device__ __forceinline__ void hll_hit_one(const HllHitArgs& a, const uint4* __restrict__ tab, uint64_t w, uint32_t s, uint64_t per_tile, uint64_t low_mask)
+{
+	const uint32_t tile = (uint32_t)(w / per_tile), r = (uint32_t)((w - (uint64_t)tile * per_tile) >> 5), ln = (uint32_t)w & 31u;
+	const uint32_t rec = tile * pl::kTileRecs + s * 32u + ln;
+	if (rec >= a.n_rec)
+		return; // slots past the end of the batch
+	const uint32_t* rw = a.words + (uint64_t)rec * a.stride + 1;
+	if (r + a.K.k > __ldg(rw - 1))
+		return; // past the end of a shorter record of a mixed-length tile (it ran on the padding)
+	const uint32_t last = a.stride - 2u;
+	const uint64_t h = pl::canonical_hash<false>(a.K, tab, pl::hit_issue<false>(rw, r, last), rw, r, last);
+	hll_comp(h, a.regs, low_mask);
+}
+
+__global__ void __launch_bounds__(256) hll_hit_kernel(const HllHitArgs a)
 {
 	__shared__ uint4 tab[8 * 256];
+	__shared__ unsigned long long q_w[8][kHllQueue];
+	__shared__ uint8_t q_s[8][kHllQueue];
+	__shared__ uint32_t q_n[8];
 	for (uint32_t i = threadIdx.x; i < 8 * 256; i += blockDim.x)
-		tab[i] = d_tab[i];
+		tab[i] = a.d_tab[i];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	if (lane == 0)
+		q_n[warp] = 0;
 	__syncthreads();
-	const uint64_t low_mask = ((uint64_t)1 << nBits) - 1;
-	const uint32_t last = stride - 2u;
-	const uint64_t per_tile = (uint64_t)npos_max * 32u, total = (uint64_t)n_tiles * per_tile;
-	for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-		uint32_t x = __ldcs(masks + w);
-		if (!x)
-			continue;
-		const uint32_t tile = (uint32_t)(w / per_tile), r = (uint32_t)((w - (uint64_t)tile * per_tile) >> 5), ln = (uint32_t)w & 31u;
-		const uint32_t info = __ldg(tile_info + tile);
-		if (info == pl::kTileFlag || r >= info) // rows past the tile's k-mer positions hold nothing (the scan kernel zeroed them)
-			continue;
-		while (x) {
-			const uint32_t s = 31u - (uint32_t)__clz(x);
-			x ^= 1u << s;
-			const uint32_t rec = tile * pl::kTileRecs + s * 32u + ln;
-			if (rec >= n_rec)
-				continue; // slots past the end of the batch
-			const uint32_t* rw = words + (uint64_t)rec * stride + 1;
-			if (r + K.k > __ldg(rw - 1))
-				continue; // past the end of a shorter record of a mixed-length tile (it ran on the padding)
-			const uint64_t h = pl::canonical_hash<false>(K, tab, pl::hit_issue<false>(rw, r, last), rw, r, last);
-			hll_comp(h, regs, low_mask);
+	const uint64_t low_mask = ((uint64_t)1 << a.nBits) - 1;
+	const uint64_t per_tile = (uint64_t)a.npos_max * 32u, total = (uint64_t)a.n_tiles * per_tile;
+	const uint64_t n_iter = (total + 31) / 32; // warp-uniform trip count: one mask row (32 words) per warp and iteration
+	for (uint64_t it = (uint64_t)blockIdx.x * 8 + warp; it < n_iter; it += (uint64_t)gridDim.x * 8) {
+		const uint64_t w = it * 32 + lane;
+		uint32_t x = w < total ? __ldcs(a.masks + w) : 0u;
+		if (x) {
+			const uint32_t tile = (uint32_t)(w / per_tile), r = (uint32_t)((w - (uint64_t)tile * per_tile) >> 5);
+			const uint32_t info = __ldg(a.tile_info + tile);
+			if (info == pl::kTileFlag || r >= info) // rows past the tile's k-mer positions hold nothing
+				x = 0;
 		}
+		// skewed data (a low-complexity tile: every slot of a word marked): more set bits than the queue has room for -- those lanes
+		// hash their own bits directly
+		uint32_t cnt = (uint32_t)__popc(x);
+		const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, cnt);
+		if (tot == 0)
+			continue;
+		const uint32_t n0 = q_n[warp]; // every lane reads it before any lane adds to it
+		__syncwarp();
+		if (n0 + tot > kHllQueue) {
+			while (x) {
+				const uint32_t s = 31u - (uint32_t)__clz(x);
+				x ^= 1u << s;
+				hll_hit_one(a, tab, w, s, per_tile, low_mask);
+			}
+			__syncwarp();
+			continue;
+		}
+		if (x) {
+			uint32_t at = atomicAdd(&q_n[warp], cnt);
+			while (x) {
+				const uint32_t s = 31u - (uint32_t)__clz(x);
+				x ^= 1u << s;
+				q_w[warp][at] = w;
+				q_s[warp][at] = (uint8_t)s;
+				at++;
+			}
+		}
+		__syncwarp();
+		uint32_t n = q_n[warp];
+		while (n >= 32) { // a full batch: every lane hashes one candidate (taken from the end of the queue)
+			const uint32_t i = n - 32 + lane;
+			hll_hit_one(a, tab, q_w[warp][i], q_s[warp][i], per_tile, low_mask);
+			n -= 32;
+		}
+		__syncwarp();
+		if (lane == 0)
+			q_n[warp] = n;
+		__syncwarp();
 	}
+	const uint32_t n = q_n[warp];
+	if (lane < n)
+		hll_hit_one(a, tab, q_w[warp][lane], q_s[warp][lane], per_tile, low_mask);
 }
 
 cudaError_t launch_hll_hit(const uint32_t* d_words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, uint32_t npos_max, const uint32_t* d_masks,
     const uint32_t* d_tile_info, const uint4* d_tab, uint32_t k, uint32_t nBits, uint8_t* d_regs, int n_sm, cudaStream_t st)
 {
-	const pl::HashK K = pl::make_hashk(k);
-	hll_hit_kernel<<<(unsigned)n_sm * 8u, 256, 0, st>>>(d_words, stride, n_rec, n_tiles, npos_max, d_masks, d_tile_info, d_tab, K, nBits,
-	    reinterpret_cast<uint32_t*>(d_regs));
+	HllHitArgs a;
+	a.words = d_words;
+	a.stride = stride;
+	a.n_rec = n_rec;
+	a.n_tiles = n_tiles;
+	a.npos_max = npos_max;
+	a.masks = d_masks;
+	a.tile_info = d_tile_info;
+	a.d_tab = d_tab;
+	a.K = pl::make_hashk(k);
+	a.nBits = nBits;
+	a.regs = reinterpret_cast<uint32_t*>(d_regs);
+	hll_hit_kernel<<<(unsigned)n_sm * 8u, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
 
