@@ -192,7 +192,7 @@ def main():
     import torch.distributed as dist
 
     import ntcard_b200 as nt
-    from ntcard_b200.dist import PeerReducer, all_reduce_sketch, reduce_scatter_hist
+    from ntcard_b200.dist import PeerReducer, all_reduce_sketch, exchange_hist, reduce_scatter_hist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
@@ -244,8 +244,10 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize(dev)
 
-        reduce_kind = {"peer": 0, "dense": 0}
+        reduce_kind = {"peer": 0, "exchange": 0, "dense": 0}
         reducer = PeerReducer(sk, dev) if world > 1 else None
+        if reducer is not None and not reducer.ok and rank == 0:
+            print(f"bench.py: no peer access between the GPUs ({reducer.error}); falling back to the host-planned hit-log exchange", file=sys.stderr)
 
         def dense_reduce():
             """Fallback when some rank's hit log is no longer complete: reduce-scatter of the uint32 counters, histogram of
@@ -262,6 +264,15 @@ def main():
             histograms its slices; two small all-reduces (F1 + completeness flag before, the 512 KiB/k histogram after) are the
             only collectives and the only barriers.  No host synchronisation unless fetch: then the global histogram and F1
             are read back (and the dense fallback runs if a log was incomplete)."""
+            if not reducer.ok:  # no peer memory on this box: the round-1 reduction (hit-log all-to-all planned on the host)
+                tots = []
+                p = exchange_hist(sk, RBITS, dev, totals_out=tots)
+                if p is None:
+                    reduce_kind["dense"] += 1
+                    return dense_reduce()
+                reduce_kind["exchange"] += 1
+                sk.set_totals(tots[0])
+                return p
             reducer.reduce()
             if not fetch:
                 reduce_kind["peer"] += 1
@@ -347,8 +358,14 @@ def main():
         else:
             # untimed: the peer-memory reduction of one more step against the dense path (all-reduce of the uint32 counters,
             # histogram of the whole table) on the same reads -- the result must be identical, bin by bin
-            step_resident()
-            p_peer, f1 = reducer.result(RBITS)
+            if reducer.ok:
+                step_resident()
+                p_peer, f1 = reducer.result(RBITS)
+            else:
+                sk.reset()
+                submit_resident()
+                p_peer = reduce_sketch(True)
+                f1 = sk.totals()
             assert int(f1.sum()) == kmers_rank * world, (f1, kmers_rank, world)
             sk.reset()
             submit_resident()

@@ -617,10 +617,6 @@ __global__ void __launch_bounds__(kApplyThreads) apply_owned_kernel(const Pool P
 		const uint32_t j0 = blockIdx.x * nwarp + warp, jstep = gridDim.x * nwarp;
 		for (uint32_t si = 0; si < n_order; si++) {
 			const uint32_t s = order[si];
-			if (rtid == 0)
-				while (ld_acquire(P.zero_done + si) < gridDim.x)
-					__nanosleep(20);
-			role_sync(role);
 			uint32_t* ctr = counters + (size_t)(s / P.nbins) * per_k;
 			// The blocks of slice s in ALL logs form one index space (peer q', block j), walked by all warps together: a loop over
 			// the peers with a loop over blocks inside costs one NVLink round trip per (slice, peer) and leaves most warps idle
@@ -645,7 +641,11 @@ __global__ void __launch_bounds__(kApplyThreads) apply_owned_kernel(const Pool P
 				j = g - first[i];
 			};
 			constexpr int kFly = 4; // blocks in flight per warp: a list entry, then 1 KB of entries, each an NVLink round trip
-			for (uint32_t g = j0; g < total; g += kFly * jstep) {
+			// The loads of the first round are requested BEFORE the warp waits for the slice to be zeroed -- they do not depend on it,
+			// and with one round per warp and slice (9 k blocks, 2.4 k warps) the three remote round trips (block counts, list
+			// entries, entries) would otherwise be paid once per slice, one after the other, behind the zero-fill.
+			bool waited = false;
+			for (uint32_t g = j0; g < total || !waited; g += kFly * jstep) {
 				const uint32_t* eb[kFly];
 				uint32_t fl[kFly];
 				uint32_t le[kFly];
@@ -669,6 +669,13 @@ __global__ void __launch_bounds__(kApplyThreads) apply_owned_kernel(const Pool P
 #pragma unroll
 					for (int u = 0; u < kV; u++)
 						v[f][u] = lane + 32u * u < fl[f] ? __ldcg(e + lane + 32u * u) : kVoid;
+				}
+				if (!waited) { // every applier thread passes here exactly once per slice
+					if (rtid == 0)
+						while (ld_acquire(P.zero_done + si) < gridDim.x)
+							__nanosleep(20);
+					role_sync(role);
+					waited = true;
 				}
 #pragma unroll
 				for (int f = 0; f < kFly; f++)

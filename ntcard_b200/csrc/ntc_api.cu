@@ -275,9 +275,10 @@ int pool_create(ntc_ctx* c)
 	P.ahead = getenv("NTC_APPLY_AHEAD") ? (uint32_t)atoi(getenv("NTC_APPLY_AHEAD")) : 2u;
 	const uint32_t idx_bits = c->rBits + 1;
 	{
-		// 2^22 counters = 16 MiB per slice, 64 slices per k at r = 27 (measured, 10 M reads: apply 0.347 ms against 0.371 ms with 2^23,
-		// 0.74 ms with 2^24 -- the slices being zeroed, applied and evicted must all fit L2; profiles/r02_apply_tuning.txt)
-		const uint32_t ss = getenv("NTC_SLICE_SHIFT") ? (uint32_t)atoi(getenv("NTC_SLICE_SHIFT")) : 22u;
+		// 2^23 counters = 32 MiB per slice, 32 slices per k at r = 27.  Measured (profiles/r02_apply_tuning.txt): on one GPU 16 MiB slices
+		// are 2 % faster per step (apply 0.347 vs 0.371 ms), but the multi-GPU reduction pays a fixed cost per owned slice (remote round
+		// trips, hand-offs): 8 GPUs 7.9e12 k-mers/s with 32 MiB slices against 7.1e12 with 16 MiB; 64 MiB: apply 0.74 ms (L2 footprint)
+		const uint32_t ss = getenv("NTC_SLICE_SHIFT") ? (uint32_t)atoi(getenv("NTC_SLICE_SHIFT")) : 23u;
 		P.bin_shift = idx_bits <= ss ? idx_bits : std::max(ss, idx_bits - 6u); // <= 64 slices per k
 	}
 	P.nbins = 1u << (idx_bits - P.bin_shift);

@@ -195,7 +195,15 @@ class PeerReducer:
         self.nK = sketch.nK
         self.status = torch.zeros(self.nK + 1, dtype=torch.int64, device=device)
         self.hist = torch.zeros(self.nK * 2 * 65536, dtype=torch.int32, device=device)
-        peer_setup(sketch)
+        # every rank must be able to map every other rank's log (CUDA IPC + peer access); all ranks take the same decision
+        try:
+            peer_setup(sketch)
+            mine, self.error = 1, None
+        except Exception as e:  # e.g. no peer access between two devices
+            mine, self.error = 0, e
+        flag = torch.tensor([mine], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.ok = bool(flag.item())
 
     def reduce(self):
         self.sk.log_status_device(self.status.data_ptr())

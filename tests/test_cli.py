@@ -141,3 +141,36 @@ def test_golden_hist_layout(tmp_path):
     for i in range(1, 1001):
         a_, b_ = lines[i + 1].split("\t")
         assert int(a_) == i and int(b_) >= 0
+
+
+@pytest.mark.gpu
+def test_cli_more_threads_than_files_parses_one_file_in_parallel(tmp_path):
+    """-t N with fewer files than threads: the spare threads parse pieces of the same FASTQ / FASTA file (the reference reads a file
+    with one thread whatever -t says, ntcard.cpp:445).  The .hist files must be byte-identical to the -t1 run, also for a FASTQ
+    with CRLF line ends and N runs, and for multi-line FASTA."""
+    import numpy as np
+    n, L = 120_000, 150
+    a = nt.gen_ascii(9, 0, n, L, mode=2).reshape(n, L)
+    rec = np.empty((n, 2 * L + 9), dtype=np.uint8)                       # "@r\r\n" seq "\r\n+\r\n" qual "\r\n"
+    rec[:, 0:4] = np.frombuffer(b"@r\r\n", dtype=np.uint8)
+    rec[:, 4:4 + L] = a
+    rec[:, 4 + L:9 + L] = np.frombuffer(b"\r\n+\r\n", dtype=np.uint8)
+    rec[:, 9 + L:9 + 2 * L] = np.frombuffer(b"I" * L, dtype=np.uint8)
+    fq = tmp_path / "big_crlf.fq"
+    with open(fq, "wb") as f:
+        f.write(rec.tobytes().replace(b"I" * L, b"I" * L + b"\r\n"))
+    fa = tmp_path / "big.fa"
+    with open(fa, "wb") as f:
+        for i in range(n // 6):
+            s = bytes(a[i * 6:(i + 1) * 6].reshape(-1))
+            f.write(b">s%d\n" % i + b"\n".join(s[j:j + 80] for j in range(0, len(s), 80)) + b"\n")
+    assert os.path.getsize(fq) > 4 * (8 << 20) and os.path.getsize(fa) > 2 * (8 << 20)
+    for path, threads in ((fq, 4), (fa, 2)):
+        outs = []
+        for t in (1, threads):
+            pref = str(tmp_path / f"out_{path.name}_{t}")
+            r = run([f"-t{t}", "-k21,32", "-c40", "-p", pref, str(path)])
+            assert r.returncode == 0, r.stderr
+            outs.append([open(f"{pref}_k{k}.hist", "rb").read() for k in (21, 32)])
+        assert outs[0] == outs[1], path.name
+        assert b"F0\t" in outs[0][0] and not outs[0][0].startswith(b"F1\t0\n")

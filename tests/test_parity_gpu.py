@@ -521,7 +521,7 @@ def test_hit_log_exchange_between_two_contexts_on_one_gpu(oracle):
         counts = np.stack([c.astype(np.int64) for c, _, _ in got])
         infos = np.array([i for _, _, i in got], dtype=np.int64)
         n_slices = counts.shape[1]
-        assert n_slices == len(kList) * 16 and exchange_feasible(counts, infos)
+        assert n_slices == len(kList) * 8 and exchange_feasible(counts, infos)
         plans = [plan_exchange(counts, r) for r in range(2)]
         bufs = []
         for r in range(2):
