@@ -378,8 +378,7 @@ def main():
         # ---- e2e leg: host buffers through the C-ABI ------------------------------------------------
         e2e = None
         if not args.no_e2e:
-            # host buffers are packed tightly (1 length word + ceil(L/16) base words = 44 bytes per 150 bp read); the library
-            # pads the records to 16 bytes on the device
+            # host buffers are packed tightly; the library pads the records to 16 bytes on the device
             estride = nt.stride_words(L, False)
             if ragged:
                 # the ragged batches as the host packer made them, in pinned host memory: words + offsets per batch
@@ -393,13 +392,16 @@ def main():
                     e_words += nw + nr + 1
                 torch.cuda.synchronize(dev)
             else:
-                e_words = n_reads * estride
-                d_tight = torch.empty(e_words, dtype=torch.int32, device=dev)
+                # uniform reads of one length: no length words on the wire (ntc_submit_bases: ceil(L/16) words = 40 bytes per 150 bp read;
+                # the device adds the length word while padding the records to 16 bytes)
+                wpr = (L + 15) // 16
+                e_words = n_reads * wpr
+                d_tight = torch.empty(n_reads * estride, dtype=torch.int32, device=dev)
                 sk.gen_packed_device(gseed, first, n_reads, L, 0, 0, estride, d_tight.data_ptr())
                 pinned = nt.PinnedBuffer(e_words)
                 torch.cuda.synchronize(dev)
-                host_view = torch.from_numpy(pinned.array.view(np.int32))
-                host_view.copy_(d_tight)  # the same reads as the device-resident leg, now in pinned HOST memory
+                host_view = torch.from_numpy(pinned.array.view(np.int32)).view(n_reads, wpr)
+                host_view.copy_(d_tight.view(n_reads, estride)[:, 1:1 + wpr])  # the same reads as the device-resident leg, now in pinned HOST memory
                 del d_tight
             nchunk = max(1, args.e2e_chunks) if not ragged else len(rag)
             cper = (n_reads + nchunk - 1) // nchunk
@@ -413,7 +415,7 @@ def main():
                 for c in range(nchunk):
                     r0 = c * cper
                     r1 = min(n_reads, r0 + cper)
-                    sk.submit(pinned.array[r0 * estride:r1 * estride], None, r1 - r0, estride)
+                    sk.submit_bases(pinned.array[r0 * wpr:r1 * wpr], r1 - r0, L)
 
             def step_e2e():
                 sk.reset()

@@ -96,6 +96,10 @@ int ntc_set_gap(ntc_ctx* ctx, unsigned gap);
  * *ticket (optional) identifies the batch for ntc_wait(). */
 int ntc_submit(ntc_ctx* ctx, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec,
     uint32_t stride_words, uint64_t* ticket);
+/* Reads of ONE length (the common case: a sequencing run's 150 bp reads without N) need no length words: n_rec records of
+ * ceil(len_bases / 16) words of bases each, back to back -- 40 instead of 44 bytes per 150 bp read over PCIe, which is what bounds
+ * the end-to-end rate.  The length words are added on the device.  Otherwise like ntc_submit. */
+int ntc_submit_bases(ntc_ctx* ctx, const uint32_t* bases, size_t n_rec, uint32_t len_bases, uint64_t* ticket);
 /* Same, for a batch already resident in DEVICE memory (synthetic generator,
  * device-side producers).  The buffers must stay valid until ntc_sync(). */
 int ntc_submit_device(ntc_ctx* ctx, const uint32_t* d_words, size_t n_words, const uint32_t* d_off, size_t n_rec,

@@ -18,7 +18,7 @@ KERNEL_AUTO, KERNEL_ROLL64, KERNEL_BITSLICE = 0, 1, 2
 
 # every symbol include/ntcard_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_set_gap", "ntc_submit", "ntc_submit_device", "ntc_wait",
+    "ntc_create", "ntc_destroy", "ntc_reset", "ntc_set_kernel", "ntc_set_gap", "ntc_submit", "ntc_submit_bases", "ntc_submit_device", "ntc_wait",
     "ntc_sync", "ntc_flush", "ntc_log_info", "ntc_log_counts", "ntc_log_export", "ntc_log_import", "ntc_flush_slices",
     "ntc_hist_slices", "ntc_stream_sync", "ntc_counters_device", "ntc_hist_range", "ntc_totals", "ntc_totals_nosync", "ntc_set_totals", "ntc_finish", "ntc_estimate",
     "ntc_host_alloc", "ntc_host_free", "ntc_pack_bound", "ntc_pack_bound_k", "ntc_pack_seqs", "ntc_gen_ascii", "ntc_gen_packed",
@@ -50,6 +50,7 @@ def _load():
         "ntc_set_kernel": (C.c_int, [vp, C.c_int]),
         "ntc_set_gap": (C.c_int, [vp, C.c_uint]),
         "ntc_submit": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, u64p]),
+        "ntc_submit_bases": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, u64p]),
         "ntc_submit_device": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]),
         "ntc_wait": (C.c_int, [vp, C.c_uint64]),
         "ntc_sync": (C.c_int, [vp]),
@@ -265,6 +266,14 @@ class Sketch:
             _check(lib.ntc_submit(self.h, words.ctypes.data, len(words), off.ctypes.data, n_rec, 0, C.byref(t)))
         else:
             _check(lib.ntc_submit(self.h, words.ctypes.data, len(words), None, n_rec, stride, C.byref(t)))
+        return t.value
+
+    def submit_bases(self, bases, n_rec, L):
+        """Host batch of n_rec reads of ONE length L without length words: ceil(L/16) uint32 words of bases per read."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint32)
+        assert len(bases) == n_rec * ((L + 15) // 16)
+        t = C.c_uint64()
+        _check(lib.ntc_submit_bases(self.h, bases.ctypes.data, n_rec, L, C.byref(t)))
         return t.value
 
     def submit_device(self, d_words, n_words, n_rec, stride=0, d_off=None):

@@ -17,6 +17,7 @@ struct BatchView {          // a packed record stream resident in device memory
 	uint64_t n_words;
 	uint32_t uniform_len;   // bases per record when the host knows all records are equal, else 0
 	uint32_t max_rec_words; // ragged batches: words of the longest record when the host knows it, else 0
+	uint32_t headerless_len = 0; // != 0: records carry no length word -- stride words of bases each, all this many bases long
 };
 
 size_t piece_scan_temp_bytes(uint32_t n_items);
@@ -32,6 +33,8 @@ cudaError_t launch_retile_fill(const BatchView& b, uint32_t Lp, uint32_t D, uint
 cudaError_t launch_check_offsets(const uint32_t* d_off, uint32_t n_rec, uint64_t n_words, uint32_t* d_out /* [2], zeroed */, int n_sm, cudaStream_t st);
 cudaError_t launch_stride_offsets(uint32_t stride, uint32_t n_rec, uint32_t* d_off, cudaStream_t st);
 cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t stride_out, uint32_t n_rec, uint32_t* d_out, int n_sm, cudaStream_t st);
+cudaError_t launch_add_headers(const uint32_t* d_in, uint32_t wpr, uint32_t len, uint32_t stride_out, uint32_t n_rec, uint32_t* d_out, int n_sm,
+    cudaStream_t st);
 cudaError_t launch_pad_ragged(const uint32_t* d_in, const uint32_t* d_off, uint32_t n_rec, uint32_t stride_out, uint32_t* d_out, int n_sm,
     cudaStream_t st);
 cudaError_t launch_roll64(const BatchView& b, bool record_is_piece, uint64_t n_pieces_bound, const uint32_t* d_piece_first,

@@ -881,7 +881,21 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 		return rc;
 	CK(cudaEventRecord(e0, c->stream));
 	if (c->hll_bits) {
-		if ((rc = run_hll(c, b_in, record_is_piece)))
+		ntc::BatchView hb = b_in;
+		if (hb.headerless_len) { // as below: records without length words get one
+			const uint32_t s4 = (hb.stride + 1u + 3u) & ~3u;
+			if ((uint64_t)hb.n_rec * s4 > 0xFFFFFFF0ull)
+				return set_err(NTC_EINVAL, "batch too large: %u records of %u words", hb.n_rec, s4);
+			if ((rc = grow(&c->d_rt_uniform, &c->cap_rt_uniform, (size_t)hb.n_rec * s4 + 4, false)))
+				return rc;
+			CK(ntc::launch_add_headers(hb.words, hb.stride, hb.headerless_len, s4, hb.n_rec, c->d_rt_uniform, c->n_sm, c->stream));
+			c->n_launches++;
+			hb.words = c->d_rt_uniform;
+			hb.stride = s4;
+			hb.n_words = (uint64_t)hb.n_rec * s4;
+			hb.headerless_len = 0;
+		}
+		if ((rc = run_hll(c, hb, record_is_piece)))
 			return rc;
 		CK(cudaEventRecord(e1, c->stream));
 		c->timing.emplace_back(e0, e1);
@@ -890,6 +904,21 @@ int run_batch(ntc_ctx* c, const ntc::BatchView& b_in, bool record_is_piece)
 	}
 	PipeShape shape[NTC_MAX_K];
 	ntc::BatchView b = b_in;
+	if (b.headerless_len) {
+		// records without length words (ntc_submit_bases): give them their length word while padding them to a multiple of 4 words
+		const uint32_t s4 = (b.stride + 1u + 3u) & ~3u;
+		if ((uint64_t)b.n_rec * s4 > 0xFFFFFFF0ull)
+			return set_err(NTC_EINVAL, "batch too large: %u records of %u words", b.n_rec, s4);
+		if ((rc = grow(&c->d_rt_uniform, &c->cap_rt_uniform, (size_t)b.n_rec * s4 + 4, false)))
+			return rc;
+		CK(ntc::launch_add_headers(b.words, b.stride, b.headerless_len, s4, b.n_rec, c->d_rt_uniform, c->n_sm, c->stream));
+		c->n_launches++;
+		b.words = c->d_rt_uniform;
+		b.stride = s4;
+		b.n_words = (uint64_t)b.n_rec * s4;
+		b.uniform_len = b.headerless_len;
+		b.headerless_len = 0;
+	}
 	if (!b.off && (b.stride & 3u) && b.stride >= 2 && b.n_rec >= 1024 && c->use_pipeline && !c->gap && c->kernel != NTC_KERNEL_ROLL64 &&
 	    record_is_piece) {
 		// tightly packed uniform batch: pad every record to a multiple of 4 words on the device, then it can take the pipeline
@@ -1293,8 +1322,25 @@ int ntc_set_kernel(ntc_ctx* c, int kernel)
 	return NTC_OK;
 }
 
+static int submit_host(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec, uint32_t stride_words,
+    uint32_t headerless_len, uint64_t* ticket);
+
 int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec, uint32_t stride_words,
     uint64_t* ticket)
+{
+	return submit_host(c, words, n_words, off, n_rec, stride_words, 0, ticket);
+}
+
+int ntc_submit_bases(ntc_ctx* c, const uint32_t* bases, size_t n_rec, uint32_t len_bases, uint64_t* ticket)
+{
+	if (len_bases == 0)
+		return set_err(NTC_EINVAL, "ntc_submit_bases: len_bases must be >= 1");
+	const uint32_t wpr = (len_bases + 15u) / 16u;
+	return submit_host(c, bases, n_rec * (size_t)wpr, nullptr, n_rec, wpr, len_bases, ticket);
+}
+
+static int submit_host(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t* off, size_t n_rec, uint32_t stride_words,
+    uint32_t headerless_len, uint64_t* ticket)
 {
 	std::unique_lock<std::recursive_mutex> lk_;
 	if (c)
@@ -1358,7 +1404,8 @@ int ntc_submit(ntc_ctx* c, const uint32_t* words, size_t n_words, const uint32_t
 		HT(c, "submit: cudaMemcpyAsync offsets", CK(cudaMemcpyAsync(s.d_off, src_off, (n_rec + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream)));
 	HT(c, "submit: record copied + stream wait", CK(cudaEventRecord(s.copied, c->copy_stream)); CK(cudaStreamWaitEvent(c->stream, s.copied, 0)));
 	ntc::BatchView b{ s.d_words, off ? s.d_off : nullptr, stride_words, (uint32_t)n_rec, n_words, 0, off ? max_rec_words : 0u };
-	HT(c, "submit: run_batch (all of it)", rc = run_batch(c, b, single_piece_records(c, max_rec_words)));
+	b.headerless_len = headerless_len;
+	HT(c, "submit: run_batch (all of it)", rc = run_batch(c, b, single_piece_records(c, headerless_len ? max_rec_words + 1 : max_rec_words)));
 	if (rc)
 		return rc;
 	CK(cudaEventRecord(s.consumed, c->stream));

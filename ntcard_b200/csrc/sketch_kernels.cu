@@ -345,6 +345,28 @@ cudaError_t launch_restride(const uint32_t* d_in, uint32_t stride_in, uint32_t s
 	return cudaGetLastError();
 }
 
+// headerless uniform batch (ntc_submit_bases: n records of wpr base words each, all `len` bases long, NO length words: 40 instead of 44
+// bytes per 150 bp read over PCIe) -> length-prefixed records at a stride that is a multiple of 4 words
+__global__ void __launch_bounds__(256) add_headers_kernel(const uint32_t* __restrict__ in, uint32_t wpr, uint32_t len, uint32_t stride_out,
+    uint64_t n_out_words, uint32_t* __restrict__ out)
+{
+	for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_out_words; x += (uint64_t)gridDim.x * blockDim.x) {
+		const uint64_t rec = x / stride_out;
+		const uint32_t w = (uint32_t)(x - rec * stride_out);
+		out[x] = w == 0 ? len : w <= wpr ? __ldg(in + rec * wpr + (w - 1)) : 0u;
+	}
+}
+
+cudaError_t launch_add_headers(const uint32_t* d_in, uint32_t wpr, uint32_t len, uint32_t stride_out, uint32_t n_rec, uint32_t* d_out, int n_sm,
+    cudaStream_t st)
+{
+	const uint64_t n = (uint64_t)n_rec * stride_out;
+	if (n == 0)
+		return cudaSuccess;
+	add_headers_kernel<<<grid_for(n, 256, (unsigned)n_sm * 32u), 256, 0, st>>>(d_in, wpr, len, stride_out, n, d_out);
+	return cudaGetLastError();
+}
+
 // ragged batch of short records -> the same records zero-padded to one stride (a multiple of 4 words), so that they can take the
 // pipeline as tiles of mixed lengths (scan_kernel.cuh)
 __global__ void __launch_bounds__(256) pad_ragged_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ off, uint32_t stride_out,

@@ -599,6 +599,39 @@ def test_at_size_against_the_reference(oracle, name, n, L, kList, sBits, S, mode
     assert int(want_p[:, :, 1:].sum()) > 0
 
 
+def test_headerless_uniform_batches(oracle):
+    """ntc_submit_bases: reads of one length without length words (40 instead of 44 bytes per 150 bp read over PCIe).  Same sketch as
+    the oracle's for lengths around the word and 16-byte-group boundaries, pinned and pageable sources, small batches (general kernel)
+    and the nthll context."""
+    kList, rBits, sBits = [25, 32, 64], 22, 7
+    for L, n in ((150, 9000), (144, 5000), (160, 5000), (100, 300), (64, 2000)):
+        a = oracle.gen_reads(73, 0, n, L, 1, max(n // 5, 1))
+        reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+        want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+        stride = nt.stride_words(L, False)
+        wpr = (L + 15) // 16
+        words = nt.gen_packed(73, 0, n, L, 1, max(n // 5, 1), stride)
+        bases = np.ascontiguousarray(words.reshape(n, stride)[:, 1:1 + wpr]).reshape(-1)
+        pin = nt.PinnedBuffer(len(bases))
+        pin.array[:] = bases
+        with nt.Sketch(kList, rBits=rBits, sBits=sBits) as sk:
+            for src in (bases, pin.array):
+                sk.reset()
+                half = n // 2
+                sk.submit_bases(src[:half * wpr], half, L)
+                sk.submit_bases(src[half * wpr:], n - half, L)
+                t, f1, _ = sk.finish(counters=True, hist=False)
+                assert np.array_equal(f1, wf1), L
+                assert np.array_equal(t.reshape(-1), want), L
+        pin.free()
+        if L == 150:
+            with nt.HllSketch(32, 16) as h:
+                h.submit_bases(bases, n, L)
+                regs, nk = h.finish()
+                assert nk == n * (L - 32 + 1)
+                assert np.array_equal(regs, oracle.hll_registers(reads, 32, 16, nthreads=4))
+
+
 def test_device_resident_ragged_batches(oracle):
     """Ragged batches that already live in device memory (ntc_submit_device with offsets): the library finds the longest
     record and checks the offsets ON the device, then short records are padded for the pipeline and long ones re-tiled --
