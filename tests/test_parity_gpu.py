@@ -599,6 +599,33 @@ def test_at_size_against_the_reference(oracle, name, n, L, kList, sBits, S, mode
     assert int(want_p[:, :, 1:].sum()) > 0
 
 
+@pytest.mark.parametrize("pool", [None, "64"])
+def test_fused_kernel_experiment_stays_exact(oracle, monkeypatch, pool):
+    """NTC_FUSED=1: the fused scan + hash + append kernel of round 2 (fused_kernel.cuh; measured slower than scan + hit, DESIGN 5b, and
+    therefore not the default) must keep producing the oracle's sketch -- uniform and mixed-length tiles, several k classes, and with a
+    64-block pool (tiles deferred to the second pass, then direct increments)."""
+    monkeypatch.setenv("NTC_FUSED", "1")
+    if pool:
+        monkeypatch.setenv("NTC_POOL_BLOCKS", pool)
+    kList, rBits, sBits, L, n = [12, 25, 32, 64, 96], 20, 7, 150, 12000
+    a = oracle.gen_reads(74, 0, n, L, 1, n // 6)
+    reads = [bytes(a[i * L:(i + 1) * L]) for i in range(n)]
+    reads[100:140] = [b"A" * L] * 20 + [b"ACGT" * 37 + b"AC"] * 20      # low complexity: queue overflow / re-scan rounds
+    want, wf1 = oracle.sketch_reads(reads, kList, rBits, sBits, nthreads=4)
+    stride = nt.stride_words(L)
+    words, off = nt.pack_reads(reads, min_len=1)
+    uni = np.zeros(n * stride, dtype=np.uint32)
+    for i in range(n):                                                        # all reads are N-free: one record each
+        uni[i * stride:i * stride + (off[i + 1] - off[i])] = words[off[i]:off[i + 1]]
+    with nt.Sketch(kList, rBits=rBits, sBits=sBits) as sk:
+        sk.set_kernel(nt.KERNEL_BITSLICE)
+        sk.submit(uni[:5000 * stride], None, 5000, stride)
+        sk.submit(uni[5000 * stride:], None, n - 5000, stride)
+        t, f1, _ = sk.finish(counters=True, hist=False)
+    assert np.array_equal(f1, wf1)
+    assert np.array_equal(t.reshape(-1), want)
+
+
 def test_headerless_uniform_batches(oracle):
     """ntc_submit_bases: reads of one length without length words (40 instead of 44 bytes per 150 bp read over PCIe).  Same sketch as
     the oracle's for lengths around the word and 16-byte-group boundaries, pinned and pageable sources, small batches (general kernel)
