@@ -101,7 +101,9 @@ int ntc_submit(ntc_ctx* ctx, const uint32_t* words, size_t n_words, const uint32
  * the end-to-end rate.  The length words are added on the device.  Otherwise like ntc_submit. */
 int ntc_submit_bases(ntc_ctx* ctx, const uint32_t* bases, size_t n_rec, uint32_t len_bases, uint64_t* ticket);
 /* Same, for a batch already resident in DEVICE memory (synthetic generator,
- * device-side producers).  The buffers must stay valid until ntc_sync(). */
+ * device-side producers).  The buffers must stay valid until ntc_sync().  Ragged batches (d_off != NULL) get the
+ * checks of ntc_check_offsets on the device (NTC_EINVAL for broken offsets) and their longest record measured there,
+ * which costs one synchronisation of the context's stream per call; uniform batches stay asynchronous. */
 int ntc_submit_device(ntc_ctx* ctx, const uint32_t* d_words, size_t n_words, const uint32_t* d_off, size_t n_rec,
     uint32_t stride_words);
 int ntc_wait(ntc_ctx* ctx, uint64_t ticket); /* host buffer of that batch is reusable */
