@@ -8,7 +8,7 @@
 //   fh = sror^(32-tprime)( FB(head) ^ head_c ),  rh = RB(head) ^ head_d;   then per full block m = 1 .. nblk-1:
 //   fh = srol^32(fh) ^ FB_m,                      rh ^= srol^(tprime + 32 (m-1)) RB_m
 // with FB = XOR_i srol^(31-i) seed[c_i], RB = XOR_i srol^i seed[3-c_i] over the 32 codes of a block (NTF64 / NTR64 base forms,
-// nthash.hpp:220-239, regrouped; checked against the oracle for every k class by tests/test_parity_gpu.py::test_bitslice_every_k_class).  No per-base loop:
+// nthash.hpp:220-239, regrouped; checked for every k class by tests/test_parity_gpu.py::test_bitslice_every_k_class).  No per-base loop:
 // k = 25 costs one block like k = 32, k = 31 one, k = 64 two.
 #pragma once
 #include <cuda_runtime.h>
