@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A small pass through every kernel of the pipeline (scan, hit staged + plain, apply zero / prefetch mode, fallback,
-re-tiling, general kernel, histograms) for compute-sanitizer:
+re-tiling, general kernel, histograms; round 2: headerless batches, device-resident ragged batches, the peer-memory reduction
+between two contexts, the nthll pre-filter, the fused kernel) for compute-sanitizer:
     compute-sanitizer --tool memcheck  python tools/sanitize_case.py
     compute-sanitizer --tool racecheck python tools/sanitize_case.py
     compute-sanitizer --tool synccheck python tools/sanitize_case.py"""
@@ -41,5 +42,61 @@ def main():
         print("F1", [int(x) for x in f1], "hist sum", int(p.sum()))
 
 
+def round2():
+    import torch
+    n, L = 3000, 150
+    stride = nt.stride_words(L)
+    words = nt.gen_packed(5, 0, n, L, 1, n // 4, stride)
+    del os.environ["NTC_POOL_BLOCKS"]
+    # headerless uniform batch, device-resident ragged batch (check_offsets_kernel, pad_ragged)
+    with nt.Sketch([25, 32], rBits=20, sBits=7) as sk:
+        wpr = (L + 15) // 16
+        sk.submit_bases(np.ascontiguousarray(words.reshape(n, stride)[:, 1:1 + wpr]).reshape(-1), n, L)
+        chars = nt.gen_ascii(4, 0, 2500, 150, mode=2)
+        w, off = nt.pack_chars(chars, np.arange(2501, dtype=np.uint64) * 150, min_len=25)
+        dw, do = torch.from_numpy(w.view(np.int32)).cuda(), torch.from_numpy(off.view(np.int32)).cuda()
+        sk.submit_device(dw.data_ptr(), len(w), len(off) - 1, 0, d_off=do.data_ptr())
+        _, f1, p = sk.finish(counters=False, hist=True)
+        print("round 2 headerless + device ragged: F1", [int(x) for x in f1], "hist sum", int(p.sum()))
+    # peer-memory reduction between two contexts (apply_owned_kernel, log_status_kernel, hist_slices)
+    ranks = [nt.Sketch([32], rBits=20, sBits=7) for _ in range(2)]
+    for r, sk in enumerate(ranks):
+        sk.peer_attach_contexts(r, ranks)
+    status = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in ranks]
+    hist = [torch.zeros(2 * 65536, dtype=torch.int32, device="cuda") for _ in ranks]
+    for r, sk in enumerate(ranks):
+        sk.submit(words[r * 1500 * stride:(r + 1) * 1500 * stride], None, 1500, stride)
+        sk.log_status_device(status[r].data_ptr())
+    for sk in ranks:
+        sk.stream_sync()
+    tot = torch.stack(status).sum(dim=0)
+    for r, sk in enumerate(ranks):
+        sk.reduce_owned(tot.data_ptr(), hist[r].data_ptr())
+    for sk in ranks:
+        sk.stream_sync()
+    print("round 2 peer reduction: hist sum", int(torch.stack(hist).sum()))
+    for sk in ranks:
+        sk.close()
+    # nthll pre-filter (scan MODE 1 + hll_hit_kernel + hll_min_kernel): 64 registers, so that the first batch already lifts every
+    # register to 8 and the second one takes the filter
+    with nt.HllSketch(32, 6) as h:
+        big = nt.gen_packed(7, 0, 5000, L, 0, 0, stride)
+        h.submit(big[:4096 * stride], None, 4096, stride)   # general kernel + hll_min
+        l0 = h.stats()["launches"]
+        h.submit(big, None, 5000, stride)                    # pre-filter path (smallest register >= 8)
+        r_, nk = h.finish()
+        print("round 2 nthll: k-mers", nk, "min / max register", int(r_.min()), int(r_.max()), "launches of the 2nd batch", h.stats()["launches"] - l0)
+    os.environ["NTC_FUSED"] = "1"
+    with nt.Sketch([32, 64], rBits=20, sBits=7) as sk:      # fused scan + hash + append kernel
+        sk.submit(words, None, n, stride)
+        _, f1, p = sk.finish(counters=False, hist=True)
+        print("round 2 fused kernel: F1", [int(x) for x in f1], "hist sum", int(p.sum()))
+    del os.environ["NTC_FUSED"]
+
+
 if __name__ == "__main__":
-    main()
+    if "--round2-only" not in sys.argv:
+        main()
+    else:
+        os.environ["NTC_POOL_BLOCKS"] = "64"
+    round2()
