@@ -211,3 +211,21 @@ def test_parallel_file_reader_equals_serial(tmp_path):
         assert " x 1 threads" in outs[0] and " x 2 threads" in outs[1] and " x 3 threads" in outs[2]
         tails = [o.split(");", 1)[1].split(" batches")[0].rsplit(",", 1)[0] + o.split("digest")[1] for o in outs]   # "<n> records" + digest
         assert tails[0] == tails[1] == tails[2], (name, outs)
+
+
+def test_pack_bound_holds_for_the_worst_case():
+    """'ANAN...' with min_len = 1 costs about one word per character -- more than the old bound
+    n + total/16 + total/2 allowed, so pack_reads raised NTC_ENOMEM.  ntc_pack_bound is safe for any min_len now and
+    ntc_pack_bound_k is tight enough for long sequences with a real k."""
+    worst = b"AN" * 5000
+    w, off = nt.pack_reads([worst], min_len=1)
+    assert len(off) - 1 == 5000 and len(w) == 2 * 5000            # 5000 records of one base: length word + one base word
+    assert nt.lib.ntc_pack_bound(1, len(worst)) >= len(w)
+    assert nt.lib.ntc_pack_bound_k(1, len(worst), 1) >= len(w)
+    for m in (2, 3, 16, 31):
+        seq = (b"A" * m + b"N") * 700
+        w, off = nt.pack_reads([seq], min_len=m)
+        assert len(off) - 1 == 700
+        assert nt.lib.ntc_pack_bound_k(1, len(seq), m) >= len(w), m
+    long_seq = b"ACGT" * 250_000                                      # 1 Mbp, no N: the tight bound stays near len/16
+    assert nt.lib.ntc_pack_bound_k(1, len(long_seq), 32) < len(long_seq) // 8
