@@ -5,14 +5,18 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU, NCCL
 
-Workload (config.workload): BASELINE config 2 -- 10 M synthetic 150 bp reads PER GPU, k=32, s=7
-(ntcard.cpp:430-431 forces s=7 below 50 GB), r=27; weak scaling, reads sharded over ranks, one
-all-reduce of the sketch at the end.  A step = one whole pass of the hot path over the shard:
-zero the sketch, hash+sample+increment every k-mer, (N>1) all-reduce counters and F1.
+Workload (config.workload): BASELINE config 2 by default -- 10 M synthetic 150 bp reads PER GPU, k=32, s=7
+(ntcard.cpp:430-431 forces s=7 below 50 GB), r=27; weak scaling, reads sharded over ranks, one reduction at the end.
+--workload config3 | config4 | config5 run the other BASELINE configs (config5: a 10 % sample, ragged batches).
+A step = one whole pass of the hot path over the shard: reset the sketch, hash+sample+increment every k-mer, then
+  N = 1: flush -- the step ends with the complete sketch in HBM;
+  N > 1: the reduction over NVLink peer memory (ntcard_b200.dist.PeerReducer) -- the step ends with the global
+         counter-value histogram and F1 on every rank's device; one more untimed step is checked against the dense
+         all-reduce path and reported as "parity_check".
   value : k-mers/s, packed reads already resident in HBM.
-  e2e   : the same through the C-ABI with HOST (pinned) buffers: H2D copies of the packed reads,
-          kernels, all-reduce, finish (narrow + counter-value histogram on device, D2H of the
-          histogram, host estimator) all inside the timed region.
+  e2e   : the same through the C-ABI with HOST (pinned) buffers: H2D copies of the packed reads (ntc_submit_bases: no
+          length words on the wire), kernels, flush / reduction, counter-value histogram on the device, D2H of the
+          histogram, host estimator -- all inside the timed region.
 Prints ONE JSON line on rank 0.
 """
 import argparse
