@@ -426,80 +426,6 @@ __device__ __forceinline__ void role_sync(uint32_t role)
 	asm volatile("bar.sync %0, %1;" ::"r"(role + 1u), "n"(kApplyThreads / 2) : "memory");
 }
 
-// ---- stagers, version 2 (round 2): one coordinator warp + seven writer warps ------------------------------------------------
-// In version 1 all 256 stager threads of a CTA met at a barrier after every slice, then thread 0 fenced (waiting for the CTA's
-// stores to be acknowledged), signalled, and polled the appliers' counter before anybody wrote the next slice: ~3 us of bubble
-// on the ~7 us a 32 MiB slice takes at full write bandwidth (apply 0.37 ms against ~0.2 ms for the zero-fill alone).  Here the
-// writers never stop: they zero slice after slice as long as the slice is below the CTA's permission counter in shared memory,
-// and report each finished slice in another; warp 0 alone runs the protocol -- waits for the writers' report, fences (the
-// fence is cumulative: the writers' stores happen before their report, which the coordinator has read), signals zero_done, waits
-// for the appliers of that slice and extends the permission (still at most `ahead` slices in front of the appliers: L2 footprint).
-struct StagerShared {
-	uint32_t allowed;  // writers may stage slice si while si < allowed
-	uint32_t wdone;    // writer warps x slices finished
-};
-
-__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p)
-{
-	return *reinterpret_cast<const volatile uint32_t*>(p);
-}
-
-// rtid: thread index inside the stager role (0..255); slices order[0..NS) (order == nullptr: 0..NS-1).  zero_mode: write zeros and
-// signal zero_done; otherwise issue L2 prefetches for the slices whose log is not sparse.
-__device__ __forceinline__ void stage_slices_v2(const Pool& P, uint32_t* __restrict__ counters, const uint32_t* __restrict__ order, uint32_t NS,
-    bool zero_mode, uint32_t ahead, uint32_t sparse_below, uint32_t rtid, StagerShared* sh)
-{
-	constexpr uint32_t kWriters = kApplyThreads / 2 - 32; // 224 threads = 7 warps
-	const size_t slice_len = (size_t)1 << P.bin_shift;
-	const size_t per_k = (size_t)2 << P.rBits;
-	const size_t n16 = slice_len / 4; // 16-byte units per slice
-	const size_t a0 = n16 * blockIdx.x / gridDim.x, a1 = n16 * (blockIdx.x + 1) / gridDim.x;
-	const uint32_t lane = rtid & 31u;
-	if (rtid < 32) {
-		// ---- coordinator ----
-		if (lane == 0) {
-			for (uint32_t si = 0; si < NS; si++) {
-				while (ld_volatile_shared(&sh->wdone) < (kWriters / 32) * (si + 1))
-					__nanosleep(20);
-				if (zero_mode) {
-					__threadfence();
-					atomicAdd(P.zero_done + si, 1u);
-				}
-				if (si + ahead < NS) { // slice si + ahead may be staged once the appliers are through with slice si
-					while (ld_acquire(P.apply_done + si) < gridDim.x)
-						__nanosleep(20);
-					*reinterpret_cast<volatile uint32_t*>(&sh->allowed) = si + ahead + 1;
-				}
-			}
-		}
-		return;
-	}
-	// ---- writers ----
-	const uint32_t wtid = rtid - 32;
-	for (uint32_t si = 0; si < NS; si++) {
-		if (lane == 0)
-			while (ld_volatile_shared(&sh->allowed) <= si)
-				__nanosleep(20);
-		__syncwarp();
-		const uint32_t s = order ? order[si] : si;
-		uint4* p = reinterpret_cast<uint4*>(counters + (size_t)(s / P.nbins) * per_k + (size_t)(s % P.nbins) * slice_len);
-		if (zero_mode) {
-			for (size_t i = a0 + wtid; i < a1; i += kWriters)
-				p[i] = make_uint4(0u, 0u, 0u, 0u);
-		} else if (min(P.slice_nblk[s], P.slice_cap) >= sparse_below) {
-			for (size_t i = a0 + (size_t)wtid * 256; i < a1; i += (size_t)kWriters * 256) { // 4 KB per request
-				const uint32_t bytes = (uint32_t)(min(a1 - i, (size_t)256) * 16);
-				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + i), "r"(bytes) : "memory");
-			}
-		}
-		__syncwarp();
-		if (lane == 0) {
-			__threadfence_block(); // the warp's stores before its report
-			atomicAdd(&sh->wdone, 1u);
-		}
-	}
-}
-
 // Two roles per CTA, decoupled through per-slice arrival counters in global memory:
 //   stagers  (threads 0..255)   bring slice s into L2 -- write zeros (first flush after a reset) or issue L2
 //                               prefetches -- at most kApplyAhead slices ahead of the slowest applier;
@@ -511,7 +437,6 @@ __device__ __forceinline__ void stage_slices_v2(const Pool& P, uint32_t* __restr
 __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint32_t* __restrict__ counters, int force, uint32_t reserve_blocks,
     const uint32_t* __restrict__ order, uint32_t n_order)
 {
-	__shared__ StagerShared stager_sh;
 	const uint32_t kApplyAhead = P.ahead;
 	const uint32_t NS = order ? n_order : P.n_slices;
 	// ---- decide (every CTA reads the same values: they were written by earlier kernels) ----
@@ -539,16 +464,7 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 	const size_t per_k = (size_t)2 << P.rBits;
 	const uint32_t sparse_below = (uint32_t)(slice_len / 64 / kBlkEntries); // fewer entries than 1/8 of the slice's sectors: no prefetch
 
-	if (P.stager_v2) { // set up before the roles part: the permission for the first `ahead` slices
-		if (threadIdx.x == 0) {
-			stager_sh.allowed = min(NS, kApplyAhead);
-			stager_sh.wdone = 0;
-		}
-		__syncthreads();
-	}
-	if (role == 0 && P.stager_v2) {
-		stage_slices_v2(P, counters, order, NS, zero_mode, kApplyAhead, sparse_below, rtid, &stager_sh);
-	} else if (role == 0) {
+	if (role == 0) {
 		// ================= stagers =================
 		const size_t n16 = slice_len / 4; // 16-byte units per slice
 		const size_t a0 = n16 * blockIdx.x / gridDim.x, a1 = n16 * (blockIdx.x + 1) / gridDim.x;
@@ -669,23 +585,13 @@ __global__ void __launch_bounds__(kApplyThreads) apply_kernel(const Pool P, uint
 __global__ void __launch_bounds__(kApplyThreads) apply_owned_kernel(const Pool P, const PeerLogs G, uint32_t* __restrict__ counters,
     const uint32_t* __restrict__ order, uint32_t n_order, const long long* __restrict__ status, uint32_t status_idx)
 {
-	__shared__ StagerShared stager_sh;
 	if (status && status[status_idx] != 0)
 		return;
 	const uint32_t kApplyAhead = P.ahead;
 	const uint32_t role = threadIdx.x / (kApplyThreads / 2), rtid = threadIdx.x % (kApplyThreads / 2), nrt = kApplyThreads / 2;
 	const size_t slice_len = (size_t)1 << P.bin_shift;
 	const size_t per_k = (size_t)2 << P.rBits;
-	if (P.stager_v2) {
-		if (threadIdx.x == 0) {
-			stager_sh.allowed = min(n_order, kApplyAhead);
-			stager_sh.wdone = 0;
-		}
-		__syncthreads();
-	}
-	if (role == 0 && P.stager_v2) {
-		stage_slices_v2(P, counters, order, n_order, true, kApplyAhead, 0u, rtid, &stager_sh);
-	} else if (role == 0) {
+	if (role == 0) {
 		const size_t n16 = slice_len / 4;
 		const size_t a0 = n16 * blockIdx.x / gridDim.x, a1 = n16 * (blockIdx.x + 1) / gridDim.x;
 		for (uint32_t si = 0; si < n_order; si++) {

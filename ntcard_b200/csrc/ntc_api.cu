@@ -273,7 +273,6 @@ int pool_create(ntc_ctx* c)
 	P.rBits = c->rBits;
 	P.nK = c->nK;
 	P.ahead = getenv("NTC_APPLY_AHEAD") ? (uint32_t)atoi(getenv("NTC_APPLY_AHEAD")) : 2u;
-	P.stager_v2 = (getenv("NTC_APPLY_V2") && atoi(getenv("NTC_APPLY_V2")) != 0) ? 1u : 0u; // off until validated on the GPU
 	const uint32_t idx_bits = c->rBits + 1;
 	{
 		// 2^23 counters = 32 MiB per slice, 32 slices per k at r = 27.  Measured (profiles/r02_apply_tuning.txt): on one GPU 16 MiB slices

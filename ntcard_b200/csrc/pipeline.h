@@ -55,7 +55,6 @@ struct Pool {                    // device pointers + geometry, passed by value
 	uint32_t* gstate;            // [nK][max_groups][gstate_row(nbins)]: open / spare blocks of every hit group, kept over launches
 	uint32_t max_groups, epoch;  // epoch: bumped by ntc_reset (host); with the full 32-bit CTL_FLUSHES it dates gstate
 	uint32_t ahead;              // apply kernel: slices the stagers may run ahead of the appliers (L2 footprint)
-	uint32_t stager_v2;          // apply kernels: coordinator warp + writer warps instead of barrier-synchronised stagers (NTC_APPLY_V2, default 1)
 };
 
 constexpr uint32_t kMaxPeers = 8;
