@@ -206,6 +206,28 @@ template <int TQ, int T> BS_HD uint32_t zero_top_mask(const State& st)
 	return ~nzA | ~nzB;
 }
 
+// The same with the number of bits chosen at run time (warp-uniform lev = 0..5: no filter, top 5, 7, 9, 11, 13 bits), so that one
+// kernel serves every stage of a run and picks its filter from the smallest register as it stands on the device.
+template <int TQ> BS_HD uint32_t zero_top_mask_lev(const State& st, uint32_t lev)
+{
+	uint32_t a = 0, b = 0, nzA, nzB;
+	FoldOr<TQ, 0, 5>::run(st, a, b);
+	nzA = lev >= 1 ? a : 0u, nzB = lev >= 1 ? b : 0u;
+	a = b = 0;
+	FoldOr<TQ, 5, 7>::run(st, a, b);
+	nzA |= lev >= 2 ? a : 0u, nzB |= lev >= 2 ? b : 0u;
+	a = b = 0;
+	FoldOr<TQ, 7, 9>::run(st, a, b);
+	nzA |= lev >= 3 ? a : 0u, nzB |= lev >= 3 ? b : 0u;
+	a = b = 0;
+	FoldOr<TQ, 9, 11>::run(st, a, b);
+	nzA |= lev >= 4 ? a : 0u, nzB |= lev >= 4 ? b : 0u;
+	a = b = 0;
+	FoldOr<TQ, 11, 13>::run(st, a, b);
+	nzA |= lev >= 5 ? a : 0u, nzB |= lev >= 5 ? b : 0u;
+	return ~nzA | ~nzB;
+}
+
 // Initial state cancelling the constants the k virtual steps inject (see header comment):
 //   forward : E0 = XOR_{i<k} sror^{1+i}( srol^k(seed[A]) )        reverse : E0 = XOR_{i<k} srol^i( seed[T] )
 // Physical register j holds logical bit j at q = 0.  Returns broadcast words (0 / 0xFFFFFFFF).

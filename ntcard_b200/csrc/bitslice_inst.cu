@@ -26,8 +26,8 @@ cudaError_t BS_CAT(launch_scan_km_, BS_KM)(unsigned sBits, const ScanArgs& a)
 // nthll pre-filter variants: candidates = k-mers whose canonical hash has its top T bits zero
 cudaError_t BS_CAT(launch_hllscan_km_, BS_KM)(unsigned T, const ScanArgs& a)
 {
-	if (T == 9)
-		return launch_scan_one<BS_KM, 9, 1>(a);
+	if (T == 0) // the filter follows the smallest register on the device (a.hll_min)
+		return a.hll_min ? launch_scan_one<BS_KM, 13, 2>(a) : cudaErrorInvalidValue;
 	if (T == 13)
 		return launch_scan_one<BS_KM, 13, 1>(a);
 	return cudaErrorInvalidValue;

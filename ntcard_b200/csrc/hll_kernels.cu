@@ -202,7 +202,7 @@ cudaError_t launch_hll(const BatchView& b, bool record_is_piece, uint64_t n_piec
 }
 
 // ------------------------------------------------------------------------------------------------
-// fast path: bit-sliced pre-filter (scan_kernel, MODE 1) + this kernel
+// fast path: bit-sliced pre-filter (scan_kernel, MODE 2: T from the smallest register on the device; MODE 1: fixed T) + this kernel
 // ------------------------------------------------------------------------------------------------
 // Once every register is >= T - 1, only k-mers whose canonical hash has its top T bits zero can raise one (ntComp raises a
 // register only when clz > register, nthll.cpp:94-95).  The scan kernel marks exactly those (1 in 2^(T-1): T = 9 -> 0.4 %) at
@@ -210,9 +210,9 @@ cudaError_t launch_hll(const BatchView& b, bool record_is_piece, uint64_t n_piec
 // the marked k-mers in full (hit_hash.cuh) and applies ntComp to the registers in global memory (64 KB: L2 resident).
 // Registers stay bit-exact: the filter has no false negatives, and every candidate goes through the same ntComp.
 // Candidates are rare (T = 9: one mask word in 8 has a bit), so a warp first COMPACTS them: every lane pushes the set bits of its
-// mask word into the warp's queue in shared memory, and whenever 32 are waiting all 32 lanes hash one each (walking the bits
+// mask words into the warp's queue in shared memory, and whenever 32 are waiting all 32 lanes hash one each (walking the bits
 // lane by lane left 1 lane in 8 busy: 0.8 ms per 10 M reads instead of ~0.1).
-constexpr uint32_t kHllQueue = 32 + 32 * 4; // a full batch + what one more round of mask words may add on skewed data before draining
+constexpr uint32_t kHllQueue = 32 + 32 * 4; // a full batch + what four more mask rows may add before draining (more than that: hashed in place)
 
 struct HllHitArgs {
 	const uint32_t* words;
@@ -225,9 +225,9 @@ struct HllHitArgs {
 	uint32_t* regs;
 };
 
-__device__ __forceinline__ void hll_hit_one(const HllHitArgs& a, const uint4* __restrict__ tab, uint64_t w, uint32_t s, uint64_t per_tile, uint64_t low_mask)
+__device__ __forceinline__ void hll_hit_one(const HllHitArgs& a, const uint4* __restrict__ tab, uint32_t tile, uint32_t r, uint32_t ln, uint32_t s,
+    uint64_t low_mask)
 {
-	const uint32_t tile = (uint32_t)(w / per_tile), r = (uint32_t)((w - (uint64_t)tile * per_tile) >> 5), ln = (uint32_t)w & 31u;
 	const uint32_t rec = tile * pl::kTileRecs + s * 32u + ln;
 	if (rec >= a.n_rec)
 		return; // slots past the end of the batch
@@ -239,72 +239,84 @@ __device__ __forceinline__ void hll_hit_one(const HllHitArgs& a, const uint4* __
 	hll_comp(h, a.regs, low_mask);
 }
 
-__global__ void __launch_bounds__(256) hll_hit_kernel(const HllHitArgs a)
+// One warp per 16 mask rows of a tile (grid-stride).  The 2 KB of a unit are fetched with four 16-byte loads per lane, all in flight
+// before the first is looked at (the walk is latency-bound otherwise: 152 MB of masks per 10 M reads against ~2 M marked k-mers);
+// lane l's load q covers row c0 + 4q + l/8, records 4*(l%8) .. +3 of that row.  Queue entry: row << 10 | record lane << 5 | slot.
+__global__ void __launch_bounds__(256, 4) hll_hit_kernel(const HllHitArgs a)
 {
 	__shared__ uint4 tab[8 * 256];
-	__shared__ unsigned long long q_w[8][kHllQueue];
-	__shared__ uint8_t q_s[8][kHllQueue];
-	__shared__ uint32_t q_n[8];
+	__shared__ uint32_t q_e[8][kHllQueue];
 	for (uint32_t i = threadIdx.x; i < 8 * 256; i += blockDim.x)
 		tab[i] = a.d_tab[i];
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	if (lane == 0)
-		q_n[warp] = 0;
 	__syncthreads();
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint64_t low_mask = ((uint64_t)1 << a.nBits) - 1;
-	const uint64_t per_tile = (uint64_t)a.npos_max * 32u, total = (uint64_t)a.n_tiles * per_tile;
-	const uint64_t n_iter = (total + 31) / 32; // warp-uniform trip count: one mask row (32 words) per warp and iteration
-	for (uint64_t it = (uint64_t)blockIdx.x * 8 + warp; it < n_iter; it += (uint64_t)gridDim.x * 8) {
-		const uint64_t w = it * 32 + lane;
-		uint32_t x = w < total ? __ldcs(a.masks + w) : 0u;
-		if (x) {
-			const uint32_t tile = (uint32_t)(w / per_tile), r = (uint32_t)((w - (uint64_t)tile * per_tile) >> 5);
-			const uint32_t info = __ldg(a.tile_info + tile);
-			if (info == pl::kTileFlag || r >= info) // rows past the tile's k-mer positions hold nothing
-				x = 0;
+	uint32_t* q = q_e[warp];
+	constexpr uint32_t kChunk = 16; // rows per unit of work: a tile is shared by several warps, for balance on small batches
+	constexpr int kLoads = kChunk / 4;
+	const uint32_t cpt = (a.npos_max + kChunk - 1) / kChunk, n_units = a.n_tiles * cpt;
+	const uint32_t sub_row = lane >> 3, rl0 = (lane & 7u) * 4u;
+	for (uint32_t u = blockIdx.x * 8 + warp; u < n_units; u += gridDim.x * 8) {
+		const uint32_t tile = u / cpt, c0 = (u - tile * cpt) * kChunk;
+		const uint32_t info = __ldg(a.tile_info + tile);
+		const uint32_t npos = info == pl::kTileFlag ? 0u : min(info, a.npos_max); // rows past it hold nothing (or are another tile's)
+		const uint4* m = reinterpret_cast<const uint4*>(a.masks + (size_t)tile * a.npos_max * 32u) + lane;
+		uint4 x[kLoads];
+#pragma unroll
+		for (int g = 0; g < kLoads; g++) {
+			const uint32_t r = c0 + 4u * g + sub_row;
+			x[g] = r < npos ? __ldcs(m + (size_t)(r - sub_row) * 8u) : make_uint4(0, 0, 0, 0);
 		}
-		// skewed data (a low-complexity tile: every slot of a word marked): more set bits than the queue has room for -- those lanes
-		// hash their own bits directly
-		uint32_t cnt = (uint32_t)__popc(x);
-		const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, cnt);
-		if (tot == 0)
-			continue;
-		const uint32_t n0 = q_n[warp]; // every lane reads it before any lane adds to it
-		__syncwarp();
-		if (n0 + tot > kHllQueue) {
-			while (x) {
-				const uint32_t s = 31u - (uint32_t)__clz(x);
-				x ^= 1u << s;
-				hll_hit_one(a, tab, w, s, per_tile, low_mask);
+		uint32_t n = 0; // queued candidates of this warp (warp-uniform)
+#pragma unroll
+		for (int g = 0; g < kLoads; g++) {
+			const uint32_t r = c0 + 4u * g + sub_row;
+			uint32_t y[4] = {x[g].x, x[g].y, x[g].z, x[g].w};
+			const uint32_t cnt = (uint32_t)(__popc(y[0]) + __popc(y[1]) + __popc(y[2]) + __popc(y[3]));
+			const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, cnt);
+			if (tot == 0)
+				continue;
+			if (n + tot > kHllQueue) { // skewed data: more marked k-mers in four rows than the queue has room for
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					while (y[j]) {
+						const uint32_t s = 31u - (uint32_t)__clz(y[j]);
+						y[j] ^= 1u << s;
+						hll_hit_one(a, tab, tile, r, rl0 + j, s, low_mask);
+					}
+				continue;
+			}
+			// exclusive prefix of cnt over the lanes: where this lane's candidates go in the queue
+			uint32_t at = cnt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, at, d);
+				if (lane >= (uint32_t)d)
+					at += t;
+			}
+			at = n + at - cnt;
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				while (y[j]) {
+					const uint32_t s = 31u - (uint32_t)__clz(y[j]);
+					y[j] ^= 1u << s;
+					q[at++] = (r << 10) | ((rl0 + j) << 5) | s;
+				}
+			n += tot;
+			__syncwarp();
+			while (n >= 32) { // a full batch: every lane hashes one candidate (taken from the end of the queue)
+				const uint32_t e = q[n - 32 + lane];
+				hll_hit_one(a, tab, tile, e >> 10, (e >> 5) & 31u, e & 31u, low_mask);
+				n -= 32;
 			}
 			__syncwarp();
-			continue;
 		}
-		if (x) {
-			uint32_t at = atomicAdd(&q_n[warp], cnt);
-			while (x) {
-				const uint32_t s = 31u - (uint32_t)__clz(x);
-				x ^= 1u << s;
-				q_w[warp][at] = w;
-				q_s[warp][at] = (uint8_t)s;
-				at++;
-			}
+		if (lane < n) { // what is left of this unit
+			const uint32_t e = q[lane];
+			hll_hit_one(a, tab, tile, e >> 10, (e >> 5) & 31u, e & 31u, low_mask);
 		}
-		__syncwarp();
-		uint32_t n = q_n[warp];
-		while (n >= 32) { // a full batch: every lane hashes one candidate (taken from the end of the queue)
-			const uint32_t i = n - 32 + lane;
-			hll_hit_one(a, tab, q_w[warp][i], q_s[warp][i], per_tile, low_mask);
-			n -= 32;
-		}
-		__syncwarp();
-		if (lane == 0)
-			q_n[warp] = n;
 		__syncwarp();
 	}
-	const uint32_t n = q_n[warp];
-	if (lane < n)
-		hll_hit_one(a, tab, q_w[warp][lane], q_s[warp][lane], per_tile, low_mask);
 }
 
 cudaError_t launch_hll_hit(const uint32_t* d_words, uint32_t stride, uint32_t n_rec, uint32_t n_tiles, uint32_t npos_max, const uint32_t* d_masks,
@@ -322,7 +334,13 @@ cudaError_t launch_hll_hit(const uint32_t* d_words, uint32_t stride, uint32_t n_
 	a.K = pl::make_hashk(k);
 	a.nBits = nBits;
 	a.regs = reinterpret_cast<uint32_t*>(d_regs);
-	hll_hit_kernel<<<(unsigned)n_sm * 8u, 256, 0, st>>>(a);
+	const unsigned units = n_tiles * ((npos_max + 15u) / 16u);
+	static int per_sm = 0; // resident CTAs per SM (registers bound it); the same for every device of the box
+	if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hll_hit_kernel, 256, 0) != cudaSuccess || per_sm < 1))
+		per_sm = 1;
+	const unsigned resident = (unsigned)(n_sm * per_sm);
+	const unsigned ctas = (units + 7) / 8 < resident ? (units + 7) / 8 : resident;
+	hll_hit_kernel<<<ctas ? ctas : 1, 256, 0, st>>>(a);
 	return cudaGetLastError();
 }
 
@@ -334,8 +352,24 @@ __global__ void __launch_bounds__(1024) hll_min_kernel(const uint32_t* __restric
 		s_min = 255u;
 	__syncthreads();
 	uint32_t m = 0xFFFFFFFFu; // per-byte minimum
-	for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x)
-		m = __vminu4(m, __ldcg(regs + i));
+	if ((n_words & 3u) == 0) { // 16-byte loads, four in flight per thread: the kernel sits between two chunks of a batch
+		const uint4* r4 = reinterpret_cast<const uint4*>(regs);
+		const uint32_t n4 = n_words >> 2;
+		for (uint32_t i0 = 0; i0 < n4; i0 += 4 * blockDim.x) {
+			uint4 x[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const uint32_t i = i0 + j * blockDim.x + threadIdx.x;
+				x[j] = i < n4 ? __ldcg(r4 + i) : make_uint4(~0u, ~0u, ~0u, ~0u);
+			}
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				m = __vminu4(m, __vminu4(__vminu4(x[j].x, x[j].y), __vminu4(x[j].z, x[j].w)));
+		}
+	} else {
+		for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x)
+			m = __vminu4(m, __ldcg(regs + i));
+	}
 	uint32_t v = 255u;
 	for (uint32_t j = 0; j < 4 && j < n_regs; j++)
 		v = min(v, (m >> (8 * j)) & 0xFFu);

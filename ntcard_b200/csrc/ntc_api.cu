@@ -81,6 +81,7 @@ struct ntc_ctx {
 	size_t hll_bytes = 0;
 	// nthll fast path: the smallest register as last seen by the host (registers only rise, so a stale value is a safe bound)
 	uint32_t hll_min = 0;
+	uint64_t hll_seen = 0;               // records since the last reset (sizes the chunks of the pre-filter path)
 	uint32_t* d_hll_scratch = nullptr;   // [0] smallest register (hll_min_kernel), [2..3] candidate count, [4..] scan-kernel control words
 	uint32_t* h_hll_min = nullptr;       // pinned
 	cudaEvent_t hll_min_ev = nullptr;
@@ -708,8 +709,8 @@ int hll_min_poll(ntc_ctx* c, bool wait)
 }
 
 // nthll mode: every canonical hash of the batch into the HyperLogLog registers (hll_kernels.cu).  Uniform-stride batches take
-// the bit-sliced pre-filter (scan kernel, "top T bits zero") + hll_hit_kernel as soon as every register has reached T - 1;
-// until then -- the first ~2 M reads of a run at 2^16 registers -- chunks go through the 64-bit recurrence.
+// the bit-sliced pre-filter (scan kernel, "top T bits zero") + hll_hit_kernel as soon as every register has reached 4;
+// until then -- the first 256 K reads of a run at 2^16 registers -- chunks go through the 64-bit recurrence.
 int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 {
 	int rc;
@@ -730,19 +731,27 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 	while (done < b.n_rec) {
 		if ((rc = hll_min_poll(c, false)))
 			return rc;
-		const unsigned T = c->hll_min >= 12 ? 13u : c->hll_min >= 8 ? 9u : 0u;
 		ntc::BatchView sub = b;
 		sub.words = b.words + (uint64_t)done * b.stride;
-		if (!T) {
-			// registers still low: 2 M records through the 64-bit recurrence, then look at the smallest register again
-			sub.n_rec = std::min<uint32_t>(b.n_rec - done, 2u << 20);
+		if (c->hll_min < 4) {
+			// registers still low: 256 K records through the 64-bit recurrence, then look at the smallest register again
+			sub.n_rec = std::min<uint32_t>(b.n_rec - done, 256u << 10);
 			sub.n_words = (uint64_t)sub.n_rec * b.stride;
 			if ((rc = run_hll_general(c, sub, true)) || (rc = hll_min_request(c)) || (rc = hll_min_poll(c, true)))
 				return rc;
 			done += sub.n_rec;
+			c->hll_seen += sub.n_rec;
 			continue;
 		}
+		// T = 13 once the host knows every register is >= 12; until then the scan kernel reads the smallest register from the
+		// device (written by hll_min_kernel after the previous chunk, no host round trip) and filters at 5, 7, 9, 11 or 13 bits.
+		// Chunks double with the records seen so far, which is how fast the smallest register climbs.
+		const unsigned T = c->hll_min >= 12 ? 13u : 0u;
 		sub.n_rec = b.n_rec - done;
+		if (!T)
+			sub.n_rec = (uint32_t)std::min<uint64_t>(sub.n_rec, std::max<uint64_t>(256u << 10, c->hll_seen));
+		if (b.n_rec - done - sub.n_rec < 4096)
+			sub.n_rec = b.n_rec - done; // no crumbs
 		sub.n_words = (uint64_t)sub.n_rec * b.stride;
 		const uint32_t n_tiles = (sub.n_rec + 1023) / 1024;
 		if ((rc = grow(&c->d_masks, &c->cap_masks, (size_t)n_tiles * npos_max * 32, false)) ||
@@ -766,6 +775,7 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		sa.f1_k = c->d_f1;
 		sa.cand = reinterpret_cast<unsigned long long*>(c->d_hll_scratch + 2);
 		sa.ctl = c->d_hll_scratch + 4;
+		sa.hll_min = c->d_hll_scratch;
 		sa.grid = std::min<unsigned>((unsigned)c->n_sm, n_tiles);
 		sa.smem_bytes = nw * per_warp;
 		sa.stream = c->stream;
@@ -779,9 +789,10 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		if ((rc = stage_end(c)))
 			return rc;
 		c->n_launches += 2;
-		if (T < 13 && (rc = hll_min_request(c))) // a later batch may be able to use the sharper filter
+		if (T < 13 && (rc = hll_min_request(c))) // the next chunk filters by it
 			return rc;
-		done = b.n_rec;
+		done += sub.n_rec;
+		c->hll_seen += sub.n_rec;
 	}
 	return NTC_OK;
 }
@@ -1262,6 +1273,7 @@ int ntc_reset(ntc_ctx* c)
 			CK(cudaEventSynchronize(c->hll_min_ev));
 		c->hll_min_pending = false;
 		c->hll_min = 0;
+		c->hll_seen = 0;
 		c->totals_overridden = false;
 		c->pending = false;
 		return NTC_OK;

@@ -90,6 +90,7 @@ struct ScanArgs {
 	unsigned long long* f1_k;
 	unsigned long long* cand;
 	uint32_t* ctl;
+	const uint32_t* hll_min = nullptr; // nthll pre-filter: device word holding the smallest register (launch_hll_min)
 	unsigned grid;
 	size_t smem_bytes;
 	cudaStream_t stream;
@@ -133,7 +134,8 @@ bool have_scan_kernel(unsigned k, unsigned sBits);
 void build_tables(uint32_t* tab /* 8*256*4 words */);
 cudaError_t launch_scan(unsigned k, unsigned sBits, const ScanArgs& a);
 cudaError_t launch_fused(unsigned k, unsigned sBits, const FusedArgs& a);
-// nthll pre-filter (hll_kernels.cu): the scan kernel with "top T bits of the canonical hash are zero" as its predicate; T = 9 or 13
+// nthll pre-filter (hll_kernels.cu): the scan kernel with "top T bits of the canonical hash are zero" as its predicate; T = 13, or
+// T = 0: 5 / 7 / 9 / 11 / 13 bits by the smallest register as ScanArgs::hll_min holds it when the kernel starts
 cudaError_t launch_hllscan(unsigned k, unsigned T, const ScanArgs& a);
 size_t fused_smem_bytes(uint32_t ring, uint32_t nwarps, uint32_t qlane, uint32_t nbins);
 bool hit_can_stage(uint32_t stride, uint32_t units_per_tile, uint32_t tiles_per_unit);

@@ -44,26 +44,27 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const uint4* p, uint64_t policy)
 // 0..2, so the kScanBlock slots of a block can be addressed from one base without wrapping.  The k "virtual"
 // positions before the read (window not full yet) are the k slots before slot 0, zeroed at the start of a tile.
 // pin / pout / mb: plane slot of the block's first entering / leaving position, mask row of its first position.
-// MODE 0: ntComp's sampling predicate with sBits = S; MODE 1: nthll pre-filter, top S bits of the canonical hash all zero
+// MODE 0: ntComp's sampling predicate with sBits = S; MODE 1: nthll pre-filter, top S bits of the canonical hash all zero;
+// MODE 2: nthll pre-filter at the run-time level lev (bitslice_core.cuh zero_top_mask_lev)
 template <int KM, int S, int U, int MODE> struct ScanBlock {
 	static __device__ __forceinline__ void run(bs::State& st, const uint2* __restrict__ pin, const uint2* __restrict__ pout,
-	    uint32_t* __restrict__ mb, int qb, int k, int n, uint32_t& cand)
+	    uint32_t* __restrict__ mb, int qb, int k, int n, uint32_t& cand, uint32_t lev)
 	{
 		const uint2 in = pin[U * 32];
 		const uint2 out = pout[U * 32];
 		bs::step<KM, U>(st, in.x, in.y, out.x, out.y);
-		const uint32_t m = MODE ? bs::zero_top_mask<U, S>(st) : bs::sampled_mask<U, S>(st); // slots past the end of the batch are dropped by the hit kernel
+		const uint32_t m = MODE == 2 ? bs::zero_top_mask_lev<U>(st, lev) : MODE ? bs::zero_top_mask<U, S>(st) : bs::sampled_mask<U, S>(st); // slots past the end of the batch are dropped by the hit kernel
 		const int q = qb + U;
 		if (q >= k - 1 && q < n) {
 			__stcs(mb + U * 32, m); // streaming store: read once by the hit kernel
 			cand += __popc(m);
 		}
-		ScanBlock<KM, S, U + 1, MODE>::run(st, pin, pout, mb, qb, k, n, cand);
+		ScanBlock<KM, S, U + 1, MODE>::run(st, pin, pout, mb, qb, k, n, cand, lev);
 	}
 };
 template <int KM, int S, int MODE> struct ScanBlock<KM, S, kScanBlock, MODE> {
 	static __device__ __forceinline__ void run(bs::State&, const uint2* __restrict__, const uint2* __restrict__, uint32_t* __restrict__, int, int, int,
-	    uint32_t&)
+	    uint32_t&, uint32_t)
 	{
 	}
 };
@@ -92,12 +93,19 @@ __device__ __forceinline__ void zero_rows(uint32_t* __restrict__ masks, uint32_t
 template <int KM, int S, int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* __restrict__ words, uint32_t stride, uint32_t n_rec, ScanLaunch L,
     uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_info, unsigned long long* __restrict__ f1_k,
-    unsigned long long* __restrict__ cand_out, uint32_t* __restrict__ ctl)
+    unsigned long long* __restrict__ cand_out, uint32_t* __restrict__ ctl, const uint32_t* __restrict__ hll_min)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	if (warp >= L.nwarps)
 		return;
+	// MODE 2: the filter follows the smallest register as the device has it now (hll_min_kernel ran on this stream after the
+	// previous chunk): top T bits zero is necessary for a k-mer to raise a register once every register is >= T - 1
+	uint32_t lev = 0;
+	if (MODE == 2) {
+		const uint32_t mn = __ldcg(hll_min);
+		lev = mn >= 12 ? 5u : mn >= 10 ? 4u : mn >= 8 ? 3u : mn >= 6 ? 2u : mn >= 4 ? 1u : 0u;
+	}
 	const int R = (int)L.ring; // multiple of 16, >= k + 16
 	uint2* planes = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * (L.ring + 3u) * 256u); // [position mod ring (+3 mirror slots)][lane]
 
@@ -249,7 +257,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const uint32_t* _
 			for (int qb = q0; qb < q0 + nq; qb += kScanBlock) {
 				int ob = cout + (qb - q0);
 				ob = ob >= R ? ob - R : ob; // a block may start up to 3 slots before the end of the ring: mirror slots
-				ScanBlock<KM, S, 0, MODE>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, mptr, qb, k, n, cand);
+				ScanBlock<KM, S, 0, MODE>::run(st, planes + lane + (cin + (qb - q0)) * 32, planes + lane + ob * 32, mptr, qb, k, n, cand, lev);
 				scan_rotate_home(st);
 				mptr += kScanBlock * 32;
 			}
@@ -292,7 +300,7 @@ cudaError_t launch_scan_one(const ScanArgs& a)
 		if (dev >= 0 && dev < 64)
 			smem_set[dev] = a.smem_bytes;
 	}
-	kern<<<a.grid, kScanThreads, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.masks, a.tile_info, a.f1_k, a.cand, a.ctl);
+	kern<<<a.grid, kScanThreads, a.smem_bytes, a.stream>>>(a.words, a.stride, a.n_rec, a.L, a.masks, a.tile_info, a.f1_k, a.cand, a.ctl, a.hll_min);
 	return cudaGetLastError();
 }
 

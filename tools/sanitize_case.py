@@ -77,15 +77,18 @@ def round2():
     print("round 2 peer reduction: hist sum", int(torch.stack(hist).sum()))
     for sk in ranks:
         sk.close()
-    # nthll pre-filter (scan MODE 1 + hll_hit_kernel + hll_min_kernel): 64 registers, so that the first batch already lifts every
-    # register to 8 and the second one takes the filter
-    with nt.HllSketch(32, 6) as h:
+    # nthll pre-filter (scan MODE 2 / 1 + hll_hit_kernel + hll_min_kernel): 1024 registers, so that the first batch (general kernel)
+    # lifts every register past 4 and the next ones take the filter at the level the device reads, then the fixed 13-bit one
+    with nt.HllSketch(32, 10) as h:
         big = nt.gen_packed(7, 0, 5000, L, 0, 0, stride)
         h.submit(big[:4096 * stride], None, 4096, stride)   # general kernel + hll_min
         l0 = h.stats()["launches"]
-        h.submit(big, None, 5000, stride)                    # pre-filter path (smallest register >= 8)
+        h.submit(big, None, 5000, stride)                    # pre-filter path, level from the device word
+        l1 = h.stats()["launches"]
+        for _ in range(12):
+            h.submit(big, None, 5000, stride)
         r_, nk = h.finish()
-        print("round 2 nthll: k-mers", nk, "min / max register", int(r_.min()), int(r_.max()), "launches of the 2nd batch", h.stats()["launches"] - l0)
+        print("round 2 nthll: k-mers", nk, "min / max register", int(r_.min()), int(r_.max()), "launches of the 2nd batch", l1 - l0)
     os.environ["NTC_FUSED"] = "1"
     with nt.Sketch([32, 64], rBits=20, sBits=7) as sk:      # fused scan + hash + append kernel
         sk.submit(words, None, n, stride)
