@@ -87,6 +87,7 @@ struct ntc_ctx {
 	cudaEvent_t hll_min_ev = nullptr;
 	bool hll_min_pending = false;
 	bool hll_fast = true;                // NTC_HLL_FAST=0: the 64-bit recurrence only
+	uint32_t hll_first = 256u << 10;     // records per chunk while the registers are below 4, and the smallest pre-filter chunk (NTC_HLL_FIRST_K, in K records)
 	uint32_t* d_counters = nullptr;
 	bool own_counters = false;
 	size_t n_counters = 0;
@@ -735,7 +736,7 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		sub.words = b.words + (uint64_t)done * b.stride;
 		if (c->hll_min < 4) {
 			// registers still low: 256 K records through the 64-bit recurrence, then look at the smallest register again
-			sub.n_rec = std::min<uint32_t>(b.n_rec - done, 256u << 10);
+			sub.n_rec = std::min<uint32_t>(b.n_rec - done, c->hll_first);
 			sub.n_words = (uint64_t)sub.n_rec * b.stride;
 			if ((rc = run_hll_general(c, sub, true)) || (rc = hll_min_request(c)) || (rc = hll_min_poll(c, true)))
 				return rc;
@@ -749,7 +750,7 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 		const unsigned T = c->hll_min >= 12 ? 13u : 0u;
 		sub.n_rec = b.n_rec - done;
 		if (!T)
-			sub.n_rec = (uint32_t)std::min<uint64_t>(sub.n_rec, std::max<uint64_t>(256u << 10, c->hll_seen));
+			sub.n_rec = (uint32_t)std::min<uint64_t>(sub.n_rec, std::max<uint64_t>(c->hll_first, c->hll_seen));
 		if (b.n_rec - done - sub.n_rec < 4096)
 			sub.n_rec = b.n_rec - done; // no crumbs
 		sub.n_words = (uint64_t)sub.n_rec * b.stride;
@@ -1150,6 +1151,8 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 		c->fused_dbg = (unsigned)atoi(getenv("NTC_FUSED_DBG"));
 	c->no_retile = getenv("NTC_NO_RETILE") != nullptr;
 	c->hll_fast = !(getenv("NTC_HLL_FAST") && atoi(getenv("NTC_HLL_FAST")) == 0);
+	if (getenv("NTC_HLL_FIRST_K") && atoi(getenv("NTC_HLL_FIRST_K")) >= 4)
+		c->hll_first = (uint32_t)std::min(atoi(getenv("NTC_HLL_FIRST_K")), 1 << 20) << 10;
 	// two 8-byte cudaMemsetAsync per batch (default) or one 1-thread kernel (NTC_CLEAR_MEMSET=0): measured, the kernel variant makes the host
 	// spend ~6 ms per ntc_submit on the ragged host path (tools/bench_ragged.py: 53.7 vs 7.9 ms per pass) -- unexplained, see DESIGN section 8
 	c->clear_by_memset = !(getenv("NTC_CLEAR_MEMSET") && atoi(getenv("NTC_CLEAR_MEMSET")) == 0);

@@ -213,6 +213,42 @@ def test_device_hll_fast_path_at_size_is_bit_exact(oracle, k, nBits, L):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k,nBits", [(32, 12), (40, 16)])
+def test_device_hll_fast_path_with_records_of_mixed_lengths(oracle, k, nBits):
+    """Uniform-stride batches whose records differ in length (some shorter than k): the pre-filter scans such tiles at the longest
+    length and hll_hit_kernel drops the candidates that lie past a record's own end.  nBits = 12: the registers pass 12 within the
+    first batch, so the second one takes the fixed 13-bit filter; nBits = 16: levels picked on the device throughout."""
+    import ctypes
+    import os
+    n, L = 800_000, 150
+    stride = nt.stride_words(L)
+    a = oracle.gen_reads(77, 0, n, L, 0, 0).reshape(n, L)
+    rng = np.random.default_rng(5)
+    lens = np.where(rng.random(n) < 0.3, rng.integers(20, L + 1, n), L).astype(np.uint64)
+    keep = np.arange(L, dtype=np.uint64)[None, :] < lens[:, None]
+    buf = np.ascontiguousarray(a[keep])
+    off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    want = np.zeros(1 << nBits, dtype=np.uint8)
+    oracle.lib.orc_hll_batch(buf.ctypes.data, off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), n, k, nBits, want.ctypes.data, os.cpu_count() or 1)
+    w, woff = nt.pack_chars(buf, off, min_len=1)
+    assert len(woff) - 1 == n
+    cnt = np.diff(woff.astype(np.int64))
+    rows = np.zeros((n, stride), dtype=np.uint32)
+    rows[np.arange(stride)[None, :] < cnt[:, None]] = w      # record i = its length word + packed bases, zero padding behind
+    rows = rows.reshape(-1)
+    with nt.HllSketch(k, nBits) as h:
+        half = n // 2
+        h.submit(rows[:half * stride], None, half, stride)
+        l0 = h.stats()["launches"]
+        h.submit(rows[half * stride:], None, n - half, stride)
+        assert h.stats()["launches"] - l0 <= 3 * 4                  # scan + hit (+ min) per chunk: no recurrence in the second batch
+        regs, nk = h.finish()
+    assert nk == int(np.maximum(lens.astype(np.int64) - k + 1, 0).sum())
+    assert np.array_equal(regs, want), (k, nBits, int((regs != want).sum()))
+
+
+@pytest.mark.gpu
 def test_device_hll_caller_owned_registers_merge_by_max(oracle):
     """two contexts on one device, sharded reads, registers in torch tensors, merged by max = one context over all reads
     (the N>1 path without a second GPU: ntcard_b200.dist.all_reduce_hll does torch.maximum's job across ranks)"""
