@@ -209,7 +209,8 @@ int ntc_estimate(const uint32_t* p_hist, const uint16_t* t_Counter, unsigned rBi
  * `seq.length() >= k` test, nthll.cpp:112,129,146, is implied: shorter records hold no k-mer); the entry points of the
  * ntCard sketch (ntc_finish, ntc_counters_device, ntc_log_*, ...) return NTC_ESTATE on it, and ntc_hll_* return
  * NTC_ESTATE on a sketch context.  d_regs: optional caller-owned DEVICE buffer of max(4, 2^nBits) bytes (e.g. a torch
- * uint8 tensor that torch.distributed will max-all-reduce), NULL lets the context allocate it. */
+ * uint8 tensor that torch.distributed will max-all-reduce), NULL lets the context allocate it.  The caller may change the
+ * content of its buffer between two batches (never while one is in flight): the context looks at it afresh per batch. */
 int ntc_hll_create(ntc_ctx** out, unsigned k, unsigned nBits, int device, void* d_regs, void* cuda_stream);
 /* The registers on the device (uint8 [2^nBits]); multi-GPU: wait (ntc_sync), max-all-reduce them, then ntc_hll_finish. */
 int ntc_hll_registers_device(ntc_ctx* ctx, void** d_regs, size_t* n_regs);

@@ -728,6 +728,15 @@ int run_hll(ntc_ctx* c, const ntc::BatchView& b, bool record_is_piece)
 	if (nw < 1)
 		return run_hll_general(c, b, record_is_piece);
 	const uint32_t npos_max = max_len - k + 1;
+	if (!c->own_hll) {
+		// caller-owned registers (a torch tensor): the caller may have cleared or replaced them between two batches, so what the
+		// host and the device word remember of their minimum is not to be trusted -- one look per batch (a stream sync)
+		if ((rc = hll_min_poll(c, true)))
+			return rc;
+		c->hll_min = 0;
+		if ((rc = hll_min_request(c)) || (rc = hll_min_poll(c, true)))
+			return rc;
+	}
 	uint32_t done = 0;
 	while (done < b.n_rec) {
 		if ((rc = hll_min_poll(c, false)))

@@ -249,6 +249,32 @@ def test_device_hll_fast_path_with_records_of_mixed_lengths(oracle, k, nBits):
 
 
 @pytest.mark.gpu
+def test_device_hll_caller_owned_registers_cleared_by_the_caller(oracle):
+    """Registers in a torch tensor that the caller clears between two batches WITHOUT ntc_reset: the pre-filter must not go on
+    assuming the high registers of the first batch (it re-reads their minimum once per batch when it does not own them)."""
+    import ctypes
+    import os
+    import torch
+    n, L, k, nBits = 400_000, 150, 32, 10
+    stride = nt.stride_words(L)
+    t = torch.zeros(1 << nBits, dtype=torch.uint8, device="cuda")
+    words = nt.gen_packed(91, 0, 2 * n, L, 0, 0, stride)
+    a = oracle.gen_reads(91, n, n, L, 0, 0)
+    off = np.arange(n + 1, dtype=np.uint64) * L
+    want = np.zeros(1 << nBits, dtype=np.uint8)
+    oracle.lib.orc_hll_batch(a.ctypes.data, off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), n, k, nBits, want.ctypes.data, os.cpu_count() or 1)
+    with nt.HllSketch(k, nBits, d_regs=t.data_ptr()) as h:
+        h.submit(words[:n * stride], None, n, stride)
+        h.sync()
+        assert int(t.min()) >= 12                                  # the fixed 13-bit filter would be next
+        t.zero_()
+        torch.cuda.synchronize()
+        h.submit(words[n * stride:], None, n, stride)
+        h.sync()
+        assert np.array_equal(t.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
 def test_device_hll_caller_owned_registers_merge_by_max(oracle):
     """two contexts on one device, sharded reads, registers in torch tensors, merged by max = one context over all reads
     (the N>1 path without a second GPU: ntcard_b200.dist.all_reduce_hll does torch.maximum's job across ranks)"""
