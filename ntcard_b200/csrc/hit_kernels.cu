@@ -287,6 +287,18 @@ __global__ void __launch_bounds__(kGroups * kGroupThreads, kStaged ? 1 : 2) hit_
 		}
 		const uint32_t nw = U.nrows * 32u;
 		const uint32_t* m = a.masks + ((size_t)U.tile0 * a.npos_max + U.r0) * 32u;
+		if (a.mask_prefetch && !U.multi) {
+			// the next unit's mask rows (128 bytes each) on their way to L2 while this one is processed: the enumeration below
+			// otherwise starts every unit with a full DRAM latency that nothing covers (the whole group waits for it)
+			const uint32_t nu = unit + gridDim.x * kGroups;
+			if (nu < a.n_units) {
+				const uint32_t t1 = nu / a.units_per_tile, r1 = (nu - t1 * a.units_per_tile) * a.rows_per_unit;
+				const uint32_t rows = min(a.rows_per_unit, a.npos_max - min(r1, a.npos_max));
+				const uint32_t* m1 = a.masks + ((size_t)t1 * a.npos_max + r1) * 32u;
+				for (uint32_t r = gtid; r < rows; r += kGroupThreads)
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(m1 + (size_t)r * 32u));
+			}
+		}
 		if (gtid == 0) {
 			sm.scal[0] = 0;
 			sm.scal[1] = 0;

@@ -86,6 +86,7 @@ struct ntc_ctx {
 	uint32_t* h_hll_min = nullptr;       // pinned
 	cudaEvent_t hll_min_ev = nullptr;
 	bool hll_min_pending = false;
+	uint32_t mask_prefetch = 1;          // hit kernel prefetches its next unit's mask rows to L2 (NTC_MASK_PREFETCH=0: off)
 	bool hll_fast = true;                // NTC_HLL_FAST=0: the 64-bit recurrence only
 	uint32_t hll_first = 256u << 10;     // records per chunk while the registers are below 4, and the smallest pre-filter chunk (NTC_HLL_FIRST_K, in K records)
 	uint32_t* d_counters = nullptr;
@@ -606,6 +607,7 @@ int run_pipeline_chunk(ntc_ctx* c, const ntc::BatchView& b, unsigned ki, const P
 	ha.ki = ki;
 	ha.sBits = c->sBits;
 	ha.npos_max = sh.npos_max;
+	ha.mask_prefetch = c->mask_prefetch;
 	ha.rows_per_unit = sh.rows_per_unit;
 	ha.units_per_tile = sh.units_per_tile;
 	ha.tiles_per_unit = sh.tiles_per_unit;
@@ -1159,6 +1161,7 @@ static int create_ctx(ntc_ctx** out, const unsigned* kList, unsigned nK, unsigne
 	if (getenv("NTC_FUSED_DBG"))
 		c->fused_dbg = (unsigned)atoi(getenv("NTC_FUSED_DBG"));
 	c->no_retile = getenv("NTC_NO_RETILE") != nullptr;
+	c->mask_prefetch = getenv("NTC_MASK_PREFETCH") ? (uint32_t)atoi(getenv("NTC_MASK_PREFETCH")) : 1u;
 	c->hll_fast = !(getenv("NTC_HLL_FAST") && atoi(getenv("NTC_HLL_FAST")) == 0);
 	if (getenv("NTC_HLL_FIRST_K") && atoi(getenv("NTC_HLL_FIRST_K")) >= 4)
 		c->hll_first = (uint32_t)std::min(atoi(getenv("NTC_HLL_FIRST_K")), 1 << 20) << 10;

@@ -125,6 +125,7 @@ struct HitArgs {
 	HashK hk;
 	uint32_t* ctr_k;             // counters of this k
 	Pool pool;
+	uint32_t mask_prefetch = 0;  // != 0: a group asks for its next unit's mask rows (prefetch.global.L2) before it works on the current one
 	cudaStream_t stream;
 };
 
